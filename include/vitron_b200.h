@@ -1,0 +1,173 @@
+/* vitron_b200 — C ABI of the B200 (sm_100a) kernels behind Vitron's multimodal forward path.
+ *
+ * The reference (SkyworkAI/Vitron) has no FFI of its own: its "operator interface" for this path
+ * is a set of torch nn.Module forwards.  Every entry point below replaces the
+ * arithmetic of the reference call cited next to it; the Python drop-in modules in vitron_b200/
+ * keep the reference's class names / signatures and call these through ctypes.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, device pointers unless stated; bf16 = 2-byte bfloat16 storage;
+ *   - no allocation, no implicit synchronisation, work is enqueued on `stream`;
+ *   - returns 0 (VB_OK) or a negative VB_ERR_* code, never throws;
+ *   - re-entrant provided distinct (stream, workspace) pairs.
+ */
+#ifndef VITRON_B200_H_
+#define VITRON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define VB_ACT_NONE 0
+#define VB_ACT_GELU 1       /* exact erf GELU  (nn.GELU(), CLIP "gelu")            */
+#define VB_ACT_QUICK_GELU 2 /* x*sigmoid(1.702x) (CLIP "quick_gelu")                */
+#define VB_ACT_RELU 3
+#define VB_ACT_SILU 4
+
+#define VB_GLU_NONE 0
+#define VB_GLU_SWIGLU 1 /* silu(a) * b   — LlamaMLP: a = gate_proj, b = up_proj     */
+#define VB_GLU_GEGLU 2  /* a * gelu(b)   — GEGLU: x, gate = proj(x).chunk(2)       */
+
+/* Fused GEMM / conv epilogue:  v = acc + bias[col] + rowbias[row / rowbias_rows][col];
+ *   GLU: columns are packed in blocks of 32 = [16 x a | 16 x b] -> 16 outputs; else v = act(v);
+ *   out = residual ? residual[row, col] + alpha * v : alpha * v;   stored as bf16 (or fp32). */
+typedef struct vb_epilogue {
+  const void* bias;     /* bf16 [N] or NULL */
+  const void* rowbias;  /* bf16 [groups, N] or NULL */
+  int64_t rowbias_rows; /* rows per rowbias group */
+  const void* residual; /* bf16 [M, ldr] or NULL (may alias `out`) */
+  int64_t ldr;
+  float alpha;
+  int32_t act;
+  int32_t glu;
+  int32_t out_fp32;
+} vb_epilogue;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* vb200_version(void);
+const char* vb200_last_error(void); /* text of the last CUDA error seen by this library */
+int vb200_device_ok(void);          /* 1 iff the current device is sm_100 (B200) */
+
+/* ---- GEMM: out[M,N] = epi(A[M,K] @ W[N,K]^T), tcgen05 + TMA (gemm_tcgen05.cu) --------------
+ * Replaces every nn.Linear on the path: HF LlamaAttention/LlamaMLP/lm_head (transformers 4.31,
+ * call sites vitron/model/language_model/llava_llama.py:91-102), CLIPAttention/CLIPMLP
+ * (languagebind/image/modeling_image.py:136-151), mm_projector (multimodal_projector/
+ * builder.py:33-51), region MLP (region_extractor/layer.py:17-20), UNet/SEEM/GLIGEN linears.
+ * M <= 64 runs swap-AB + split-K (weights stream through the 128-row MMA slot) and needs the
+ * workspace reported by vb200_gemm_bf16_workspace_size. lda/ldw/ldo in elements, multiples of 8. */
+size_t vb200_gemm_bf16_workspace_size(int64_t M, int64_t N, int64_t K);
+int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
+                    int64_t M, int64_t N, int64_t K, const vb_epilogue* epi, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- implicit-GEMM convolution on NHWC activations, im2col-free (gemm_tcgen05.cu) ----------
+ * X [nb,h,w,cin]; Wt [cout, kh*kw, ceil64(cin)] (zero padded); out [nb,ho,wo,cout].
+ * Replaces nn.Conv2d 3x3/1x1 (i2vgen util.py:651,677; Upsample/Downsample util.py:579-607,
+ * 732-756), Conv3d (3,1,1) as kh=3,kw=1 over [b, f, h*w, c] (util.py:1360-1375), SEEM FPN convs
+ * (transformer_encoder_fpn.py:54-107). stride in {1,2}. */
+int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int64_t nb, int64_t h,
+                         int64_t w, int64_t cin, int64_t cout, int kh, int kw, int stride,
+                         int pad_h, int pad_w, const vb_epilogue* epi, cudaStream_t stream);
+
+/* direct (SIMT) convolution for the two odd-shaped layers (cin < 8-aligned or tiny cout) */
+int vb200_conv_nhwc_direct(const void* X, const void* Wt, const void* bias, void* out, int64_t nb,
+                           int64_t h, int64_t w, int64_t cin, int64_t cout, int kh, int kw,
+                           int stride, int pad_h, int pad_w, cudaStream_t stream);
+
+/* ---- normalisation (norm.cu) ----------------------------------------------------------------
+ * rmsnorm: HF LlamaRMSNorm (fp32 statistics). layernorm: nn.LayerNorm. groupnorm: nn.GroupNorm
+ * over NHWC [n, spatial, c] (+ optional SiLU / ReLU), i2vgen util.py:640-655,1358-1375. */
+int vb200_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out, int64_t ldo,
+                  int64_t rows, int64_t d, float eps, cudaStream_t stream);
+int vb200_layernorm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out,
+                    int64_t ldo, int64_t rows, int64_t d, float eps, cudaStream_t stream);
+size_t vb200_groupnorm_workspace_size(int64_t n, int64_t groups);
+int vb200_groupnorm_nhwc(const void* x, const void* weight, const void* bias, void* out, int64_t n,
+                         int64_t spatial, int64_t c, int64_t groups, float eps, int act,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- attention (attention.cu) ---------------------------------------------------------------
+ * Flash-style softmax(QK^T*scale + mask)V with generic element strides (batch, seq, head); the
+ * head dim is contiguous. kv_len: int32 [B] valid keys per batch or NULL. causal: key j visible
+ * to query i iff j <= i + (kv_len - q_len). mask: uint8, non-zero = masked out, element strides
+ * (mb, mh, mq) with keys contiguous, or NULL. Rows with every key masked produce zeros.
+ * Replaces HF LlamaAttention / CLIPAttention eager bmm+softmax, xformers
+ * memory_efficient_attention (i2vgen util.py:253-258; GLIGEN attention.py:176,247) and SEEM
+ * multi_head_attention_forward (utils/attn.py:296-316). head_dim in {40,64,80,128,160}. */
+int vb200_attention(const void* q, const void* k, const void* v, void* out, int64_t B, int64_t H,
+                    int64_t Sq, int64_t Skv, int64_t head_dim, int64_t q_sb, int64_t q_ss,
+                    int64_t q_sh, int64_t k_sb, int64_t k_ss, int64_t k_sh, int64_t v_sb,
+                    int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh,
+                    float scale, int causal, const int32_t* kv_len, const uint8_t* mask,
+                    int64_t m_sb, int64_t m_sh, int64_t m_sq, cudaStream_t stream);
+/* tiny sequences (S <= 32, head_dim 64): temporal attention of the video tower
+ * (modeling_video.py:105-127) and of TemporalTransformer (util.py:1061-1066). */
+int vb200_attention_short(const void* q, const void* k, const void* v, void* out, int64_t nseq,
+                          int64_t H, int64_t S, int64_t head_dim, int64_t q_sb, int64_t q_ss,
+                          int64_t q_sh, int64_t k_sb, int64_t k_ss, int64_t k_sh, int64_t v_sb,
+                          int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh,
+                          float scale, cudaStream_t stream);
+
+/* ---- LLaMA decode path (llm.cu) -------------------------------------------------------------
+ * Paged KV cache per layer: k_pages / v_pages [num_pages, n_heads, page_size, head_dim] bf16,
+ * block_table int32 [B, max_pages]. (The reference grows KV with torch.cat.) */
+int vb200_rope_kv_append(void* qkv, int64_t ld_qkv, const int32_t* positions,
+                         const int32_t* batch_of_token, const int32_t* slot_of_token, void* k_pages,
+                         void* v_pages, const int32_t* block_table, int64_t max_pages,
+                         int64_t tokens, int64_t n_heads, int64_t head_dim, int64_t page_size,
+                         float rope_theta, cudaStream_t stream);
+size_t vb200_attn_decode_workspace_size(int64_t B, int64_t n_heads, int64_t head_dim,
+                                        int64_t max_splits);
+int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* k_pages, const void* v_pages,
+                            const int32_t* block_table, int64_t max_pages, const int32_t* kv_len,
+                            void* out, int64_t ld_o, int64_t B, int64_t n_heads, int64_t head_dim,
+                            int64_t page_size, int64_t max_kv_len, float scale, void* workspace,
+                            size_t workspace_bytes, cudaStream_t stream);
+/* inputs_embeds[b, s] = srcmap >= 0 ? embed[srcmap] : feats[-srcmap-1] : the device half of
+ * prepare_inputs_labels_for_multimodal (vitron/model/llava_arch.py:478-521); pad rows (srcmap ==
+ * INT32_MIN) are zero-filled. */
+int vb200_splice_multimodal(const void* embed, int64_t vocab, const void* feats,
+                            int64_t n_feat_rows, const int32_t* srcmap, void* out, int64_t rows,
+                            int64_t d, cudaStream_t stream);
+int vb200_argmax_rows(const void* logits, int is_fp32, int64_t ld, int64_t rows, int64_t n,
+                      int64_t* out_idx, cudaStream_t stream);
+
+/* ---- vision / diffusion glue (vision.cu) ----------------------------------------------------
+ * patchify: NCHW pixels -> [nb*gh*gw, kpad] rows ordered (c, py, px) for the patch-embed GEMM
+ * (HF CLIPVisionEmbeddings Conv2d(3,1024,14,14,bias=False)); vit_embed adds cls + position and
+ * applies pre_layrnorm (modeling_image.py:651-655). */
+int vb200_patchify(const void* pixels, int in_is_fp32, void* out, int64_t nb, int64_t c, int64_t h,
+                   int64_t w, int64_t patch, int64_t kpad, cudaStream_t stream);
+int vb200_vit_embed_ln(const void* patch_out, const void* cls, const void* pos, const void* ln_w,
+                       const void* ln_b, void* out, int64_t nb, int64_t npatch, int64_t d,
+                       float eps, cudaStream_t stream);
+/* nearest x2 upsample NHWC (util.py:579-607) */
+int vb200_upsample2x_nhwc(const void* x, void* out, int64_t nb, int64_t h, int64_t w, int64_t c,
+                          cudaStream_t stream);
+/* out = a + b (bf16, n elements), with optional broadcast period for b */
+int vb200_add_bf16(const void* a, const void* b, void* out, int64_t n, int64_t b_period,
+                   cudaStream_t stream);
+/* classifier-free guidance combine u + s (y - u) in fp32 (diffusion_ddim.py:156-158) */
+int vb200_cfg_combine(const void* y, const void* u, void* out, float scale, int64_t n,
+                      cudaStream_t stream);
+/* region mask pooling: feats [B, g*g, C] bf16, boxes fp32 [B,4] on a image_size canvas ->
+ * pooled [B, C] (region_extractor/layer.py:27-43,77-112 incl. the x-indexes-rows quirk) */
+int vb200_region_mask_pool(const void* feats, const float* boxes, void* out, int64_t B,
+                           int64_t grid, int64_t c, int64_t image_size, cudaStream_t stream);
+/* SEEM mask head: mask logits [Q, H, W] fp32 -> next-layer bool attention mask [Q, h2*w2]
+ * = bilinear(align_corners=False) resize, sigmoid < 0.5; rows that end up fully masked are
+ * cleared (seem.py:569-574, attention_data_struct.py:187). */
+int vb200_seem_attn_mask(const float* mask_logits, uint8_t* out_mask, int64_t Q, int64_t H,
+                         int64_t W, int64_t h2, int64_t w2, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITRON_B200_H_ */

@@ -1,0 +1,723 @@
+// vitron_b200 — bf16 GEMM / implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   D[M, N] = epilogue( A[M, K] · B[N, K]^T )        (both operands K-major, fp32 accumulate)
+//
+// One persistent, warp-specialised kernel:
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, accumulators in TMEM)
+//   warps 2..5  epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+// TMEM holds two accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// The A operand comes either from a plain 2-D row-major matrix or, for convolutions, straight
+// from the NHWC activation tensor through a 4-D tensor map: every (tap, channel-chunk) k-step is
+// one TMA box {64 ch, TW, TH, TN} fetched at the tap-shifted coordinate, out-of-bounds pixels are
+// zero-filled by the TMA unit (= zero padding), so no im2col buffer ever exists.
+//
+// Covers (reference file:line in DESIGN.md): LLaMA q/k/v/o/gate/up/down/lm_head, CLIP ViT
+// q/k/v/out/fc1/fc2, mm_projector, region MLP, every Linear / Conv2d(3x3,1x1) / Conv3d(3,1,1) of
+// UNetSD_I2VGen, SEEM FPN convs + mask einsum, GLIGEN fuser linears.
+#include "common.cuh"
+#include "vitron_b200.h"
+
+namespace vb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct GemmParams {
+  int M, N;           // logical output extent (rows of A-space, rows of B)
+  int num_k_blocks;   // k-steps of BLOCK_K (conv: taps * cin_chunks)
+  int splits;         // split-K factor (>=1)
+  int m_blocks, n_blocks;
+  // ---- A addressing
+  int a_mode;         // 0: 2-D matrix, 1: NHWC conv
+  int cin_chunks;     // conv: BLOCK_K chunks per tap
+  int kw;             // conv: kernel width (tap -> dy = tap / kw, dx = tap % kw)
+  int stride, pad_h, pad_w;
+  int tw, th, tn;     // conv: output-pixel tile (tw*th*tn <= 128)
+  int wo, ho, nb;     // conv: output width / height / images
+  int tiles_w, tiles_h;
+  uint32_t a_box_bytes;
+  // ---- epilogue
+  void* out;          // bf16 or fp32 [rows, ldo]
+  long long ldo;
+  const bf16* bias;      // [N] or null
+  const bf16* rowbias;   // [groups, N] or null; group = out_row / rowbias_rows
+  int rowbias_rows;
+  const bf16* residual;  // [rows, ldr] or null; out = residual + alpha * v
+  long long ldr;
+  float alpha;
+  int act;            // VB_ACT_*
+  int glu;            // VB_GLU_*
+  int out_fp32;
+  int swap;           // accumulator rows are output columns (decode / tiny-M path) -> workspace
+  float* ws;          // split-K / swap workspace [splits, rows_c, cols_c] fp32
+  long long ws_split_stride;
+  long long ws_ld;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case VB_ACT_GELU: return gelu_erf(x);
+    case VB_ACT_QUICK_GELU: return quick_gelu(x);
+    case VB_ACT_RELU: return fmaxf(x, 0.f);
+    case VB_ACT_SILU: return silu(x);
+    default: return x;
+  }
+}
+
+struct TileCoord {
+  int m_blk, n_blk, split;
+};
+
+__device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int unit) {
+  TileCoord t;
+  int tile = unit / p.splits;
+  t.split = unit - tile * p.splits;
+  // grouped rasterisation: 16 m-blocks wide so a wave of CTAs re-uses A and B tiles through L2
+  const int GROUP_M = 16;
+  int per_group = GROUP_M * p.n_blocks;
+  int group = tile / per_group;
+  int first_m = group * GROUP_M;
+  int gsize = min(p.m_blocks - first_m, GROUP_M);
+  int in_group = tile - group * per_group;
+  t.m_blk = first_m + in_group % gsize;
+  t.n_blk = in_group / gsize;
+  return t;
+}
+
+__device__ __forceinline__ void split_range(const GemmParams& p, int split, int& k0, int& k1) {
+  int base = p.num_k_blocks / p.splits, rem = p.num_k_blocks % p.splits;
+  k0 = split * base + min(split, rem);
+  k1 = k0 + base + (split < rem ? 1 : 0);
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int ACC_STAGES = 2;
+  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32)    ? 32
+                                 : (ACC_STAGES * BLOCK_N <= 64)  ? 64
+                                 : (ACC_STAGES * BLOCK_N <= 128) ? 128
+                                 : (ACC_STAGES * BLOCK_N <= 256) ? 256
+                                                                 : 512;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_units = p.m_blocks * p.n_blocks * p.splits;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        TileCoord t = decode_work(p, unit);
+        int k0, k1;
+        split_range(p, t.split, k0, k1);
+        int cw = 0, ch = 0, cn = 0;
+        if (p.a_mode == 1) {
+          int tiw = t.m_blk % p.tiles_w;
+          int rest = t.m_blk / p.tiles_w;
+          int tih = rest % p.tiles_h;
+          int tin = rest / p.tiles_h;
+          cw = tiw * p.tw * p.stride - p.pad_w;
+          ch = tih * p.th * p.stride - p.pad_h;
+          cn = tin * p.tn;
+        }
+        for (int kb = k0; kb < k1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes + B_BYTES);
+          if (p.a_mode == 0) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, t.m_blk * BLOCK_M);
+          } else {
+            int tap = kb / p.cin_chunks;
+            int cc = kb - tap * p.cin_chunks;
+            int dy = tap / p.kw, dx = tap - dy * p.kw;
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], cc * BLOCK_K, cw + dx, ch + dy, cn);
+          }
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, t.n_blk * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      TileCoord t = decode_work(p, unit);
+      int k0, k1;
+      split_range(p, t.split, k0, k1);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = k0; kb < k1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const uint64_t da = umma_desc_kmajor_sw128(sa);
+          const uint64_t db = umma_desc_kmajor_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in 16-byte units
+            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (kb == k1 - 1) tc_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (k1 <= k0 && lane == 0) tc_commit(&tmem_full[acc]);  // degenerate (never for K>0)
+      __syncwarp();
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================================================== epilogue warps
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      TileCoord t = decode_work(p, unit);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int r = quad * 32 + lane;  // accumulator row owned by this thread
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
+
+      // ---- output row of this accumulator row
+      long long orow = -1;
+      if (p.a_mode == 0) {
+        long long g = static_cast<long long>(t.m_blk) * BLOCK_M + r;
+        if (g < p.M) orow = g;
+      } else {
+        int tiw = t.m_blk % p.tiles_w;
+        int rest = t.m_blk / p.tiles_w;
+        int tih = rest % p.tiles_h;
+        int tin = rest / p.tiles_h;
+        int tx = r % p.tw;
+        int r2 = r / p.tw;
+        int ty = r2 % p.th;
+        int tz = r2 / p.th;
+        int x = tiw * p.tw + tx, y = tih * p.th + ty, n = tin * p.tn + tz;
+        if (tz < p.tn && x < p.wo && y < p.ho && n < p.nb)
+          orow = (static_cast<long long>(n) * p.ho + y) * p.wo + x;
+      }
+      const int col0 = t.n_blk * BLOCK_N;
+
+      if (p.ws != nullptr) {
+        // -------- raw fp32 partials to the workspace (split-K and/or swap-AB)
+        float* wsp = p.ws + static_cast<long long>(t.split) * p.ws_split_stride;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + c, v);
+          tmem_ld_wait();
+          if (orow >= 0) {
+            if (p.swap) {
+              // C[token = col, feature = orow]; a warp writes 32 consecutive features per token
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                int tok = col0 + c + j;
+                if (tok < p.N) wsp[static_cast<long long>(tok) * p.ws_ld + orow] = __uint_as_float(v[j]);
+              }
+            } else {
+              float* dst = wsp + orow * p.ws_ld + col0 + c;
+              if (col0 + c + 16 <= p.N && (p.ws_ld & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(dst + j) =
+                      make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (col0 + c + j < p.N) dst[j] = __uint_as_float(v[j]);
+              }
+            }
+          }
+        }
+      } else {
+        // -------- fused epilogue straight to the output tensor
+        const bf16* rb = nullptr;
+        if (p.rowbias != nullptr && orow >= 0)
+          rb = p.rowbias + (orow / p.rowbias_rows) * static_cast<long long>(p.N);
+        constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += CH) {
+          float f[CH];
+          if constexpr (CH == 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          } else {
+            uint32_t v[16];
+            tmem_ld_32x16(taddr + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          }
+          if (orow < 0) continue;
+          const int gc = col0 + c;  // first accumulator column of this chunk
+          if (gc >= p.N) continue;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (gc + j < p.N) f[j] += __bfloat162float(p.bias[gc + j]);
+          }
+          if (rb != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (gc + j < p.N) f[j] += __bfloat162float(rb[gc + j]);
+          }
+          int nout = CH, oc = gc;
+          if (p.glu != VB_GLU_NONE) {
+            // packed GLU: accumulator columns come in blocks of 32 = [16 x "a" | 16 x "b"]
+            if constexpr (CH == 32) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a = f[j], b = f[j + 16];
+                f[j] = (p.glu == VB_GLU_SWIGLU) ? silu(a) * b : a * gelu_erf(b);
+              }
+            }
+            nout = 16;
+            oc = gc >> 1;
+          } else if (p.act != VB_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) f[j] = apply_act(f[j], p.act);
+          }
+          const int n_out_total = (p.glu != VB_GLU_NONE) ? (p.N >> 1) : p.N;
+          if (p.residual != nullptr) {
+            const bf16* rp = p.residual + orow * p.ldr + oc;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (j < nout && oc + j < n_out_total) f[j] = __bfloat162float(rp[j]) + p.alpha * f[j];
+          } else if (p.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) f[j] *= p.alpha;
+          }
+          if (p.out_fp32) {
+            float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldo + oc;
+            if (oc + nout <= n_out_total && (p.ldo & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4)
+                if (j < nout)
+                  *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (j < nout && oc + j < n_out_total) dst[j] = f[j];
+            }
+          } else {
+            bf16* dst = reinterpret_cast<bf16*>(p.out) + orow * p.ldo + oc;
+            if (oc + nout <= n_out_total && (p.ldo & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 8)
+                if (j < nout)
+                  *reinterpret_cast<uint4*>(dst + j) =
+                      make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                 pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (j < nout && oc + j < n_out_total) dst[j] = __float2bfloat16(f[j]);
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ split-K / swap reduce
+// out[m, n'] = epilogue( sum_s ws[s, m, n] ), same epilogue semantics as the fused path.
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits,
+                                     long long split_stride, long long ws_ld, int rows, int ncols,
+                                     void* out, long long ldo, const bf16* __restrict__ bias,
+                                     const bf16* __restrict__ rowbias, int rowbias_rows,
+                                     const bf16* __restrict__ residual, long long ldr, float alpha,
+                                     int act, int glu, int out_fp32) {
+  const int n_out_total = glu != VB_GLU_NONE ? ncols / 2 : ncols;
+  const int groups = (n_out_total + 7) / 8;
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * groups) return;
+  const int row = static_cast<int>(idx / groups);
+  const int oc = static_cast<int>(idx % groups) * 8;
+  int ca = oc, cb = -1;
+  if (glu != VB_GLU_NONE) {
+    ca = (oc / 16) * 32 + (oc % 16);
+    cb = ca + 16;
+  }
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* src = ws + s * split_stride + row * ws_ld;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (oc + j < n_out_total) {
+        a[j] += src[ca + j];
+        if (cb >= 0) b[j] += src[cb + j];
+      }
+    }
+  }
+  const bf16* rb = rowbias ? rowbias + (row / rowbias_rows) * static_cast<long long>(ncols) : nullptr;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (oc + j >= n_out_total) continue;
+    float va = a[j], vb_ = b[j];
+    if (bias) {
+      va += __bfloat162float(bias[ca + j]);
+      if (cb >= 0) vb_ += __bfloat162float(bias[cb + j]);
+    }
+    if (rb) {
+      va += __bfloat162float(rb[ca + j]);
+      if (cb >= 0) vb_ += __bfloat162float(rb[cb + j]);
+    }
+    float v;
+    if (glu == VB_GLU_SWIGLU) v = silu(va) * vb_;
+    else if (glu == VB_GLU_GEGLU) v = va * gelu_erf(vb_);
+    else v = apply_act(va, act);
+    if (residual) v = __bfloat162float(residual[row * ldr + oc + j]) + alpha * v;
+    else v *= alpha;
+    if (out_fp32) reinterpret_cast<float*>(out)[row * ldo + oc + j] = v;
+    else reinterpret_cast<bf16*>(out)[row * ldo + oc + j] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
+                     const uint32_t* estr) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return VB_ERR_DRIVER;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims,
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VB_OK : VB_ERR_DRIVER;
+}
+
+template <int BN, int STAGES>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                      cudaStream_t stream) {
+  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 1024 + 256;
+  static_assert(smem <= SMEM_LIMIT, "smem budget");
+  static bool attr_set = false;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
+    attr_set = true;
+  }
+  int units = p.m_blocks * p.n_blocks * p.splits;
+  int grid = units < vb_num_sms() ? units : vb_num_sms();
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+static int launch_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_cfg<256, 4>(ta, tb, p, stream);
+    case 128: return launch_cfg<128, 6>(ta, tb, p, stream);
+    case 64: return launch_cfg<64, 8>(ta, tb, p, stream);
+    case 32: return launch_cfg<32, 10>(ta, tb, p, stream);
+    case 16: return launch_cfg<16, 10>(ta, tb, p, stream);
+    default: return VB_ERR_ARG;
+  }
+}
+
+static int pick_block_n(long long M, long long N, int glu) {
+  // widest tile wins unless it leaves most SMs idle: score = tile efficiency x wave utilisation
+  (void)glu;
+  const int sms = vb_num_sms();
+  const long long mb = (M + BLOCK_M - 1) / BLOCK_M;
+  const int cands[4] = {256, 128, 64, 32};
+  const float eff[4] = {1.0f, 0.92f, 0.62f, 0.36f};
+  int best = 32;
+  float best_score = -1.f;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const long long nbk = (N + bn - 1) / bn;
+    const long long tiles = mb * nbk;
+    const long long waves = (tiles + sms - 1) / sms;
+    const float util = static_cast<float>(tiles) / static_cast<float>(waves * sms);
+    const float fill = static_cast<float>(N) / static_cast<float>(nbk * bn);  // padded columns
+    const float score = eff[i] * util * fill;
+    if (score > best_score) { best_score = score; best = bn; }
+  }
+  return best;
+}
+
+static int swap_splits(long long M, long long N, long long K) {
+  (void)M;
+  const int m_blocks = static_cast<int>((N + BLOCK_M - 1) / BLOCK_M);
+  const int kblocks = static_cast<int>((K + BLOCK_K - 1) / BLOCK_K);
+  int splits = (2 * vb_num_sms() + m_blocks - 1) / m_blocks;  // ~2 waves of CTAs stream W
+  if (splits > 16) splits = 16;
+  if (splits > kblocks) splits = kblocks;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+static int run_reduce(const GemmParams& p, int rows, int ncols, void* out, long long ldo,
+                      const vb_epilogue* e, cudaStream_t stream) {
+  int n_out = e->glu != VB_GLU_NONE ? ncols / 2 : ncols;
+  long long work = static_cast<long long>(rows) * ((n_out + 7) / 8);
+  int threads = 256;
+  long long blocks = (work + threads - 1) / threads;
+  splitk_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+      p.ws, p.splits, p.ws_split_stride, p.ws_ld, rows, ncols, out, ldo,
+      reinterpret_cast<const bf16*>(e->bias), reinterpret_cast<const bf16*>(e->rowbias),
+      e->rowbias_rows > 0 ? e->rowbias_rows : 1, reinterpret_cast<const bf16*>(e->residual),
+      e->ldr, e->alpha, e->act, e->glu, e->out_fp32);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+static int validate_epi(const vb_epilogue* e, long long N) {
+  if (e->glu != VB_GLU_NONE && (N % 32) != 0) return VB_ERR_ARG;
+  if (e->act < VB_ACT_NONE || e->act > VB_ACT_SILU) return VB_ERR_ARG;
+  if (e->glu < VB_GLU_NONE || e->glu > VB_GLU_GEGLU) return VB_ERR_ARG;
+  return VB_OK;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" size_t vb200_gemm_bf16_workspace_size(int64_t M, int64_t N, int64_t K) {
+  if (M <= 0 || N <= 0 || K <= 0 || M > 64) return 0;  // only the swap-AB (tiny-M) path needs one
+  return static_cast<size_t>(swap_splits(M, N, K)) * static_cast<size_t>(M) *
+         static_cast<size_t>(N) * sizeof(float);
+}
+
+extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
+                               int64_t ldo, int64_t M, int64_t N, int64_t K,
+                               const vb_epilogue* epi, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream) {
+  VB_CHECK_ARG(A && W && out && epi);
+  VB_CHECK_ARG(M > 0 && N > 0 && K > 0);
+  VB_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && lda >= K && ldw >= K);
+  VB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  if (int r = validate_epi(epi, N)) return r;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_k_blocks = static_cast<int>((K + BLOCK_K - 1) / BLOCK_K);
+  p.a_mode = 0;
+  p.a_box_bytes = BLOCK_M * BLOCK_K * 2;
+  p.bias = reinterpret_cast<const bf16*>(epi->bias);
+  p.rowbias = reinterpret_cast<const bf16*>(epi->rowbias);
+  p.rowbias_rows = epi->rowbias_rows > 0 ? epi->rowbias_rows : 1;
+  p.residual = reinterpret_cast<const bf16*>(epi->residual);
+  p.ldr = epi->ldr;
+  p.alpha = epi->alpha;
+  p.act = epi->act;
+  p.glu = epi->glu;
+  p.out_fp32 = epi->out_fp32;
+  p.out = out;
+  p.ldo = ldo;
+
+  CUtensorMap ta, tb;
+  const uint32_t estr2[2] = {1, 1};
+  const bool swap = (M <= 64);  // tiny-M (decode, region MLP): weights take the 128-row MMA slot
+  if (swap) {
+    // kernel-M = N (weight rows), kernel-N = M (tokens); partials -> workspace -> reduce kernel
+    const int bn = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+    p.M = static_cast<int>(N);
+    p.N = static_cast<int>(M);
+    p.m_blocks = static_cast<int>((N + BLOCK_M - 1) / BLOCK_M);
+    p.n_blocks = 1;
+    const int splits = swap_splits(M, N, K);
+    p.splits = splits;
+    size_t need = static_cast<size_t>(splits) * M * N * sizeof(float);
+    if (workspace == nullptr || workspace_bytes < need) return VB_ERR_WORKSPACE;
+    p.swap = 1;
+    p.ws = reinterpret_cast<float*>(workspace);
+    p.ws_ld = N;
+    p.ws_split_stride = M * N;
+    uint64_t dA[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t sA[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t bA[2] = {BLOCK_K, BLOCK_M};
+    if (int r = make_tmap(&ta, W, 2, dA, sA, bA, estr2)) return r;
+    uint64_t dB[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t sB[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
+    if (int r = make_tmap(&tb, A, 2, dB, sB, bB, estr2)) return r;
+    if (int r = launch_gemm(bn, ta, tb, p, stream)) return r;
+    return run_reduce(p, static_cast<int>(M), static_cast<int>(N), out, ldo, epi, stream);
+  }
+
+  int bn = pick_block_n(M, N, epi->glu);
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.m_blocks = static_cast<int>((M + BLOCK_M - 1) / BLOCK_M);
+  p.n_blocks = static_cast<int>((N + bn - 1) / bn);
+  p.splits = 1;
+  uint64_t dA[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+  uint64_t sA[1] = {static_cast<uint64_t>(lda) * 2};
+  uint32_t bA[2] = {BLOCK_K, BLOCK_M};
+  if (int r = make_tmap(&ta, A, 2, dA, sA, bA, estr2)) return r;
+  uint64_t dB[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+  uint64_t sB[1] = {static_cast<uint64_t>(ldw) * 2};
+  uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
+  if (int r = make_tmap(&tb, W, 2, dB, sB, bB, estr2)) return r;
+  return launch_gemm(bn, ta, tb, p, stream);
+}
+
+extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int64_t nb,
+                                    int64_t h, int64_t w, int64_t cin, int64_t cout, int kh,
+                                    int kw, int stride, int pad_h, int pad_w,
+                                    const vb_epilogue* epi, cudaStream_t stream) {
+  // X [nb, h, w, cin] bf16 NHWC; Wt [cout, kh*kw, cin_pad] bf16 with cin_pad = ceil64(cin)
+  // (zero padded); out [nb, ho, wo, cout(/2 if GLU)].
+  VB_CHECK_ARG(X && Wt && out && epi);
+  VB_CHECK_ARG(nb > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && kh > 0 && kw > 0);
+  VB_CHECK_ARG(stride == 1 || stride == 2);
+  VB_CHECK_ARG((cin % 8) == 0);
+  if (int r = validate_epi(epi, cout)) return r;
+  const int ho = static_cast<int>((h + 2 * pad_h - kh) / stride + 1);
+  const int wo = static_cast<int>((w + 2 * pad_w - kw) / stride + 1);
+  VB_CHECK_ARG(ho > 0 && wo > 0);
+  const int cin_chunks = static_cast<int>((cin + BLOCK_K - 1) / BLOCK_K);
+  const int cin_pad = cin_chunks * BLOCK_K;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int tw = wo < 128 ? wo : 128;
+  // keep boxes rectangular: tw must not exceed 128/stride-independent limit of 256 elements
+  int th = 128 / tw;
+  if (th > ho) th = ho;
+  if (th < 1) th = 1;
+  int tn = 128 / (tw * th);
+  if (tn > nb) tn = static_cast<int>(nb);
+  if (tn < 1) tn = 1;
+  p.a_mode = 1;
+  p.cin_chunks = cin_chunks;
+  p.kw = kw;
+  p.stride = stride;
+  p.pad_h = pad_h;
+  p.pad_w = pad_w;
+  p.tw = tw; p.th = th; p.tn = tn;
+  p.wo = wo; p.ho = ho; p.nb = static_cast<int>(nb);
+  p.tiles_w = (wo + tw - 1) / tw;
+  p.tiles_h = (ho + th - 1) / th;
+  int tiles_n = static_cast<int>((nb + tn - 1) / tn);
+  p.m_blocks = p.tiles_w * p.tiles_h * tiles_n;
+  p.M = static_cast<int>(nb) * ho * wo;
+  p.N = static_cast<int>(cout);
+  p.num_k_blocks = kh * kw * cin_chunks;
+  p.splits = 1;
+  p.a_box_bytes = static_cast<uint32_t>(tw * th * tn) * BLOCK_K * 2;
+  p.bias = reinterpret_cast<const bf16*>(epi->bias);
+  p.rowbias = reinterpret_cast<const bf16*>(epi->rowbias);
+  p.rowbias_rows = epi->rowbias_rows > 0 ? epi->rowbias_rows : 1;
+  p.residual = reinterpret_cast<const bf16*>(epi->residual);
+  p.ldr = epi->ldr;
+  p.alpha = epi->alpha;
+  p.act = epi->act;
+  p.glu = epi->glu;
+  p.out_fp32 = epi->out_fp32;
+  p.out = out;
+  p.ldo = epi->glu != VB_GLU_NONE ? cout / 2 : cout;
+
+  int bn = pick_block_n(static_cast<long long>(p.m_blocks) * BLOCK_M, cout, epi->glu);
+  p.n_blocks = static_cast<int>((cout + bn - 1) / bn);
+
+  CUtensorMap ta, tb;
+  uint64_t dA[4] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(w), static_cast<uint64_t>(h),
+                    static_cast<uint64_t>(nb)};
+  uint64_t sA[3] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(cin) * w * 2,
+                    static_cast<uint64_t>(cin) * w * h * 2};
+  // box extents are in traversed global elements: (tw-1)*stride+1 columns yield tw samples
+  uint32_t bA[4] = {BLOCK_K, static_cast<uint32_t>((tw - 1) * stride + 1),
+                    static_cast<uint32_t>((th - 1) * stride + 1), static_cast<uint32_t>(tn)};
+  uint32_t eA[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
+  if (int r = make_tmap(&ta, X, 4, dA, sA, bA, eA)) return r;
+  uint64_t dB[2] = {static_cast<uint64_t>(kh) * kw * cin_pad, static_cast<uint64_t>(cout)};
+  uint64_t sB[1] = {static_cast<uint64_t>(kh) * kw * cin_pad * 2};
+  uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
+  const uint32_t estr2[2] = {1, 1};
+  if (int r = make_tmap(&tb, Wt, 2, dB, sB, bB, estr2)) return r;
+  return launch_gemm(bn, ta, tb, p, stream);
+}

@@ -1,0 +1,344 @@
+// vitron_b200 — LLaMA (Vicuna-7B) token-path kernels: RoPE + paged-KV append, paged decode
+// attention (split-KV), multimodal embedding splice, greedy argmax. All HBM-bound.
+//
+// Reference arithmetic: HF transformers 4.31 LlamaAttention (rotate_half RoPE, fp32 softmax;
+// restated in vitron/train/llama_flash_attn_monkey_patch.py:30-66), KV grown by torch.cat there —
+// here a paged cache [num_pages, n_heads, page_size, head_dim]; splice =
+// LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal (vitron/model/llava_arch.py:478-521).
+#include "common.cuh"
+#include "vitron_b200.h"
+#include <limits.h>
+
+namespace vb {
+
+// ------------------------------------------------------------------ RoPE + KV append
+// qkv row = [q(H*hd) | k(H*hd) | v(H*hd)]; one CTA per token, one thread per (head, 8-dim chunk).
+__global__ void rope_kv_append_kernel(bf16* __restrict__ qkv, long long ld, const int32_t* __restrict__ positions,
+                                      const int32_t* __restrict__ batch_of_token,
+                                      const int32_t* __restrict__ slot_of_token, bf16* __restrict__ k_pages,
+                                      bf16* __restrict__ v_pages, const int32_t* __restrict__ block_table,
+                                      int max_pages, int H, int hd, int page_size, float log2_theta) {
+  const long long tok = blockIdx.x;
+  const int half = hd / 2;
+  const int chunks = half / 8;  // 16-byte chunks per half head
+  const int pos = positions[tok];
+  const int slot = slot_of_token ? slot_of_token[tok] : pos;
+  const int b = batch_of_token ? batch_of_token[tok] : 0;
+  bf16* row = qkv + tok * ld;
+  long long cache_off = -1;
+  if (slot >= 0 && k_pages != nullptr) {
+    const int page = block_table[static_cast<long long>(b) * max_pages + slot / page_size];
+    cache_off = (static_cast<long long>(page) * H) * page_size * hd + static_cast<long long>(slot % page_size) * hd;
+  }
+  for (int item = threadIdx.x; item < H * chunks; item += blockDim.x) {
+    const int h = item / chunks, c = (item % chunks) * 8;
+    float cs[8], sn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float inv_freq = exp2f(-(2.0f * (c + j) / hd) * log2_theta);
+      sincosf(static_cast<float>(pos) * inv_freq, &sn[j], &cs[j]);
+    }
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {  // 0: q, 1: k
+      bf16* base = row + static_cast<long long>(which) * H * hd + h * hd;
+      uint4 lo = *reinterpret_cast<const uint4*>(base + c);
+      uint4 hi = *reinterpret_cast<const uint4*>(base + half + c);
+      const uint32_t l4[4] = {lo.x, lo.y, lo.z, lo.w}, h4[4] = {hi.x, hi.y, hi.z, hi.w};
+      uint32_t ol[4], oh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 a = unpack_bf16(l4[j]), bb = unpack_bf16(h4[j]);
+        // rotate_half: out_lo = x_lo*cos - x_hi*sin ; out_hi = x_hi*cos + x_lo*sin
+        ol[j] = pack_bf16(a.x * cs[2 * j] - bb.x * sn[2 * j], a.y * cs[2 * j + 1] - bb.y * sn[2 * j + 1]);
+        oh[j] = pack_bf16(bb.x * cs[2 * j] + a.x * sn[2 * j], bb.y * cs[2 * j + 1] + a.y * sn[2 * j + 1]);
+      }
+      const uint4 vlo = make_uint4(ol[0], ol[1], ol[2], ol[3]), vhi = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+      *reinterpret_cast<uint4*>(base + c) = vlo;
+      *reinterpret_cast<uint4*>(base + half + c) = vhi;
+      if (which == 1 && cache_off >= 0) {
+        bf16* kc = k_pages + cache_off + static_cast<long long>(h) * page_size * hd;
+        *reinterpret_cast<uint4*>(kc + c) = vlo;
+        *reinterpret_cast<uint4*>(kc + half + c) = vhi;
+      }
+    }
+    if (cache_off >= 0) {
+      const bf16* vsrc = row + 2LL * H * hd + h * hd;
+      bf16* vc = v_pages + cache_off + static_cast<long long>(h) * page_size * hd;
+      *reinterpret_cast<uint4*>(vc + c) = *reinterpret_cast<const uint4*>(vsrc + c);
+      *reinterpret_cast<uint4*>(vc + half + c) = *reinterpret_cast<const uint4*>(vsrc + half + c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ paged decode attention
+// grid (splits, H, B); 4 warps; 8 lanes per key (16 dims each, head_dim 128), 2 keys in flight
+// per lane group; every lane group runs its own online softmax, merged through smem at the end.
+constexpr int DEC_THREADS = 128;
+constexpr int DEC_CHUNK = 256;  // keys per split
+
+__global__ void __launch_bounds__(DEC_THREADS)
+attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, const bf16* __restrict__ k_pages,
+                   const bf16* __restrict__ v_pages, const int32_t* __restrict__ block_table, int max_pages,
+                   const int32_t* __restrict__ kv_len, int H, int page_size, float scale, int splits,
+                   float* __restrict__ ws_ml, float* __restrict__ ws_o, bf16* __restrict__ out, long long ld_o) {
+  constexpr int HD = 128;
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 3, sub = lane & 7;
+  const int len = kv_len[b];
+  const int per = (len + splits - 1) / splits;
+  const int c0 = split * per, c1 = min(len, c0 + per);
+
+  float qv[16];
+  {
+    const bf16* qp = q + static_cast<long long>(b) * ld_q + h * HD + sub * 16;
+    uint4 u0 = *reinterpret_cast<const uint4*>(qp), u1 = *reinterpret_cast<const uint4*>(qp + 8);
+    const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float2 f = unpack_bf16(uu[j]); qv[2 * j] = f.x * scale; qv[2 * j + 1] = f.y * scale; }
+  }
+  float m = -INFINITY, l = 0.f, o[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = 0.f;
+  const int32_t* bt = block_table + static_cast<long long>(b) * max_pages;
+  const long long head_off = static_cast<long long>(h) * page_size * HD + sub * 16;
+  const long long page_stride = static_cast<long long>(H) * page_size * HD;
+
+  // 16 lane groups per CTA, each takes keys c0 + gid, + 16, ... two at a time
+  const int gid = warp * 4 + grp;
+  for (int tb = c0; tb < c1; tb += 32) {  // warp-uniform trip count (shuffles below use the full mask)
+    const int t0 = tb + gid, t1 = t0 + 16;
+    const bool has0 = t0 < c1, has1 = t1 < c1;
+    const int u0 = has0 ? t0 : c0, u1 = has1 ? t1 : c0;
+    const long long off0 = static_cast<long long>(bt[u0 / page_size]) * page_stride + static_cast<long long>(u0 % page_size) * HD + head_off;
+    const long long off1 = static_cast<long long>(bt[u1 / page_size]) * page_stride + static_cast<long long>(u1 % page_size) * HD + head_off;
+    uint4 ka0 = *reinterpret_cast<const uint4*>(k_pages + off0), ka1 = *reinterpret_cast<const uint4*>(k_pages + off0 + 8);
+    uint4 kb0 = *reinterpret_cast<const uint4*>(k_pages + off1), kb1 = *reinterpret_cast<const uint4*>(k_pages + off1 + 8);
+    uint4 va0 = *reinterpret_cast<const uint4*>(v_pages + off0), va1 = *reinterpret_cast<const uint4*>(v_pages + off0 + 8);
+    uint4 vb0 = *reinterpret_cast<const uint4*>(v_pages + off1), vb1 = *reinterpret_cast<const uint4*>(v_pages + off1 + 8);
+    const uint32_t ka[8] = {ka0.x, ka0.y, ka0.z, ka0.w, ka1.x, ka1.y, ka1.z, ka1.w};
+    const uint32_t kb[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 f0 = unpack_bf16(ka[j]), f1 = unpack_bf16(kb[j]);
+      s0 += qv[2 * j] * f0.x + qv[2 * j + 1] * f0.y;
+      s1 += qv[2 * j] * f1.x + qv[2 * j + 1] * f1.y;
+    }
+#pragma unroll
+    for (int sh = 1; sh < 8; sh <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, sh);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
+    }
+    if (!has0) s0 = -INFINITY;
+    if (!has1) s1 = -INFINITY;
+    const float mn = fmaxf(m, fmaxf(s0, s1));
+    const float msafe = (mn == -INFINITY) ? 0.f : mn;
+    const float corr = __expf(m - msafe);  // m = -inf on first use -> 0
+    const float p0 = __expf(s0 - msafe), p1 = __expf(s1 - msafe);
+    l = l * corr + p0 + p1;
+    m = mn;
+    const uint32_t va[8] = {va0.x, va0.y, va0.z, va0.w, va1.x, va1.y, va1.z, va1.w};
+    const uint32_t vb_[8] = {vb0.x, vb0.y, vb0.z, vb0.w, vb1.x, vb1.y, vb1.z, vb1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 f0 = unpack_bf16(va[j]), f1 = unpack_bf16(vb_[j]);
+      o[2 * j] = o[2 * j] * corr + p0 * f0.x + p1 * f1.x;
+      o[2 * j + 1] = o[2 * j + 1] * corr + p0 * f0.y + p1 * f1.y;
+    }
+  }
+
+  // ---- merge the 16 lane groups
+  __shared__ float sm_m[16], sm_l[16];
+  __shared__ float sm_o[16][HD + 4];
+  if (sub == 0) { sm_m[gid] = m; sm_l[gid] = l; }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) sm_o[gid][sub * 16 + j] = o[j];
+  __syncthreads();
+  const int d = threadIdx.x;  // one thread per output dim
+  float M = -INFINITY;
+#pragma unroll
+  for (int g = 0; g < 16; ++g) M = fmaxf(M, sm_m[g]);
+  float L = 0.f, O = 0.f;
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    const float w = (sm_m[g] == -INFINITY) ? 0.f : __expf(sm_m[g] - M);
+    L += sm_l[g] * w;
+    O += sm_o[g][d] * w;
+  }
+  if (splits == 1) {
+    out[static_cast<long long>(b) * ld_o + h * HD + d] = __float2bfloat16(L > 0.f ? O / L : 0.f);
+  } else {
+    const long long idx = (static_cast<long long>(b) * H + h) * splits + split;
+    if (d == 0) { ws_ml[idx * 2] = M; ws_ml[idx * 2 + 1] = L; }
+    ws_o[idx * HD + d] = O;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+attn_decode_combine_kernel(const float* __restrict__ ws_ml, const float* __restrict__ ws_o, int H, int splits,
+                           bf16* __restrict__ out, long long ld_o) {
+  constexpr int HD = 128;
+  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  const long long base = (static_cast<long long>(b) * H + h) * splits;
+  float M = -INFINITY;
+  for (int s = 0; s < splits; ++s) M = fmaxf(M, ws_ml[(base + s) * 2]);
+  float L = 0.f, O = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float ms = ws_ml[(base + s) * 2];
+    const float w = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+    L += ws_ml[(base + s) * 2 + 1] * w;
+    O += ws_o[(base + s) * HD + d] * w;
+  }
+  out[static_cast<long long>(b) * ld_o + h * HD + d] = __float2bfloat16(L > 0.f ? O / L : 0.f);
+}
+
+// ------------------------------------------------------------------ multimodal splice
+__global__ void splice_kernel(const bf16* __restrict__ embed, long long vocab, const bf16* __restrict__ feats,
+                              long long n_feat, const int32_t* __restrict__ srcmap, bf16* __restrict__ out,
+                              int d) {
+  const long long row = blockIdx.x;
+  const int src = srcmap[row];
+  const bf16* sp = nullptr;
+  if (src >= 0 && src < vocab) sp = embed + static_cast<long long>(src) * d;
+  else if (src < 0 && src != INT_MIN && -(static_cast<long long>(src) + 1) < n_feat)
+    sp = feats + (-(static_cast<long long>(src) + 1)) * d;
+  uint4* dst = reinterpret_cast<uint4*>(out + row * d);
+  const int nvec = d / 8;
+  if (sp) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(sp);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = s4[i];
+  } else {
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// ------------------------------------------------------------------ argmax (first maximal index)
+template <typename T>
+__global__ void __launch_bounds__(1024) argmax_kernel(const T* __restrict__ x, long long ld, int n, int64_t* __restrict__ out) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const T* row = x + blockIdx.x * ld;
+  float best = -INFINITY;
+  int bi = INT_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = static_cast<float>(row[i]);
+    if (v > best || (bi == INT_MAX && v == v)) { best = v; bi = i; }  // NaNs never win
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -INFINITY;
+    bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : INT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = bi == INT_MAX ? 0 : bi;
+  }
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vb200_rope_kv_append(void* qkv, int64_t ld_qkv, const int32_t* positions,
+                                    const int32_t* batch_of_token, const int32_t* slot_of_token,
+                                    void* k_pages, void* v_pages, const int32_t* block_table,
+                                    int64_t max_pages, int64_t tokens, int64_t n_heads,
+                                    int64_t head_dim, int64_t page_size, float rope_theta,
+                                    cudaStream_t stream) {
+  VB_CHECK_ARG(qkv && positions && tokens >= 0 && n_heads > 0);
+  VB_CHECK_ARG(head_dim % 16 == 0 && ld_qkv % 8 == 0 && ld_qkv >= 3 * n_heads * head_dim);
+  VB_CHECK_ARG((k_pages == nullptr) == (v_pages == nullptr));
+  VB_CHECK_ARG(k_pages == nullptr || (block_table != nullptr && page_size > 0 && max_pages > 0));
+  if (tokens == 0) return VB_OK;
+  rope_kv_append_kernel<<<static_cast<unsigned>(tokens), 256, 0, stream>>>(
+      reinterpret_cast<bf16*>(qkv), ld_qkv, positions, batch_of_token, slot_of_token,
+      reinterpret_cast<bf16*>(k_pages), reinterpret_cast<bf16*>(v_pages), block_table,
+      static_cast<int>(max_pages), static_cast<int>(n_heads), static_cast<int>(head_dim),
+      static_cast<int>(page_size), log2f(rope_theta));
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+static int decode_splits(int64_t max_kv_len) {
+  int s = static_cast<int>((max_kv_len + DEC_CHUNK - 1) / DEC_CHUNK);
+  if (s < 1) s = 1;
+  if (s > 32) s = 32;
+  return s;
+}
+
+extern "C" size_t vb200_attn_decode_workspace_size(int64_t B, int64_t n_heads, int64_t head_dim,
+                                                   int64_t max_splits) {
+  if (max_splits < 1) max_splits = 32;
+  return static_cast<size_t>(B) * n_heads * max_splits * (head_dim + 2) * sizeof(float);
+}
+
+extern "C" int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* k_pages,
+                                       const void* v_pages, const int32_t* block_table,
+                                       int64_t max_pages, const int32_t* kv_len, void* out,
+                                       int64_t ld_o, int64_t B, int64_t n_heads, int64_t head_dim,
+                                       int64_t page_size, int64_t max_kv_len, float scale,
+                                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  VB_CHECK_ARG(q && k_pages && v_pages && block_table && kv_len && out);
+  VB_CHECK_ARG(B > 0 && n_heads > 0 && page_size > 0 && max_pages > 0);
+  if (head_dim != 128) return VB_ERR_UNSUPPORTED;
+  VB_CHECK_ARG(ld_q % 8 == 0);
+  const int splits = decode_splits(max_kv_len);
+  float* ws_ml = nullptr;
+  float* ws_o = nullptr;
+  if (splits > 1) {
+    size_t need = vb200_attn_decode_workspace_size(B, n_heads, head_dim, splits);
+    if (!workspace || workspace_bytes < need) return VB_ERR_WORKSPACE;
+    ws_ml = reinterpret_cast<float*>(workspace);
+    ws_o = ws_ml + static_cast<size_t>(B) * n_heads * splits * 2;
+  }
+  dim3 grid(splits, static_cast<unsigned>(n_heads), static_cast<unsigned>(B));
+  attn_decode_kernel<<<grid, DEC_THREADS, 0, stream>>>(
+      reinterpret_cast<const bf16*>(q), ld_q, reinterpret_cast<const bf16*>(k_pages),
+      reinterpret_cast<const bf16*>(v_pages), block_table, static_cast<int>(max_pages), kv_len,
+      static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, ws_ml, ws_o,
+      reinterpret_cast<bf16*>(out), ld_o);
+  VB_LAUNCH_CHECK();
+  if (splits > 1) {
+    dim3 g2(static_cast<unsigned>(n_heads), static_cast<unsigned>(B));
+    attn_decode_combine_kernel<<<g2, 128, 0, stream>>>(ws_ml, ws_o, static_cast<int>(n_heads), splits,
+                                                       reinterpret_cast<bf16*>(out), ld_o);
+    VB_LAUNCH_CHECK();
+  }
+  return VB_OK;
+}
+
+extern "C" int vb200_splice_multimodal(const void* embed, int64_t vocab, const void* feats,
+                                       int64_t n_feat_rows, const int32_t* srcmap, void* out,
+                                       int64_t rows, int64_t d, cudaStream_t stream) {
+  VB_CHECK_ARG(embed && srcmap && out && d > 0 && d % 8 == 0 && rows >= 0);
+  VB_CHECK_ARG(feats != nullptr || n_feat_rows == 0);
+  if (rows == 0) return VB_OK;
+  splice_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(embed), vocab, reinterpret_cast<const bf16*>(feats), n_feat_rows,
+      srcmap, reinterpret_cast<bf16*>(out), static_cast<int>(d));
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+extern "C" int vb200_argmax_rows(const void* logits, int is_fp32, int64_t ld, int64_t rows, int64_t n,
+                                 int64_t* out_idx, cudaStream_t stream) {
+  VB_CHECK_ARG(logits && out_idx && rows >= 0 && n > 0);
+  if (rows == 0) return VB_OK;
+  if (is_fp32)
+    argmax_kernel<float><<<static_cast<unsigned>(rows), 1024, 0, stream>>>(reinterpret_cast<const float*>(logits), ld, static_cast<int>(n), out_idx);
+  else
+    argmax_kernel<bf16><<<static_cast<unsigned>(rows), 1024, 0, stream>>>(reinterpret_cast<const bf16*>(logits), ld, static_cast<int>(n), out_idx);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}

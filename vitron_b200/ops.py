@@ -1,0 +1,358 @@
+"""Torch-tensor wrappers over the C ABI (include/vitron_b200.h).
+
+torch is used only for device memory, streams and shapes: every function here enqueues one or two
+hand-written CUDA kernels from libvitron_b200.so on the current torch stream. No fallbacks.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_RELU, ACT_SILU, GLU_GEGLU, GLU_NONE,
+                   GLU_SWIGLU, Epilogue, check)
+
+BF16 = torch.bfloat16
+_ws = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def workspace(nbytes, device, tag="main"):
+    """Grow-only per-(device, tag) scratch buffer; contents are only valid within one op."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def _req(cond, msg):
+    if not cond:
+        raise ValueError(msg)
+
+
+def _rows2d(x):
+    """View x as [rows, d] with unit inner stride; returns (tensor2d, ld)."""
+    _req(x.stride(-1) == 1, "inner dimension must be contiguous")
+    if x.dim() == 2:
+        return x, x.stride(0)
+    x2 = x.reshape(-1, x.shape[-1])
+    return x2, x2.stride(0)
+
+
+def pack_glu_weight(w_a, w_b):
+    """Interleave two [F, K] weights (or [F] biases) in 16-row blocks: rows [32i,32i+16) = a,
+    [32i+16,32i+32) = b — the layout the fused GLU epilogue expects."""
+    f = w_a.shape[0]
+    _req(f % 16 == 0 and w_a.shape == w_b.shape, "GLU halves must match and be multiples of 16 rows")
+    rest = w_a.shape[1:]
+    a = w_a.reshape(f // 16, 16, *rest)
+    b = w_b.reshape(f // 16, 16, *rest)
+    return torch.stack([a, b], dim=1).reshape(2 * f, *rest).contiguous()
+
+
+def gemm(a, w, bias=None, act=ACT_NONE, glu=GLU_NONE, residual=None, alpha=1.0, rowbias=None,
+         rowbias_rows=0, out=None, out_fp32=False):
+    """out[M, N'] = epilogue(a[M, K] @ w[N, K]^T) on tcgen05 tensor cores."""
+    lib = _lib.load()
+    a2, lda = _rows2d(a)
+    _req(a2.dtype == BF16 and w.dtype == BF16, "gemm operands must be bf16")
+    _req(w.dim() == 2 and w.stride(1) == 1 and w.shape[1] == a2.shape[1], "weight must be [N, K] row-major")
+    M, K = a2.shape
+    N = w.shape[0]
+    n_out = N // 2 if glu != GLU_NONE else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float32 if out_fp32 else BF16, device=a.device)
+    else:
+        _req(out.shape[-1] == n_out and out.stride(-1) == 1, "bad out shape")
+        _req(out.dtype == (torch.float32 if out_fp32 else BF16), "bad out dtype")
+    out2, ldo = _rows2d(out)
+    epi = Epilogue()
+    epi.bias = _ptr(bias)
+    epi.rowbias = _ptr(rowbias)
+    epi.rowbias_rows = int(rowbias_rows)
+    epi.alpha = float(alpha)
+    epi.act = int(act)
+    epi.glu = int(glu)
+    epi.out_fp32 = 1 if out_fp32 else 0
+    if residual is not None:
+        r2, ldr = _rows2d(residual)
+        _req(r2.dtype == BF16 and r2.shape == (M, n_out), "bad residual")
+        epi.residual = r2.data_ptr()
+        epi.ldr = ldr
+    if bias is not None:
+        _req(bias.dtype == BF16 and bias.numel() == N and bias.is_contiguous(), "bad bias")
+    if M == 0:
+        return out.reshape(*a.shape[:-1], n_out) if a.dim() != 2 else out
+    need = lib.vb200_gemm_bf16_workspace_size(M, N, K)
+    ws = workspace(need, a.device) if need else None
+    check(lib.vb200_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), w.stride(0), out2.data_ptr(), ldo, M, N, K,
+                              C.byref(epi), _ptr(ws), need, _stream()), "vb200_gemm_bf16")
+    return out.reshape(*a.shape[:-1], n_out) if a.dim() != 2 else out
+
+
+def pack_conv_weight(w):
+    """[cout, cin, kh, kw] (torch Conv2d) or [cout, cin, kt, 1, 1] (Conv3d (k,1,1)) ->
+    [cout, kh*kw, ceil64(cin)] bf16, zero padded: the K-major layout of the implicit GEMM."""
+    if w.dim() == 5:
+        w = w[:, :, :, 0, 0].unsqueeze(-1)  # [cout, cin, kt, 1]
+    cout, cin, kh, kw = w.shape
+    cpad = (cin + 63) // 64 * 64
+    out = torch.zeros((cout, kh * kw, cpad), dtype=BF16, device=w.device)
+    out[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).to(BF16)
+    return out.contiguous()
+
+
+def conv_nhwc(x, wt, kh, kw, stride=1, pad_h=None, pad_w=None, bias=None, act=ACT_NONE, glu=GLU_NONE,
+              residual=None, alpha=1.0, rowbias=None, rowbias_rows=0, out=None):
+    """x [nb, h, w, cin] bf16 NHWC, wt from pack_conv_weight -> [nb, ho, wo, cout]."""
+    lib = _lib.load()
+    _req(x.dtype == BF16 and x.is_contiguous() and x.dim() == 4, "x must be contiguous NHWC bf16")
+    nb, h, w, cin = x.shape
+    cout = wt.shape[0]
+    pad_h = kh // 2 if pad_h is None else pad_h
+    pad_w = kw // 2 if pad_w is None else pad_w
+    ho = (h + 2 * pad_h - kh) // stride + 1
+    wo = (w + 2 * pad_w - kw) // stride + 1
+    n_out = cout // 2 if glu != GLU_NONE else cout
+    if out is None:
+        out = torch.empty((nb, ho, wo, n_out), dtype=BF16, device=x.device)
+    _req(wt.shape[1] == kh * kw and wt.shape[2] == (cin + 63) // 64 * 64, "weight not packed for this conv")
+    epi = Epilogue()
+    epi.bias = _ptr(bias)
+    epi.rowbias = _ptr(rowbias)
+    epi.rowbias_rows = int(rowbias_rows)
+    epi.alpha = float(alpha)
+    epi.act = int(act)
+    epi.glu = int(glu)
+    if residual is not None:
+        _req(residual.is_contiguous() and residual.shape == out.shape, "bad residual")
+        epi.residual = residual.data_ptr()
+        epi.ldr = n_out
+    check(lib.vb200_conv_nhwc_bf16(x.data_ptr(), wt.data_ptr(), out.data_ptr(), nb, h, w, cin, cout, kh, kw,
+                                   stride, pad_h, pad_w, C.byref(epi), _stream()), "vb200_conv_nhwc_bf16")
+    return out
+
+
+def conv_nhwc_direct(x, w_khwc, bias, kh, kw, stride=1, pad_h=None, pad_w=None):
+    """Tiny layers only. w_khwc: [cout, kh*kw, cin] bf16 (unpadded)."""
+    lib = _lib.load()
+    nb, h, w, cin = x.shape
+    cout = w_khwc.shape[0]
+    pad_h = kh // 2 if pad_h is None else pad_h
+    pad_w = kw // 2 if pad_w is None else pad_w
+    ho = (h + 2 * pad_h - kh) // stride + 1
+    wo = (w + 2 * pad_w - kw) // stride + 1
+    out = torch.empty((nb, ho, wo, cout), dtype=BF16, device=x.device)
+    check(lib.vb200_conv_nhwc_direct(x.data_ptr(), w_khwc.data_ptr(), _ptr(bias), out.data_ptr(), nb, h, w, cin,
+                                     cout, kh, kw, stride, pad_h, pad_w, _stream()), "vb200_conv_nhwc_direct")
+    return out
+
+
+def rmsnorm(x, weight, eps, out=None):
+    lib = _lib.load()
+    x2, ldx = _rows2d(x)
+    out = torch.empty_like(x) if out is None else out
+    o2, ldo = _rows2d(out)
+    check(lib.vb200_rmsnorm(x2.data_ptr(), ldx, weight.data_ptr(), o2.data_ptr(), ldo, x2.shape[0], x2.shape[1],
+                            float(eps), _stream()), "vb200_rmsnorm")
+    return out
+
+
+def layernorm(x, weight, bias, eps, out=None):
+    lib = _lib.load()
+    x2, ldx = _rows2d(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    o2, ldo = _rows2d(out)
+    check(lib.vb200_layernorm(x2.data_ptr(), ldx, weight.data_ptr(), _ptr(bias), o2.data_ptr(), ldo, x2.shape[0],
+                              x2.shape[1], float(eps), _stream()), "vb200_layernorm")
+    return out
+
+
+def groupnorm_nhwc(x, weight, bias, groups, eps, act=ACT_NONE, n=None, out=None):
+    """x [..., c] viewed as [n, spatial, c]; statistics over (spatial, c/groups) per n."""
+    lib = _lib.load()
+    _req(x.is_contiguous() and x.dtype == BF16, "x must be contiguous bf16")
+    c = x.shape[-1]
+    n = x.shape[0] if n is None else n
+    spatial = x.numel() // (n * c)
+    out = torch.empty_like(x) if out is None else out
+    need = lib.vb200_groupnorm_workspace_size(n, groups)
+    ws = workspace(need, x.device, "gn")
+    check(lib.vb200_groupnorm_nhwc(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), n, spatial, c,
+                                   groups, float(eps), int(act), ws.data_ptr(), need, _stream()),
+          "vb200_groupnorm_nhwc")
+    return out
+
+
+def _bsh(t):
+    """(batch, seq, head) element strides of a [B, S, H, D] view."""
+    _req(t.dim() == 4 and t.stride(3) == 1, "expect [B, S, H, D] with contiguous D")
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def attention(q, k, v, scale=None, causal=False, kv_len=None, mask=None, out=None):
+    """q [B, Sq, H, D], k/v [B, Skv, H, D] (any strides with contiguous D) -> [B, Sq, H, D].
+    mask: bool/uint8 [B or 1, H or 1, Sq, Skv], True = masked out."""
+    lib = _lib.load()
+    B, Sq, H, D = q.shape
+    Skv = k.shape[1]
+    scale = 1.0 / math.sqrt(D) if scale is None else scale
+    if out is None:
+        out = torch.empty((B, Sq, H, D), dtype=BF16, device=q.device)
+    m_ptr, m_sb, m_sh, m_sq = 0, 0, 0, 0
+    if mask is not None:
+        if mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        _req(mask.dim() == 4 and mask.stride(3) == 1 and mask.shape[2] == Sq and mask.shape[3] == Skv, "bad mask")
+        m_ptr = mask.data_ptr()
+        m_sb = mask.stride(0) if mask.shape[0] > 1 else 0
+        m_sh = mask.stride(1) if mask.shape[1] > 1 else 0
+        m_sq = mask.stride(2)
+    check(lib.vb200_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Sq, Skv, D,
+                              *_bsh(q), *_bsh(k), *_bsh(v), *_bsh(out), float(scale), 1 if causal else 0,
+                              _ptr(kv_len), m_ptr, m_sb, m_sh, m_sq, _stream()), "vb200_attention")
+    return out
+
+
+def attention_short(q, k, v, scale=None, out=None):
+    """q/k/v [nseq, S, H, 64] strided views, S <= 32."""
+    lib = _lib.load()
+    nseq, S, H, D = q.shape
+    scale = 1.0 / math.sqrt(D) if scale is None else scale
+    if out is None:
+        out = torch.empty((nseq, S, H, D), dtype=BF16, device=q.device)
+    check(lib.vb200_attention_short(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), nseq, H, S, D,
+                                    *_bsh(q), *_bsh(k), *_bsh(v), *_bsh(out), float(scale), _stream()),
+          "vb200_attention_short")
+    return out
+
+
+def rope_kv_append(qkv, positions, n_heads, head_dim, theta, k_pages=None, v_pages=None, block_table=None,
+                   batch_of_token=None, slot_of_token=None, page_size=0):
+    lib = _lib.load()
+    q2, ld = _rows2d(qkv)
+    max_pages = block_table.shape[1] if block_table is not None else 0
+    check(lib.vb200_rope_kv_append(q2.data_ptr(), ld, positions.data_ptr(), _ptr(batch_of_token),
+                                   _ptr(slot_of_token), _ptr(k_pages), _ptr(v_pages), _ptr(block_table),
+                                   max_pages, q2.shape[0], n_heads, head_dim, page_size, float(theta), _stream()),
+          "vb200_rope_kv_append")
+    return qkv
+
+
+def attn_decode_paged(q, k_pages, v_pages, block_table, kv_len, n_heads, head_dim, page_size, max_kv_len,
+                      scale=None, out=None):
+    """q [B, >= n_heads*head_dim] rows (e.g. the fused qkv buffer) -> out [B, n_heads*head_dim]."""
+    lib = _lib.load()
+    B = q.shape[0]
+    scale = 1.0 / math.sqrt(head_dim) if scale is None else scale
+    if out is None:
+        out = torch.empty((B, n_heads * head_dim), dtype=BF16, device=q.device)
+    need = lib.vb200_attn_decode_workspace_size(B, n_heads, head_dim, 32)
+    ws = workspace(need, q.device, "dec")
+    check(lib.vb200_attn_decode_paged(q.data_ptr(), q.stride(0), k_pages.data_ptr(), v_pages.data_ptr(),
+                                      block_table.data_ptr(), block_table.shape[1], kv_len.data_ptr(),
+                                      out.data_ptr(), out.stride(0), B, n_heads, head_dim, page_size, max_kv_len,
+                                      float(scale), ws.data_ptr(), need, _stream()), "vb200_attn_decode_paged")
+    return out
+
+
+def splice_multimodal(embed, feats, srcmap, out=None):
+    lib = _lib.load()
+    rows = srcmap.numel()
+    d = embed.shape[1]
+    if out is None:
+        out = torch.empty((*srcmap.shape, d), dtype=BF16, device=embed.device)
+    nfeat = 0 if feats is None else feats.shape[0]
+    check(lib.vb200_splice_multimodal(embed.data_ptr(), embed.shape[0], _ptr(feats), nfeat, srcmap.data_ptr(),
+                                      out.data_ptr(), rows, d, _stream()), "vb200_splice_multimodal")
+    return out
+
+
+def argmax_rows(logits, out=None):
+    lib = _lib.load()
+    l2, ld = _rows2d(logits)
+    if out is None:
+        out = torch.empty((l2.shape[0],), dtype=torch.int64, device=logits.device)
+    check(lib.vb200_argmax_rows(l2.data_ptr(), 1 if l2.dtype == torch.float32 else 0, ld, l2.shape[0], l2.shape[1],
+                                out.data_ptr(), _stream()), "vb200_argmax_rows")
+    return out
+
+
+def patchify(pixels, patch, kpad):
+    lib = _lib.load()
+    _req(pixels.is_contiguous() and pixels.dim() == 4, "pixels must be contiguous NCHW")
+    _req(pixels.dtype in (torch.float32, BF16), "pixels must be fp32 or bf16")
+    nb, c, h, w = pixels.shape
+    out = torch.empty((nb * (h // patch) * (w // patch), kpad), dtype=BF16, device=pixels.device)
+    check(lib.vb200_patchify(pixels.data_ptr(), 1 if pixels.dtype == torch.float32 else 0, out.data_ptr(), nb, c, h,
+                             w, patch, kpad, _stream()), "vb200_patchify")
+    return out
+
+
+def vit_embed_ln(patch_out, cls, pos, ln_w, ln_b, nb, npatch, eps):
+    lib = _lib.load()
+    d = patch_out.shape[-1]
+    out = torch.empty((nb, npatch + 1, d), dtype=BF16, device=patch_out.device)
+    check(lib.vb200_vit_embed_ln(patch_out.data_ptr(), cls.data_ptr(), pos.data_ptr(), ln_w.data_ptr(),
+                                 ln_b.data_ptr(), out.data_ptr(), nb, npatch, d, float(eps), _stream()),
+          "vb200_vit_embed_ln")
+    return out
+
+
+def upsample2x_nhwc(x):
+    lib = _lib.load()
+    nb, h, w, c = x.shape
+    out = torch.empty((nb, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
+    check(lib.vb200_upsample2x_nhwc(x.data_ptr(), out.data_ptr(), nb, h, w, c, _stream()), "vb200_upsample2x_nhwc")
+    return out
+
+
+def add(a, b, out=None):
+    """a + b (bf16); b may be a broadcast operand whose numel divides a's (period)."""
+    lib = _lib.load()
+    _req(a.is_contiguous() and b.is_contiguous(), "add operands must be contiguous")
+    out = torch.empty_like(a) if out is None else out
+    period = 0 if b.numel() == a.numel() else b.numel()
+    check(lib.vb200_add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), period, _stream()),
+          "vb200_add_bf16")
+    return out
+
+
+def cfg_combine(y, u, scale):
+    lib = _lib.load()
+    _req(y.dtype == torch.float32 and u.dtype == torch.float32 and y.is_contiguous() and u.is_contiguous(), "fp32")
+    out = torch.empty_like(y)
+    check(lib.vb200_cfg_combine(y.data_ptr(), u.data_ptr(), out.data_ptr(), float(scale), y.numel(), _stream()),
+          "vb200_cfg_combine")
+    return out
+
+
+def region_mask_pool(feats, boxes, image_size):
+    """feats [B, g*g, C] bf16, boxes fp32 [B, 4] -> [B, C]."""
+    lib = _lib.load()
+    B, n, c = feats.shape
+    g = int(math.isqrt(n))
+    out = torch.empty((B, c), dtype=BF16, device=feats.device)
+    check(lib.vb200_region_mask_pool(feats.data_ptr(), boxes.data_ptr(), out.data_ptr(), B, g, c, image_size,
+                                     _stream()), "vb200_region_mask_pool")
+    return out
+
+
+def seem_attn_mask(mask_logits, h2, w2):
+    """mask_logits fp32 [Q, H, W] -> uint8 [Q, h2*w2], 1 = masked out."""
+    lib = _lib.load()
+    Q, H, W = mask_logits.shape
+    out = torch.empty((Q, h2 * w2), dtype=torch.uint8, device=mask_logits.device)
+    check(lib.vb200_seem_attn_mask(mask_logits.data_ptr(), out.data_ptr(), Q, H, W, h2, w2, _stream()),
+          "vb200_seem_attn_mask")
+    return out
