@@ -96,7 +96,7 @@ int vb200_groupnorm_nhwc(const void* x, const void* weight, const void* bias, vo
 /* ---- attention (attention.cu) ---------------------------------------------------------------
  * Flash-style softmax(QK^T*scale + mask)V with generic element strides (batch, seq, head); the
  * head dim is contiguous. kv_len: int32 [B] valid keys per batch or NULL. causal: key j visible
- * to query i iff j <= i + (kv_len - q_len). mask: uint8, non-zero = masked out, element strides
+ * to query i iff j <= i + (Skv - Sq) and j < kv_len[b]. mask: uint8, non-zero = masked out, element strides
  * (mb, mh, mq) with keys contiguous, or NULL. Rows with every key masked produce zeros.
  * Replaces HF LlamaAttention / CLIPAttention eager bmm+softmax, xformers
  * memory_efficient_attention (i2vgen util.py:253-258; GLIGEN attention.py:176,247) and SEEM
@@ -138,6 +138,13 @@ int vb200_splice_multimodal(const void* embed, int64_t vocab, const void* feats,
                             int64_t d, cudaStream_t stream);
 int vb200_argmax_rows(const void* logits, int is_fp32, int64_t ld, int64_t rows, int64_t n,
                       int64_t* out_idx, cudaStream_t stream);
+
+/* greedy step: out_idx[b] = argmax(logits[b]); next_src[b] = idx (int32, feeds the next
+ * splice/embedding gather); token_log[b, kv_len[b]-prompt_len[b]] = idx; positions[b]++, kv_len[b]++.
+ * Stands in for HF GenerationMixin.greedy_search's per-token host round trip. */
+int vb200_argmax_advance(const float* logits, int64_t ld, int64_t rows, int64_t n, int64_t* out_idx,
+                         int32_t* next_src, int32_t* positions, int32_t* kv_len, int64_t* token_log,
+                         int64_t log_stride, const int32_t* prompt_len, cudaStream_t stream);
 
 /* ---- vision / diffusion glue (vision.cu) ----------------------------------------------------
  * patchify: NCHW pixels -> [nb*gh*gw, kpad] rows ordered (c, py, px) for the patch-embed GEMM

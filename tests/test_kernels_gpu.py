@@ -171,7 +171,7 @@ def sdpa_ref(q, k, v, scale, causal=False, kv_len=None, mask=None):
     dead = dead | (kk[None, None, None, :] >= lens[:, None, None, None])
     if causal:
         qi = torch.arange(Sq, device=q.device)
-        dead = dead | (kk[None, None, None, :] > (qi[None, None, :, None] + (lens[:, None, None, None] - Sq)))
+        dead = dead | (kk[None, None, None, :] > (qi[None, None, :, None] + (Skv - Sq)))
     if mask is not None:
         dead = dead | mask.bool()
     s = s.masked_fill(dead, float("-inf"))
@@ -203,6 +203,10 @@ def test_attention_fused_qkv_layout_kvlen_mask(cuda):
     lens = torch.tensor([300, 17, 129], dtype=torch.int32, device=cuda)
     out = ops.attention(q, k, v, causal=False, kv_len=lens)
     close(out, sdpa_ref(q, k, v, 1 / math.sqrt(D), False, lens), 2e-2, 2e-2, "kv_len")
+    out = ops.attention(q, k, v, causal=True, kv_len=lens)  # right-padded prefill
+    ref = sdpa_ref(q, k, v, 1 / math.sqrt(D), True, lens)
+    for b, l in enumerate(lens.tolist()):
+        close(out[b, :l], ref[b, :l], 2e-2, 2e-2, "causal + kv_len")
     g = torch.Generator().manual_seed(5)
     mask = (torch.rand((B, H, S, S), generator=g) < 0.6).to(cuda)
     mask[0, 1, 5] = True  # a fully masked row -> zeros

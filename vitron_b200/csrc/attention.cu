@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(const AttnParams
   const int g = lane >> 2, t = lane & 3;
   const int q0 = qb * FA_BM;
   const int kv_len = p.kv_len ? min(p.kv_len[b], p.Skv) : p.Skv;
-  const int causal_off = kv_len - p.Sq;  // key j visible to query i iff j <= i + causal_off
+  const int causal_off = p.Skv - p.Sq;  // key j visible to query i iff j <= i + (Skv - Sq)
 
   const bf16* qg = p.q + b * p.q_sb + h * p.q_sh + static_cast<long long>(q0) * p.q_ss;
   const bf16* kg = p.k + b * p.k_sb + h * p.k_sh;

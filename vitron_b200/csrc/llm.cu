@@ -246,9 +246,67 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const T* __restrict__ x, l
   }
 }
 
+// greedy decode bookkeeping fused with the arg-max: one CTA per sequence
+__global__ void __launch_bounds__(1024)
+argmax_advance_kernel(const float* __restrict__ logits, long long ld, int n, int64_t* __restrict__ out_idx,
+                      int32_t* __restrict__ next_src, int32_t* __restrict__ positions, int32_t* __restrict__ kv_len,
+                      int64_t* __restrict__ token_log, int log_stride, const int32_t* __restrict__ prompt_len) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const int b = blockIdx.x;
+  const float* row = logits + b * ld;
+  float best = -INFINITY;
+  int bi = INT_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = row[i];
+    if (v > best || (bi == INT_MAX && v == v)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = sv[threadIdx.x];
+    bi = si[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+      if (bi == INT_MAX) bi = 0;
+      out_idx[b] = bi;
+      if (next_src) next_src[b] = bi;
+      if (token_log) {
+        const int step = kv_len[b] - prompt_len[b];  // tokens generated before this one
+        if (step >= 0 && step < log_stride) token_log[static_cast<long long>(b) * log_stride + step] = bi;
+      }
+      if (positions) positions[b] += 1;
+      if (kv_len) kv_len[b] += 1;
+    }
+  }
+}
+
 }  // namespace vb
 
 using namespace vb;
+
+extern "C" int vb200_argmax_advance(const float* logits, int64_t ld, int64_t rows, int64_t n, int64_t* out_idx,
+                                    int32_t* next_src, int32_t* positions, int32_t* kv_len, int64_t* token_log,
+                                    int64_t log_stride, const int32_t* prompt_len, cudaStream_t stream) {
+  VB_CHECK_ARG(logits && out_idx && rows > 0 && n > 0);
+  VB_CHECK_ARG(token_log == nullptr || (kv_len != nullptr && prompt_len != nullptr));
+  argmax_advance_kernel<<<static_cast<unsigned>(rows), 1024, 0, stream>>>(
+      logits, ld, static_cast<int>(n), out_idx, next_src, positions, kv_len, token_log,
+      static_cast<int>(log_stride), prompt_len);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
 
 extern "C" int vb200_rope_kv_append(void* qkv, int64_t ld_qkv, const int32_t* positions,
                                     const int32_t* batch_of_token, const int32_t* slot_of_token,

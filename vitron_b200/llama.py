@@ -1,0 +1,318 @@
+"""Vicuna-7B / LLaMA decoder stack on the vitron_b200 kernels.
+
+Replaces the arithmetic of HF transformers 4.31 `LlamaModel` / `LlamaForCausalLM.forward` as
+called by the reference at vitron/model/language_model/llava_llama.py:91-102 (the q/k/v/RoPE/KV
+sequence is restated in-tree at vitron/train/llama_flash_attn_monkey_patch.py:30-66):
+
+    embed -> 32 x [RMSNorm, QKV, RoPE, causal attention over the KV cache, O, +res,
+                   RMSNorm, down(SiLU(gate) * up), +res] -> RMSNorm -> lm_head
+
+Differences in mechanism (not in math): q/k/v and gate/up are single fused GEMMs (weights packed
+at load), the KV cache is paged in HBM instead of grown with torch.cat, residual adds / SiLU*mul
+live in GEMM epilogues, and the decode step is one CUDA graph with the arg-max on device.
+State-dict names are the reference's.
+"""
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class LlamaConfig:
+    hidden_size: int = 4096
+    intermediate_size: int = 11008
+    num_hidden_layers: int = 32
+    num_attention_heads: int = 32
+    vocab_size: int = 32000
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    max_position_embeddings: int = 4096
+
+    @property
+    def head_dim(self):
+        return self.hidden_size // self.num_attention_heads
+
+    @staticmethod
+    def from_any(cfg):
+        """Accept an HF LlamaConfig-like object or dict."""
+        if isinstance(cfg, LlamaConfig):
+            return cfg
+        get = (lambda k, d: cfg.get(k, d)) if isinstance(cfg, dict) else (lambda k, d: getattr(cfg, k, d))
+        theta = get("rope_theta", None)
+        if theta is None:
+            rp = get("rope_parameters", None) or {}
+            theta = rp.get("rope_theta", 10000.0) if isinstance(rp, dict) else 10000.0
+        return LlamaConfig(get("hidden_size", 4096), get("intermediate_size", 11008), get("num_hidden_layers", 32),
+                           get("num_attention_heads", 32), get("vocab_size", 32000), get("rms_norm_eps", 1e-5),
+                           float(theta), get("max_position_embeddings", 4096))
+
+
+class PagedKVCache:
+    """[layers, 2, num_pages, heads, page_size, head_dim] bf16 + a per-slot block table.
+
+    Pages are handed out from a free list; a sequence slot owns ceil(len / page_size) pages."""
+
+    def __init__(self, cfg, max_batch, max_seq_len, device, page_size=64):
+        self.page_size = page_size
+        self.max_pages = (max_seq_len + page_size - 1) // page_size
+        self.num_pages = max_batch * self.max_pages
+        self.max_batch = max_batch
+        self.max_seq_len = self.max_pages * page_size
+        L, H, D = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.head_dim
+        self.pages = torch.zeros((L, 2, self.num_pages, H, page_size, D), dtype=BF16, device=device)
+        self.block_table = torch.zeros((max_batch, self.max_pages), dtype=torch.int32, device=device)
+        self._free = list(range(self.num_pages - 1, -1, -1))
+        self._owned = [[] for _ in range(max_batch)]
+        self.device = device
+
+    def reserve(self, slot, length):
+        need = (length + self.page_size - 1) // self.page_size
+        owned = self._owned[slot]
+        if need > self.max_pages:
+            raise ValueError(f"sequence of {length} tokens exceeds the cache capacity {self.max_seq_len}")
+        changed = False
+        while len(owned) < need:
+            if not self._free:
+                raise RuntimeError("KV cache out of pages")
+            owned.append(self._free.pop())
+            changed = True
+        return changed
+
+    def release(self, slot):
+        self._free.extend(reversed(self._owned[slot]))
+        self._owned[slot] = []
+
+    def sync_table(self):
+        host = torch.zeros((self.max_batch, self.max_pages), dtype=torch.int32)
+        for s, owned in enumerate(self._owned):
+            if owned:
+                host[s, :len(owned)] = torch.tensor(owned, dtype=torch.int32)
+        self.block_table.copy_(host, non_blocking=True)
+
+    def k(self, layer):
+        return self.pages[layer, 0]
+
+    def v(self, layer):
+        return self.pages[layer, 1]
+
+
+class LlamaEngine:
+    def __init__(self, config, device, max_batch=8, max_seq_len=1024, page_size=64):
+        self.cfg = LlamaConfig.from_any(config)
+        self.device = torch.device(device)
+        self.max_batch = max_batch
+        self.cache = PagedKVCache(self.cfg, max_batch, max_seq_len, self.device, page_size)
+        self.layers = []
+        self.embed = None
+        self.norm = None
+        self.lm_head = None
+        c = self.cfg
+        B = max_batch
+        dev = self.device
+        # static decode state (addresses are baked into the CUDA graph)
+        self.d_src = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.d_pos = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.d_len = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.d_prompt = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.d_bot = torch.arange(B, dtype=torch.int32, device=dev)
+        self.d_next = torch.zeros((B,), dtype=torch.int64, device=dev)
+        self.d_logits = torch.zeros((B, c.vocab_size), dtype=torch.float32, device=dev)
+        self.token_log = None
+        self._graph = None
+        self._graph_batch = 0
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd, prefix=""):
+        """HF names: model.embed_tokens.weight, model.layers.N.self_attn.{q,k,v,o}_proj.weight,
+        model.layers.N.mlp.{gate,up,down}_proj.weight, model.layers.N.{input,post_attention}_layernorm.weight,
+        model.norm.weight, lm_head.weight."""
+        dev = self.device
+
+        def get(name):
+            return sd[prefix + name].detach().to(device=dev, dtype=BF16)
+
+        self.embed = get("model.embed_tokens.weight").contiguous()
+        self.norm = get("model.norm.weight").contiguous()
+        self.lm_head = get("lm_head.weight").contiguous()
+        self.layers = []
+        for i in range(self.cfg.num_hidden_layers):
+            p = f"model.layers.{i}."
+            wqkv = torch.cat([get(p + "self_attn.q_proj.weight"), get(p + "self_attn.k_proj.weight"),
+                              get(p + "self_attn.v_proj.weight")], 0).contiguous()
+            wgu = ops.pack_glu_weight(get(p + "mlp.gate_proj.weight"), get(p + "mlp.up_proj.weight"))
+            self.layers.append(dict(
+                ln1=get(p + "input_layernorm.weight").contiguous(), wqkv=wqkv,
+                wo=get(p + "self_attn.o_proj.weight").contiguous(),
+                ln2=get(p + "post_attention_layernorm.weight").contiguous(), wgu=wgu,
+                wdown=get(p + "mlp.down_proj.weight").contiguous()))
+        self._graph = None
+        return self
+
+    def init_random(self, seed=0, std=0.02):
+        """Random-init weights of the configured architecture directly on the device (benchmarks)."""
+        c, dev = self.cfg, self.device
+        g = torch.Generator(device=dev).manual_seed(seed)
+
+        def w(*shape):
+            return (torch.randn(shape, generator=g, device=dev, dtype=torch.float32) * std).to(BF16)
+
+        ones = lambda n: torch.ones((n,), dtype=BF16, device=dev)
+        self.embed = w(c.vocab_size, c.hidden_size)
+        self.norm = ones(c.hidden_size)
+        self.lm_head = w(c.vocab_size, c.hidden_size)
+        self.layers = []
+        for _ in range(c.num_hidden_layers):
+            self.layers.append(dict(
+                ln1=ones(c.hidden_size), wqkv=w(3 * c.hidden_size, c.hidden_size), wo=w(c.hidden_size, c.hidden_size),
+                ln2=ones(c.hidden_size),
+                wgu=ops.pack_glu_weight(w(c.intermediate_size, c.hidden_size), w(c.intermediate_size, c.hidden_size)),
+                wdown=w(c.hidden_size, c.intermediate_size)))
+        self._graph = None
+        return self
+
+    def weight_bytes(self):
+        n = self.lm_head.numel()
+        for l in self.layers:
+            n += l["wqkv"].numel() + l["wo"].numel() + l["wgu"].numel() + l["wdown"].numel()
+        return 2 * n
+
+    # ------------------------------------------------------------------ layers
+    def _layer(self, i, h, positions, bot, slots, prefill_shape=None, kv_len=None, max_kv_len=0):
+        """h [T, d] is updated in place and returned."""
+        c, L, cache = self.cfg, self.layers[i], self.cache
+        H, D = c.num_attention_heads, c.head_dim
+        x = ops.rmsnorm(h, L["ln1"], c.rms_norm_eps)
+        qkv = ops.gemm(x, L["wqkv"])
+        ops.rope_kv_append(qkv, positions, H, D, c.rope_theta, cache.k(i), cache.v(i), cache.block_table, bot, slots,
+                           cache.page_size)
+        if prefill_shape is not None:
+            B, S = prefill_shape
+            q4 = qkv.view(B, S, 3, H, D)
+            att = ops.attention(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], causal=True, kv_len=kv_len)
+            att = att.view(B * S, H * D)
+        else:
+            att = ops.attn_decode_paged(qkv, cache.k(i), cache.v(i), cache.block_table, kv_len, H, D, cache.page_size,
+                                        max_kv_len)
+        ops.gemm(att, L["wo"], residual=h, out=h)
+        x = ops.rmsnorm(h, L["ln2"], c.rms_norm_eps)
+        act = ops.gemm(x, L["wgu"], glu=ops.GLU_SWIGLU)
+        ops.gemm(act, L["wdown"], residual=h, out=h)
+        return h
+
+    # ------------------------------------------------------------------ prefill
+    def prefill(self, inputs_embeds, seq_lens=None, all_logits=False):
+        """inputs_embeds [B, S, d] bf16 (right padded), seq_lens list/tensor of valid lengths.
+        Fills the KV cache for slots 0..B-1 and returns fp32 logits of the last valid token [B, V]
+        (or of every position [B, S, V] when all_logits)."""
+        c, dev, cache = self.cfg, self.device, self.cache
+        B, S, d = inputs_embeds.shape
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > engine max_batch {self.max_batch}")
+        lens = [S] * B if seq_lens is None else [int(x) for x in seq_lens]
+        for b in range(self.max_batch):
+            cache.release(b)
+        for b in range(B):
+            cache.reserve(b, min(cache.max_seq_len, lens[b]))
+        cache.sync_table()
+        ar = torch.arange(S, dtype=torch.int32)
+        lens_t = torch.tensor(lens, dtype=torch.int32)
+        pos_h = ar.repeat(B)
+        valid = (ar[None, :] < lens_t[:, None]).reshape(-1)
+        slots_h = torch.where(valid, pos_h, torch.full_like(pos_h, -1))
+        bot_h = torch.arange(B, dtype=torch.int32).repeat_interleave(S)
+        positions = pos_h.to(dev, non_blocking=True)
+        slots = slots_h.to(dev, non_blocking=True)
+        bot = bot_h.to(dev, non_blocking=True)
+        kv_len = lens_t.to(dev, non_blocking=True)
+        h = inputs_embeds.to(BF16).reshape(B * S, d).clone()
+        for i in range(c.num_hidden_layers):
+            self._layer(i, h, positions, bot, slots, prefill_shape=(B, S), kv_len=kv_len)
+        # decode state: next token goes to position / slot P, attention then spans P + 1 keys
+        self.d_pos[:B].copy_(kv_len)
+        self.d_len[:B].copy_(kv_len + 1)
+        self.d_prompt[:B].copy_(kv_len)
+        self._lens_host = list(lens)
+        if all_logits:
+            hn = ops.rmsnorm(h, self.norm, c.rms_norm_eps)
+            return ops.gemm(hn, self.lm_head, out_fp32=True).view(B, S, c.vocab_size)
+        last = (torch.arange(B) * S + (lens_t.long() - 1)).to(dev)
+        hl = h.index_select(0, last)
+        hn = ops.rmsnorm(hl, self.norm, c.rms_norm_eps)
+        return ops.gemm(hn, self.lm_head, out_fp32=True)
+
+    # ------------------------------------------------------------------ decode
+    def _decode_body(self, B):
+        """One greedy token for slots 0..B-1: reads d_src/d_pos/d_len, leaves logits in d_logits,
+        arg-max in d_next, and advances the device-side counters."""
+        c = self.cfg
+        h = ops.splice_multimodal(self.embed, None, self.d_src[:B])
+        for i in range(c.num_hidden_layers):
+            self._layer(i, h, self.d_pos[:B], self.d_bot[:B], None, kv_len=self.d_len[:B],
+                        max_kv_len=self.cache.max_seq_len)
+        hn = ops.rmsnorm(h, self.norm, c.rms_norm_eps)
+        ops.gemm(hn, self.lm_head, out=self.d_logits[:B], out_fp32=True)
+
+    def _step_kernels(self, B):
+        self._decode_body(B)
+        # token_log[b, d_len - d_prompt] = arg-max; d_src = arg-max; d_pos += 1; d_len += 1
+        ops.argmax_advance(self.d_logits[:B], self.d_next[:B], next_src=self.d_src[:B], positions=self.d_pos[:B],
+                           kv_len=self.d_len[:B], token_log=self.token_log[:B], prompt_len=self.d_prompt[:B])
+
+    def start_decode(self, first_tokens, max_new_tokens):
+        """first_tokens [B] int64: the token chosen from the prefill logits (already counted as
+        generated token 0). Prepares device state for up to max_new_tokens-1 further steps."""
+        B = first_tokens.shape[0]
+        dev = self.device
+        need = max(int(x) for x in self._lens_host) + max_new_tokens
+        if need > self.cache.max_seq_len:
+            raise ValueError(f"prompt + max_new_tokens = {need} exceeds KV capacity {self.cache.max_seq_len}")
+        changed = False
+        for b in range(B):
+            changed |= self.cache.reserve(b, self._lens_host[b] + max_new_tokens)
+        if changed:
+            self.cache.sync_table()
+        self.token_log = torch.zeros((self.max_batch, max_new_tokens), dtype=torch.int64, device=dev)
+        self.token_log[:B, 0] = first_tokens
+        self.d_src[:B] = first_tokens.to(torch.int32)
+        self._graph = None
+
+    def decode_steps(self, B, n, use_graph=True):
+        """Run n greedy decode steps for slots 0..B-1 (no host sync)."""
+        if n <= 0:
+            return
+        if not use_graph:
+            for _ in range(n):
+                self._step_kernels(B)
+            return
+        if self._graph is None or self._graph_batch != B:
+            # warm-up on a side stream (allocator + lazy init), then capture
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream())
+            saved = [t.clone() for t in (self.d_src, self.d_pos, self.d_len, self.token_log)]
+            with torch.cuda.stream(s):
+                self._step_kernels(B)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            for t, sv in zip((self.d_src, self.d_pos, self.d_len, self.token_log), saved):
+                t.copy_(sv)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_kernels(B)
+            for t, sv in zip((self.d_src, self.d_pos, self.d_len, self.token_log), saved):
+                t.copy_(sv)
+            self._graph, self._graph_batch = g, B
+        for _ in range(n):
+            self._graph.replay()
+
+    def decode_one_logits(self, tokens):
+        """Non-greedy path: feed tokens [B] and return fp32 logits [B, V] (sampling done by caller)."""
+        B = tokens.shape[0]
+        self.d_src[:B] = tokens.to(torch.int32)
+        self._decode_body(B)
+        self.d_pos[:B].add_(1)
+        self.d_len[:B].add_(1)
+        return self.d_logits[:B]

@@ -288,6 +288,16 @@ def argmax_rows(logits, out=None):
     return out
 
 
+def argmax_advance(logits, out_idx, next_src=None, positions=None, kv_len=None, token_log=None, prompt_len=None):
+    lib = _lib.load()
+    _req(logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1, "fp32 logits [B, V]")
+    check(lib.vb200_argmax_advance(logits.data_ptr(), logits.stride(0), logits.shape[0], logits.shape[1],
+                                   out_idx.data_ptr(), _ptr(next_src), _ptr(positions), _ptr(kv_len),
+                                   _ptr(token_log), token_log.shape[1] if token_log is not None else 0,
+                                   _ptr(prompt_len), _stream()), "vb200_argmax_advance")
+    return out_idx
+
+
 def patchify(pixels, patch, kpad):
     lib = _lib.load()
     _req(pixels.is_contiguous() and pixels.dim() == 4, "pixels must be contiguous NCHW")
