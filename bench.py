@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Vitron multimodal forward path on B200.
+
+Workload (BASELINE.json configs[1]): batch-8 images -> LanguageBind ViT-L/14 encode + mlp2x_gelu
+projector + splice -> Vicuna-7B prefill over 256 vision + 512 text tokens -> 128 greedy decode
+tokens, bf16, random-init weights, synthetic pixels / ids. One "step" = that whole pass for one
+batch. `value` = generated tokens / s of the whole job (all ranks) with inputs resident in HBM;
+`e2e` = same through VitronLlamaForCausalLM.generate() with HOST (pinned) inputs and the ids read
+back. N > 1: one process per GPU (torchrun), independent request batches (weak scaling), one NCCL
+all_gather of the generated ids at the end of every step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Vicuna-7B generated tokens/s, batch-8 x (256 vision + 512 text) prefill + 128-token greedy decode, incl. ViT-L/14 encode"
+VICUNA_7B = dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32,
+                 vocab_size=32000, rms_norm_eps=1e-5, rope_theta=10000.0)
+VIT_L14 = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+               image_size=224, patch_size=14, hidden_act="gelu")
+BATCH, TEXT, VISION, NEW = 8, 512, 256, 128
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            names = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            while not self.stop_flag:
+                self.samples.append(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                try:
+                    r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+                time.sleep(0.1)
+        except Exception as e:  # NVML unavailable: report it rather than invent numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def synth_inputs(seed_px=1, seed_ids=2, batch=BATCH):
+    g = torch.Generator().manual_seed(seed_px)
+    pixels = torch.randn((batch, 3, 224, 224), generator=g)
+    g = torch.Generator().manual_seed(seed_ids)
+    ids = torch.randint(3, 32000, (batch, TEXT + 1), generator=g)
+    ids[:, 0] = 1
+    ids[:, 1] = -200  # <image> right after BOS; 513 ids -> 768 positions
+    return pixels, ids
+
+
+# =============================================================================== CPU (reference arm)
+def cpu_sample(threads=None):
+    """Bounded CPU sample of the same workload with the oracle port of the reference
+    (oracle/restate_llm.py): ViT-L/14 2 of 23 needed layers on 1 image, LLaMA-7B-shaped 2 of 32
+    layers — prefill S=768 at B=1, 4 cached decode steps at B=8 — fp32, all host threads; the
+    per-layer times are scaled to the full depth and batch. Returns (tokens_per_s, info)."""
+    from oracle import restate_llm as R
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    rn = lambda *s: torch.randn(s, generator=g) * 0.02
+    LL = 2
+    d, f, V = 4096, 11008, 32000
+    if "w" in _CPU_CACHE:
+        sd, cfg, vsd, vcfg, vp = _CPU_CACHE["w"]
+        return _cpu_time(R, sd, cfg, vsd, vcfg, vp, rn, g, LL, d)
+    sd = {"model.embed_tokens.weight": rn(V, d), "lm_head.weight": rn(V, d), "model.norm.weight": torch.ones(d)}
+    for i in range(LL):
+        p = f"model.layers.{i}."
+        for n in "qkvo":
+            sd[p + f"self_attn.{n}_proj.weight"] = rn(d, d)
+        sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"], sd[p + "mlp.down_proj.weight"] = rn(f, d), rn(f, d), rn(d, f)
+        sd[p + "input_layernorm.weight"] = torch.ones(d)
+        sd[p + "post_attention_layernorm.weight"] = torch.ones(d)
+    cfg = dict(VICUNA_7B, num_hidden_layers=LL)
+    vd, vf = 1024, 4096
+    vp = "v."
+    vsd = {vp + "embeddings.class_embedding": rn(vd), vp + "embeddings.patch_embedding.weight": rn(vd, 3, 14, 14),
+           vp + "embeddings.position_embedding.weight": rn(257, vd), vp + "pre_layrnorm.weight": torch.ones(vd),
+           vp + "pre_layrnorm.bias": torch.zeros(vd)}
+    for i in range(LL):
+        p = vp + f"encoder.layers.{i}."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            vsd[p + f"self_attn.{n}.weight"], vsd[p + f"self_attn.{n}.bias"] = rn(vd, vd), torch.zeros(vd)
+        for n in ("layer_norm1", "layer_norm2"):
+            vsd[p + n + ".weight"], vsd[p + n + ".bias"] = torch.ones(vd), torch.zeros(vd)
+        vsd[p + "mlp.fc1.weight"], vsd[p + "mlp.fc1.bias"] = rn(vf, vd), torch.zeros(vf)
+        vsd[p + "mlp.fc2.weight"], vsd[p + "mlp.fc2.bias"] = rn(vd, vf), torch.zeros(vd)
+    vcfg = dict(VIT_L14, num_hidden_layers=LL, layer_norm_eps=1e-5)
+    _CPU_CACHE["w"] = (sd, cfg, vsd, vcfg, vp)
+    return _cpu_time(R, sd, cfg, vsd, vcfg, vp, rn, g, LL, d)
+
+
+_CPU_CACHE = {}
+
+
+def _cpu_time(R, sd, cfg, vsd, vcfg, vp, rn, g, LL, d):
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        R.clip_vit_hidden(vsd, vp, vcfg, torch.randn((1, 3, 224, 224), generator=g), select_layer=-1)
+        t_vit = time.perf_counter() - t0
+        m = R.LlamaCPU(sd, cfg)
+        t0 = time.perf_counter()
+        m.prefill(rn(1, VISION + TEXT, d))
+        t_pre = time.perf_counter() - t0
+        m8 = R.LlamaCPU(sd, cfg)
+        m8.prefill(rn(BATCH, 64, d))  # short context is enough for the weight-bound decode step
+        tok = torch.zeros(BATCH, dtype=torch.long)
+        t0 = time.perf_counter()
+        for _ in range(4):
+            m8.step(tok)
+        t_dec = (time.perf_counter() - t0) / 4
+    full = BATCH * (23 / LL) * t_vit + BATCH * (32 / LL) * t_pre + NEW * (32 / LL) * t_dec
+    info = {"t_vit_2layers_1img_s": round(t_vit, 3), "t_prefill_2layers_b1_s": round(t_pre, 3),
+            "t_decode_step_2layers_b8_s": round(t_dec, 4), "extrapolated_step_s": round(full, 2)}
+    return BATCH * NEW / full, info
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals, info = [], {}
+    for i in range(args.warmup + args.steps):
+        v, info = cpu_sample(cores)
+        if i >= args.warmup:
+            vals.append(v)
+    v = sum(vals) / len(vals)
+    sample = ("oracle port (fp32 torch CPU restatement of the reference path): ViT-L/14 2/23 layers on 1 image, "
+              "LLaMA-7B 2/32 layers prefill S=768 B=1 + 4 cached decode steps B=8; scaled to full depth and batch 8")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * BATCH * NEW / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample, **info},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "BASELINE.json configs[1]: batch-8 336x336 images (processor output 224x224), ViT-L/14 encode + "
+                        "Vicuna-7B 256-vision + 512-text prefill + 128-token greedy decode, bf16",
+            "global_batch": BATCH * n, "prompt_tokens": VISION + TEXT, "new_tokens": NEW, "parallelism": f"dp{n}",
+            "l2": "inputs_larger_than_L2 (13.5 GB of weights streamed per decode step)", "kv_cache": "paged, 64-token pages"}
+
+
+# =============================================================================== GPU (ours)
+def build_model(device):
+    from vitron_b200 import param_shapes as PS
+    from vitron_b200.vision_tower import VisionConfig
+    from vitron_b200.vitron_model import VitronConfig, VitronLlamaForCausalLM
+    cfg = VitronConfig(llm=VICUNA_7B, vision=VisionConfig(**VIT_L14), tokenizer_model_max_length=4096, eos_token_id=None)
+    model = VitronLlamaForCausalLM(cfg, device, max_batch=BATCH, max_seq_len=VISION + TEXT + NEW)
+    sd = PS.random_state_dict(PS.vitron_shapes(cfg), device, seed=0)
+    model.load_state_dict(sd)
+    del sd
+    torch.cuda.empty_cache()
+    return model
+
+
+def timed(fn, iters):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def roofline_decode_gemm(model, hbm_peak, peak_kind):
+    """Dominant kernel of the step = gemm_bf16_tcgen05_kernel<16,10> streaming the decoder weights at
+    M=8 (swap-AB + split-K, followed by its tiny splitk_reduce_kernel). Timed live: all 128 decode
+    GEMMs of one token (4 per layer, 32 layers = 12.95 GB of distinct weights, >> L2) back to back."""
+    from vitron_b200 import ops
+    eng = model.engine
+    d, f = eng.cfg.hidden_size, eng.cfg.intermediate_size
+    x = torch.randn((BATCH, d), device=eng.device).to(torch.bfloat16)
+    a = torch.randn((BATCH, f), device=eng.device).to(torch.bfloat16)
+
+    def one_token():
+        for L in eng.layers:
+            ops.gemm(x, L["wqkv"])
+            ops.gemm(x, L["wo"])
+            ops.gemm(x, L["wgu"], glu=ops.GLU_SWIGLU)
+            ops.gemm(a, L["wdown"])
+    for _ in range(3):
+        one_token()
+    ms = timed(one_token, 5)
+    n_launch = 4 * len(eng.layers)
+    wbytes = sum(L[k].numel() * 2 for L in eng.layers for k in ("wqkv", "wo", "wgu", "wdown"))
+    abytes = len(eng.layers) * BATCH * 2 * (d * 3 + f + (3 * d + d + f + d))  # activations in + out
+    per_launch = (wbytes + abytes) / n_launch
+    achieved = per_launch / (ms * 1e-3 / n_launch) / 1e9
+    traffic = None
+    pj = os.path.join(ROOT, "profiles", "dominant_kernel.json")
+    if os.path.exists(pj):
+        with open(pj) as fh:
+            traffic = json.load(fh).get("traffic_bytes_per_launch")
+    return {"bound": "hbm", "kernel": "gemm_bf16_tcgen05_kernel<16,10> (+ splitk_reduce_kernel), M=8 decode GEMMs",
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": traffic,
+            "algorithmic_bytes_per_launch": per_launch, "avg_launch_us": ms * 1e3 / n_launch}
+
+
+def run_ours(args, rank, world):
+    from vitron_b200 import _lib, ops
+    lib = _lib.load()
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(device)
+    if not lib.vb200_device_ok():
+        raise RuntimeError("vitron_b200 needs an sm_100 (B200) device")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    model = build_model(device)
+    pixels_h, ids_h = synth_inputs(seed_px=1 + rank, seed_ids=2 + rank)
+    pixels_pin, ids_pin = pixels_h.pin_memory(), ids_h.pin_memory()
+    pixels_d, ids_d = pixels_h.to(device), ids_h.to(device)
+    gathered = torch.zeros((world * BATCH, NEW), dtype=torch.int64, device=device) if world > 1 else None
+
+    def step(px, ids):
+        out = model.generate(ids, images=px, do_sample=False, max_new_tokens=NEW, use_cache=True, sync_every=NEW)
+        new = out[:, ids.shape[1]:]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, new.contiguous())  # the only collective on the path
+        return new
+
+    def step_resident():
+        return step(pixels_d, ids_d)
+
+    def step_e2e():
+        px = pixels_pin.to(device, non_blocking=True)
+        ids = ids_pin.to(device, non_blocking=True)
+        return step(px, ids).cpu()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(device.index or 0)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    l0 = ops.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = (ops.launch_count() - l0) // args.steps
+    if world > 1:
+        dist.barrier()
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    line = None
+    if rank == 0:
+        hbm_peak, tf_peak, kind = measured_peaks()
+        # phase breakdown (diagnostic, separate short loops)
+        eng = model.engine
+        t_vit = timed(lambda: model.encode_images(pixels_d), 3)
+        _, _, _, _, emb, _ = model.prepare_inputs_labels_for_multimodal(ids_d, None, torch.ones_like(ids_d), None, None, pixels_d)
+        t_pre = timed(lambda: eng.prefill(emb), 3)
+        first = ops.argmax_rows(eng.prefill(emb))
+        eng.start_decode(first, NEW)
+        eng.decode_steps(BATCH, 2)
+        t_dec = timed(lambda: eng.decode_steps(BATCH, 1), 64)
+        S = VISION + TEXT
+        pre_flops = BATCH * (12.95e9 * S + 2 * 4096 * 32000 + 32 * 4 * S * S * 4096 / 2)
+        dec_bytes = eng.weight_bytes() + 2 * 32 * 4096 * 2 * (S + NEW / 2) * BATCH
+        roof = roofline_decode_gemm(model, hbm_peak, kind)
+        roof["decode_step"] = {"ms": t_dec, "achieved_gbs": dec_bytes / (t_dec * 1e-3) / 1e9,
+                               "frac": dec_bytes / (t_dec * 1e-3) / 1e9 / hbm_peak}
+        roof["prefill"] = {"ms": t_pre, "achieved_tflops": pre_flops / (t_pre * 1e-3) / 1e12,
+                           "frac_of_bf16_peak": pre_flops / (t_pre * 1e-3) / 1e12 / tf_peak}
+        cpu_v, cpu_info = (None, {})
+        if world == 1:
+            cpu_v, cpu_info = cpu_sample()
+        h2d = pixels_pin.numel() * 4 + ids_pin.numel() * 8
+        d2h = BATCH * NEW * 8
+        line = {"metric": METRIC, "value": world * BATCH * NEW / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(world),
+                "e2e": {"value": world * BATCH * NEW / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                "gpu_launches": launches, "clocks": sampler.result(), "roofline": roof,
+                "phases": {"vit_projector_ms": t_vit, "prefill_ms": t_pre, "decode_ms_per_token": t_dec,
+                           "prefill_tokens_per_s": BATCH * S / (t_pre * 1e-3),
+                           "decode_tokens_per_s": BATCH / (t_dec * 1e-3)}}
+        if cpu_v is not None:
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "oracle port, fp32, ViT 2/23 + LLaMA 2/32 layers (prefill B=1 S=768, 4 decode "
+                                              "steps B=8), scaled to full depth and batch 8", **cpu_info}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    with torch.no_grad():
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -113,7 +113,9 @@ int vb200_attention_short(const void* q, const void* k, const void* v, void* out
                           int64_t H, int64_t S, int64_t head_dim, int64_t q_sb, int64_t q_ss,
                           int64_t q_sh, int64_t k_sb, int64_t k_ss, int64_t k_sh, int64_t v_sb,
                           int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh,
+                          int64_t inner, int64_t q_so, int64_t k_so, int64_t v_so, int64_t o_so,
                           float scale, cudaStream_t stream);
+/* (sequence index s = outer*inner + in lives at outer*x_so + in*x_sb; inner <= 0: single level) */
 
 /* ---- LLaMA decode path (llm.cu) -------------------------------------------------------------
  * Paged KV cache per layer: k_pages / v_pages [num_pages, n_heads, page_size, head_dim] bf16,
@@ -161,6 +163,10 @@ int vb200_upsample2x_nhwc(const void* x, void* out, int64_t nb, int64_t h, int64
 /* out = a + b (bf16, n elements), with optional broadcast period for b */
 int vb200_add_bf16(const void* a, const void* b, void* out, int64_t n, int64_t b_period,
                    cudaStream_t stream);
+/* out[row] = x[row] + table[(row / group_rows) % period] — LanguageBind temporal_embedding add on
+ * '(b t) n d' rows (modeling_video.py:110-113) */
+int vb200_add_rowgroup(const void* x, const void* table, void* out, int64_t rows, int64_t d,
+                       int64_t group_rows, int64_t period, cudaStream_t stream);
 /* classifier-free guidance combine u + s (y - u) in fp32 (diffusion_ddim.py:156-158) */
 int vb200_cfg_combine(const void* y, const void* u, void* out, float scale, int64_t n,
                       cudaStream_t stream);

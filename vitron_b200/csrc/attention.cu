@@ -272,6 +272,8 @@ struct ShortParams {
   const bf16* q; const bf16* k; const bf16* v; bf16* o;
   long long q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh;
   long long nseq; int H, S;
+  long long inner;  // sequence index = outer * inner + in; offset = outer * *_so + in * *_sb
+  long long q_so, k_so, v_so, o_so;
   float scale;
 };
 
@@ -288,9 +290,10 @@ __global__ void __launch_bounds__(WARPS * 32) attn_short_kernel(const ShortParam
   if (item >= p.nseq * p.H) return;
   const long long seq = item / p.H;
   const int h = static_cast<int>(item % p.H);
-  const bf16* qg = p.q + seq * p.q_sb + h * p.q_sh;
-  const bf16* kg = p.k + seq * p.k_sb + h * p.k_sh;
-  const bf16* vg = p.v + seq * p.v_sb + h * p.v_sh;
+  const long long so = seq / p.inner, si = seq % p.inner;
+  const bf16* qg = p.q + so * p.q_so + si * p.q_sb + h * p.q_sh;
+  const bf16* kg = p.k + so * p.k_so + si * p.k_sb + h * p.k_sh;
+  const bf16* vg = p.v + so * p.v_so + si * p.v_sb + h * p.v_sh;
   const int S = p.S;
   // each lane moves 4 bytes; a row of 64 bf16 = 32 lanes x 2 elements (fully coalesced 128 B)
   for (int s = 0; s < S; ++s) {
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_short_kernel(const ShortParam
     for (int j = 0; j < S; ++j) sp[warp][lane][j] *= inv;
   }
   __syncwarp();
-  bf16* og = p.o + seq * p.o_sb + h * p.o_sh;
+  bf16* og = p.o + so * p.o_so + si * p.o_sb + h * p.o_sh;
   for (int i = 0; i < S; ++i) {
     float a0 = 0.f, a1 = 0.f;
     for (int j = 0; j < S; ++j) {
@@ -370,9 +373,12 @@ extern "C" int vb200_attention_short(const void* q, const void* k, const void* v
                                      int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb,
                                      int64_t k_ss, int64_t k_sh, int64_t v_sb, int64_t v_ss,
                                      int64_t v_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh,
-                                     float scale, cudaStream_t stream) {
+                                     int64_t inner, int64_t q_so, int64_t k_so, int64_t v_so,
+                                     int64_t o_so, float scale, cudaStream_t stream) {
   VB_CHECK_ARG(q && k && v && out);
   VB_CHECK_ARG(nseq > 0 && H > 0 && S > 0 && S <= 32 && head_dim == 64);
+  if (inner <= 0) { inner = nseq; q_so = k_so = v_so = o_so = 0; }
+  VB_CHECK_ARG(q_so % 2 == 0 && k_so % 2 == 0 && v_so % 2 == 0 && o_so % 2 == 0);
   const int64_t strides[12] = {q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh};
   for (int i = 0; i < 12; ++i) VB_CHECK_ARG(strides[i] % 2 == 0);
   ShortParams p;
@@ -381,6 +387,7 @@ extern "C" int vb200_attention_short(const void* q, const void* k, const void* v
   p.q_sb = q_sb; p.q_ss = q_ss; p.q_sh = q_sh; p.k_sb = k_sb; p.k_ss = k_ss; p.k_sh = k_sh;
   p.v_sb = v_sb; p.v_ss = v_ss; p.v_sh = v_sh; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sh = o_sh;
   p.nseq = nseq; p.H = (int)H; p.S = (int)S; p.scale = scale;
+  p.inner = inner; p.q_so = q_so; p.k_so = k_so; p.v_so = v_so; p.o_so = o_so;
   const long long items = nseq * H;
   if (S <= 8) attn_short_kernel<8, 4><<<static_cast<unsigned>((items + 3) / 4), 128, 0, stream>>>(p);
   else if (S <= 16) attn_short_kernel<16, 4><<<static_cast<unsigned>((items + 3) / 4), 128, 0, stream>>>(p);

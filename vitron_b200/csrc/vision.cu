@@ -96,6 +96,23 @@ __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict_
   out[idx] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+__global__ void add_rowgroup_kernel(const uint4* __restrict__ x, const uint4* __restrict__ table, uint4* __restrict__ out,
+                                    long long nvec, int dv, long long group_rows, long long period) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= nvec) return;
+  const long long row = idx / dv;
+  const int c = static_cast<int>(idx % dv);
+  const uint4 a = x[idx], b = table[((row / group_rows) % period) * dv + c];
+  const uint32_t xs[4] = {a.x, a.y, a.z, a.w}, ys[4] = {b.x, b.y, b.z, b.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f = unpack_bf16(xs[j]), g = unpack_bf16(ys[j]);
+    o[j] = pack_bf16(f.x + g.x, f.y + g.y);
+  }
+  out[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 __global__ void cfg_kernel(const float* __restrict__ y, const float* __restrict__ u, float* __restrict__ out,
                            float s, long long n) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -250,6 +267,18 @@ extern "C" int vb200_add_bf16(const void* a, const void* b, void* out, int64_t n
   add_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<uint4*>(out), n / 8,
       b_period / 8);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+extern "C" int vb200_add_rowgroup(const void* x, const void* table, void* out, int64_t rows, int64_t d,
+                                  int64_t group_rows, int64_t period, cudaStream_t stream) {
+  VB_CHECK_ARG(x && table && out && rows >= 0 && d > 0 && d % 8 == 0 && group_rows > 0 && period > 0);
+  if (rows == 0) return VB_OK;
+  const long long nvec = rows * (d / 8);
+  add_rowgroup_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(table), reinterpret_cast<uint4*>(out), nvec,
+      static_cast<int>(d / 8), group_rows, period);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }

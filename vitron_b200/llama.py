@@ -121,9 +121,11 @@ class LlamaEngine:
         self.d_bot = torch.arange(B, dtype=torch.int32, device=dev)
         self.d_next = torch.zeros((B,), dtype=torch.int64, device=dev)
         self.d_logits = torch.zeros((B, c.vocab_size), dtype=torch.float32, device=dev)
-        self.token_log = None
-        self._graph = None
-        self._graph_batch = 0
+        # generated ids land here (column = tokens generated so far); persistent so the decode
+        # graph survives across generate() calls
+        self.token_log = torch.zeros((B, self.cache.max_seq_len), dtype=torch.int64, device=dev)
+        self._graphs = {}
+        self.launches_per_step = 0
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, sd, prefix=""):
@@ -149,7 +151,7 @@ class LlamaEngine:
                 wo=get(p + "self_attn.o_proj.weight").contiguous(),
                 ln2=get(p + "post_attention_layernorm.weight").contiguous(), wgu=wgu,
                 wdown=get(p + "mlp.down_proj.weight").contiguous()))
-        self._graph = None
+        self._graphs = {}
         return self
 
     def init_random(self, seed=0, std=0.02):
@@ -171,7 +173,7 @@ class LlamaEngine:
                 ln2=ones(c.hidden_size),
                 wgu=ops.pack_glu_weight(w(c.intermediate_size, c.hidden_size), w(c.intermediate_size, c.hidden_size)),
                 wdown=w(c.hidden_size, c.intermediate_size)))
-        self._graph = None
+        self._graphs = {}
         return self
 
     def weight_bytes(self):
@@ -275,10 +277,8 @@ class LlamaEngine:
             changed |= self.cache.reserve(b, self._lens_host[b] + max_new_tokens)
         if changed:
             self.cache.sync_table()
-        self.token_log = torch.zeros((self.max_batch, max_new_tokens), dtype=torch.int64, device=dev)
         self.token_log[:B, 0] = first_tokens
         self.d_src[:B] = first_tokens.to(torch.int32)
-        self._graph = None
 
     def decode_steps(self, B, n, use_graph=True):
         """Run n greedy decode steps for slots 0..B-1 (no host sync)."""
@@ -288,7 +288,7 @@ class LlamaEngine:
             for _ in range(n):
                 self._step_kernels(B)
             return
-        if self._graph is None or self._graph_batch != B:
+        if B not in self._graphs:
             # warm-up on a side stream (allocator + lazy init), then capture
             s = torch.cuda.Stream(device=self.device)
             s.wait_stream(torch.cuda.current_stream())
@@ -300,13 +300,17 @@ class LlamaEngine:
             for t, sv in zip((self.d_src, self.d_pos, self.d_len, self.token_log), saved):
                 t.copy_(sv)
             g = torch.cuda.CUDAGraph()
+            l0 = ops.launch_count()
             with torch.cuda.graph(g):
                 self._step_kernels(B)
+            self.launches_per_step = ops.launch_count() - l0
             for t, sv in zip((self.d_src, self.d_pos, self.d_len, self.token_log), saved):
                 t.copy_(sv)
-            self._graph, self._graph_batch = g, B
+            self._graphs[B] = g
+        g = self._graphs[B]
         for _ in range(n):
-            self._graph.replay()
+            g.replay()
+        ops.count_launches(n * self.launches_per_step)
 
     def decode_one_logits(self, tokens):
         """Non-greedy path: feed tokens [B] and return fp32 logits [B, V] (sampling done by caller)."""

@@ -14,6 +14,16 @@ from ._lib import (ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_RELU, ACT_SILU, GLU_G
 
 BF16 = torch.bfloat16
 _ws = {}
+_launches = [0]
+
+
+def launch_count():
+    """Number of vitron_b200 kernels enqueued so far through this module (bench.py: gpu_launches)."""
+    return _launches[0]
+
+
+def count_launches(n):
+    _launches[0] += int(n)
 
 
 def _stream():
@@ -96,6 +106,7 @@ def gemm(a, w, bias=None, act=ACT_NONE, glu=GLU_NONE, residual=None, alpha=1.0, 
     ws = workspace(need, a.device) if need else None
     check(lib.vb200_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), w.stride(0), out2.data_ptr(), ldo, M, N, K,
                               C.byref(epi), _ptr(ws), need, _stream()), "vb200_gemm_bf16")
+    _launches[0] += 2 if M <= 64 else 1
     return out.reshape(*a.shape[:-1], n_out) if a.dim() != 2 else out
 
 
@@ -139,6 +150,7 @@ def conv_nhwc(x, wt, kh, kw, stride=1, pad_h=None, pad_w=None, bias=None, act=AC
         epi.ldr = n_out
     check(lib.vb200_conv_nhwc_bf16(x.data_ptr(), wt.data_ptr(), out.data_ptr(), nb, h, w, cin, cout, kh, kw,
                                    stride, pad_h, pad_w, C.byref(epi), _stream()), "vb200_conv_nhwc_bf16")
+    _launches[0] += 1
     return out
 
 
@@ -154,6 +166,7 @@ def conv_nhwc_direct(x, w_khwc, bias, kh, kw, stride=1, pad_h=None, pad_w=None):
     out = torch.empty((nb, ho, wo, cout), dtype=BF16, device=x.device)
     check(lib.vb200_conv_nhwc_direct(x.data_ptr(), w_khwc.data_ptr(), _ptr(bias), out.data_ptr(), nb, h, w, cin,
                                      cout, kh, kw, stride, pad_h, pad_w, _stream()), "vb200_conv_nhwc_direct")
+    _launches[0] += 1
     return out
 
 
@@ -164,6 +177,7 @@ def rmsnorm(x, weight, eps, out=None):
     o2, ldo = _rows2d(out)
     check(lib.vb200_rmsnorm(x2.data_ptr(), ldx, weight.data_ptr(), o2.data_ptr(), ldo, x2.shape[0], x2.shape[1],
                             float(eps), _stream()), "vb200_rmsnorm")
+    _launches[0] += 1
     return out
 
 
@@ -175,6 +189,7 @@ def layernorm(x, weight, bias, eps, out=None):
     o2, ldo = _rows2d(out)
     check(lib.vb200_layernorm(x2.data_ptr(), ldx, weight.data_ptr(), _ptr(bias), o2.data_ptr(), ldo, x2.shape[0],
                               x2.shape[1], float(eps), _stream()), "vb200_layernorm")
+    _launches[0] += 1
     return out
 
 
@@ -191,6 +206,7 @@ def groupnorm_nhwc(x, weight, bias, groups, eps, act=ACT_NONE, n=None, out=None)
     check(lib.vb200_groupnorm_nhwc(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), n, spatial, c,
                                    groups, float(eps), int(act), ws.data_ptr(), need, _stream()),
           "vb200_groupnorm_nhwc")
+    _launches[0] += 2
     return out
 
 
@@ -221,19 +237,45 @@ def attention(q, k, v, scale=None, causal=False, kv_len=None, mask=None, out=Non
     check(lib.vb200_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Sq, Skv, D,
                               *_bsh(q), *_bsh(k), *_bsh(v), *_bsh(out), float(scale), 1 if causal else 0,
                               _ptr(kv_len), m_ptr, m_sb, m_sh, m_sq, _stream()), "vb200_attention")
+    _launches[0] += 1
     return out
 
 
 def attention_short(q, k, v, scale=None, out=None):
-    """q/k/v [nseq, S, H, 64] strided views, S <= 32."""
+    """q/k/v [nseq, S, H, 64] or [outer, inner, S, H, 64] strided views (sequence = leading dims),
+    S <= 32. out defaults to a fresh tensor of q's shape."""
     lib = _lib.load()
-    nseq, S, H, D = q.shape
-    scale = 1.0 / math.sqrt(D) if scale is None else scale
+    scale = 1.0 / math.sqrt(q.shape[-1]) if scale is None else scale
     if out is None:
-        out = torch.empty((nseq, S, H, D), dtype=BF16, device=q.device)
+        out = torch.empty(q.shape, dtype=BF16, device=q.device)
+    if q.dim() == 4:
+        nseq, S, H, D = q.shape
+        inner, so = 0, (0, 0, 0, 0)
+        b3 = [_bsh(t) for t in (q, k, v, out)]
+    else:
+        _req(q.dim() == 5, "expect 4-D or 5-D q")
+        outer, inner, S, H, D = q.shape
+        nseq = outer * inner
+        so = tuple(t.stride(0) for t in (q, k, v, out))
+        for t in (q, k, v, out):
+            _req(t.stride(4) == 1, "contiguous head dim")
+        b3 = [(t.stride(1), t.stride(2), t.stride(3)) for t in (q, k, v, out)]
     check(lib.vb200_attention_short(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), nseq, H, S, D,
-                                    *_bsh(q), *_bsh(k), *_bsh(v), *_bsh(out), float(scale), _stream()),
+                                    *b3[0], *b3[1], *b3[2], *b3[3], inner, *so, float(scale), _stream()),
           "vb200_attention_short")
+    _launches[0] += 1
+    return out
+
+
+def add_rowgroup(x, table, group_rows, period, out=None):
+    """x [rows, d] + table[(row // group_rows) % period]."""
+    lib = _lib.load()
+    x2, _ = _rows2d(x)
+    _req(x.is_contiguous() and table.is_contiguous(), "contiguous")
+    out = torch.empty_like(x) if out is None else out
+    check(lib.vb200_add_rowgroup(x2.data_ptr(), table.data_ptr(), out.data_ptr(), x2.shape[0], x2.shape[1],
+                                 group_rows, period, _stream()), "vb200_add_rowgroup")
+    _launches[0] += 1
     return out
 
 
@@ -246,6 +288,7 @@ def rope_kv_append(qkv, positions, n_heads, head_dim, theta, k_pages=None, v_pag
                                    _ptr(slot_of_token), _ptr(k_pages), _ptr(v_pages), _ptr(block_table),
                                    max_pages, q2.shape[0], n_heads, head_dim, page_size, float(theta), _stream()),
           "vb200_rope_kv_append")
+    _launches[0] += 1
     return qkv
 
 
@@ -263,6 +306,7 @@ def attn_decode_paged(q, k_pages, v_pages, block_table, kv_len, n_heads, head_di
                                       block_table.data_ptr(), block_table.shape[1], kv_len.data_ptr(),
                                       out.data_ptr(), out.stride(0), B, n_heads, head_dim, page_size, max_kv_len,
                                       float(scale), ws.data_ptr(), need, _stream()), "vb200_attn_decode_paged")
+    _launches[0] += 1 if max_kv_len <= 256 else 2
     return out
 
 
@@ -275,6 +319,7 @@ def splice_multimodal(embed, feats, srcmap, out=None):
     nfeat = 0 if feats is None else feats.shape[0]
     check(lib.vb200_splice_multimodal(embed.data_ptr(), embed.shape[0], _ptr(feats), nfeat, srcmap.data_ptr(),
                                       out.data_ptr(), rows, d, _stream()), "vb200_splice_multimodal")
+    _launches[0] += 1
     return out
 
 
@@ -285,6 +330,7 @@ def argmax_rows(logits, out=None):
         out = torch.empty((l2.shape[0],), dtype=torch.int64, device=logits.device)
     check(lib.vb200_argmax_rows(l2.data_ptr(), 1 if l2.dtype == torch.float32 else 0, ld, l2.shape[0], l2.shape[1],
                                 out.data_ptr(), _stream()), "vb200_argmax_rows")
+    _launches[0] += 1
     return out
 
 
@@ -295,6 +341,7 @@ def argmax_advance(logits, out_idx, next_src=None, positions=None, kv_len=None, 
                                    out_idx.data_ptr(), _ptr(next_src), _ptr(positions), _ptr(kv_len),
                                    _ptr(token_log), token_log.shape[1] if token_log is not None else 0,
                                    _ptr(prompt_len), _stream()), "vb200_argmax_advance")
+    _launches[0] += 1
     return out_idx
 
 
@@ -306,6 +353,7 @@ def patchify(pixels, patch, kpad):
     out = torch.empty((nb * (h // patch) * (w // patch), kpad), dtype=BF16, device=pixels.device)
     check(lib.vb200_patchify(pixels.data_ptr(), 1 if pixels.dtype == torch.float32 else 0, out.data_ptr(), nb, c, h,
                              w, patch, kpad, _stream()), "vb200_patchify")
+    _launches[0] += 1
     return out
 
 
@@ -316,6 +364,7 @@ def vit_embed_ln(patch_out, cls, pos, ln_w, ln_b, nb, npatch, eps):
     check(lib.vb200_vit_embed_ln(patch_out.data_ptr(), cls.data_ptr(), pos.data_ptr(), ln_w.data_ptr(),
                                  ln_b.data_ptr(), out.data_ptr(), nb, npatch, d, float(eps), _stream()),
           "vb200_vit_embed_ln")
+    _launches[0] += 1
     return out
 
 
@@ -324,6 +373,7 @@ def upsample2x_nhwc(x):
     nb, h, w, c = x.shape
     out = torch.empty((nb, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
     check(lib.vb200_upsample2x_nhwc(x.data_ptr(), out.data_ptr(), nb, h, w, c, _stream()), "vb200_upsample2x_nhwc")
+    _launches[0] += 1
     return out
 
 
@@ -335,6 +385,7 @@ def add(a, b, out=None):
     period = 0 if b.numel() == a.numel() else b.numel()
     check(lib.vb200_add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), period, _stream()),
           "vb200_add_bf16")
+    _launches[0] += 1
     return out
 
 
@@ -344,6 +395,7 @@ def cfg_combine(y, u, scale):
     out = torch.empty_like(y)
     check(lib.vb200_cfg_combine(y.data_ptr(), u.data_ptr(), out.data_ptr(), float(scale), y.numel(), _stream()),
           "vb200_cfg_combine")
+    _launches[0] += 1
     return out
 
 
@@ -355,6 +407,7 @@ def region_mask_pool(feats, boxes, image_size):
     out = torch.empty((B, c), dtype=BF16, device=feats.device)
     check(lib.vb200_region_mask_pool(feats.data_ptr(), boxes.data_ptr(), out.data_ptr(), B, g, c, image_size,
                                      _stream()), "vb200_region_mask_pool")
+    _launches[0] += 1
     return out
 
 
@@ -365,4 +418,5 @@ def seem_attn_mask(mask_logits, h2, w2):
     out = torch.empty((Q, h2 * w2), dtype=torch.uint8, device=mask_logits.device)
     check(lib.vb200_seem_attn_mask(mask_logits.data_ptr(), out.data_ptr(), Q, H, W, h2, w2, _stream()),
           "vb200_seem_attn_mask")
+    _launches[0] += 1
     return out
