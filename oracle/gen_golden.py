@@ -19,9 +19,9 @@ VIT_TINY = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num
                 patch_size=14)
 
 
-def _load_seeded(model, seed):
+def _load_seeded(model, seed, gain=0.8):
     shapes = shapes_of(model)
-    sd = seeded_state_dict(shapes, seed)
+    sd = seeded_state_dict(shapes, seed, gain)
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected, unexpected
     # only non-persistent buffers (rotary inv_freq, position_ids) may be absent
@@ -73,7 +73,59 @@ def gen_vitron_llm(seed=11):
     print("vitron_llm_tiny.pt", {k: (tuple(v["logits"].shape) if isinstance(v, dict) and "logits" in v else "") for k, v in out.items() if isinstance(v, dict)})
 
 
-GENERATORS = {"vitron_llm": gen_vitron_llm}
+UNET_TINY = dict(in_dim=4, concat_dim=4, dim=64, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2], num_heads=2, head_dim=64,
+                 num_res_blocks=1, attn_scales=[1.0, 0.5], num_tokens=4)
+
+
+def gen_unet(seed=21):
+    """UNetSD_I2VGen forward (b=2, f=4, 8x16 latent) + 3 DDIM steps with CFG through the reference."""
+    U = refshim.i2vgen_unet_class()
+    model = U(**UNET_TINY, dropout=0.1, temporal_attention=True, temporal_attn_times=1, use_checkpoint=False,
+              use_fps_condition=True, use_sim_mask=False, training=False, inpainting=True).eval()
+    shapes = _load_seeded(model, seed, gain=0.4)
+    g = torch.Generator().manual_seed(seed)
+    b, f, h, w = 2, 4, 8, 16
+    rn = lambda *s: torch.randn(s, generator=g)
+    inp = dict(x=rn(b, 4, f, h, w), t=torch.tensor([500, 37]), y=rn(b, 77, 1024), image=rn(b, 1, 1024),
+               local_image=rn(b, 4, f, h, w), fps=torch.tensor([8, 16]))
+    out = {"cfg": UNET_TINY, "seed": seed, "gain": 0.4, "shapes": shapes, "inputs": inp}
+    with torch.no_grad():
+        out["out"] = model(**inp).float()
+        D = refshim.i2vgen_ddim_class()
+        diff = D(schedule="cosine", schedule_param=dict(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True),
+                 mean_type="v", loss_type="mse", var_type="fixed_small", rescale_timesteps=False, noise_strength=0.1)
+        noise = rn(1, 4, f, h, w)
+        cond = dict(y=inp["y"][:1], image=inp["image"][:1], local_image=inp["local_image"][:1], fps=inp["fps"][:1])
+        unc = dict(y=inp["y"][1:], image=torch.zeros_like(inp["image"][:1]), local_image=inp["local_image"][:1], fps=inp["fps"][:1])
+        vid = diff.ddim_sample_loop(noise=noise, model=model, model_kwargs=[cond, unc], guide_scale=9.0, ddim_timesteps=4, eta=0.0)
+        out["ddim"] = dict(noise=noise, cond=cond, uncond=unc, guide_scale=9.0, ddim_timesteps=4, out=vid.float())
+    torch.save(out, os.path.join(OUT, "unet_tiny.pt"))
+    print("unet_tiny.pt", tuple(out["out"].shape), float(out["out"].abs().max()), tuple(vid.shape), float(vid.abs().max()))
+
+
+def gen_gligen(seed=31):
+    """GatedSelfAttentionDense + BasicTransformerBlock(fuser=gatedSA) at the three GLIGEN head sizes."""
+    att = refshim.gligen_attention()
+    g = torch.Generator().manual_seed(seed)
+    ctx = torch.randn((2, 20, 768), generator=g)
+    objs = torch.randn((2, 30, 768), generator=g)
+    out = {"seed": seed, "context": ctx, "objs": objs, "cases": []}
+    for (N, C, heads) in ((64, 320, 8), (36, 640, 8), (16, 1280, 8)):
+        dh = C // heads
+        blk = att.BasicTransformerBlock(C, 768, 768, heads, dh, "gatedSA", use_checkpoint=False).eval()
+        shapes = shapes_of(blk)
+        sd = seeded_state_dict(shapes, seed)
+        blk.load_state_dict(sd)
+        x = torch.randn((2, N, C), generator=g)
+        with torch.no_grad():
+            fo = blk.fuser(x, objs)
+            bo = blk(x, ctx, objs)
+        out["cases"].append(dict(N=N, C=C, heads=heads, shapes=shapes, x=x, fuser_out=fo, block_out=bo))
+    torch.save(out, os.path.join(OUT, "gligen_tiny.pt"))
+    print("gligen_tiny.pt", [tuple(c["block_out"].shape) for c in out["cases"]])
+
+
+GENERATORS = {"vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen}
 
 
 def main(argv):

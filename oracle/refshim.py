@@ -232,6 +232,14 @@ def i2vgen_unet_class():
     return mod.UNetSD_I2VGen
 
 
+def i2vgen_ddim_class():
+    setup_i2vgen()
+    base = os.path.join(REF, "modules/i2vgen-xl")
+    _pkg("tools.modules.diffusions", os.path.join(base, "tools/modules/diffusions"))
+    mod = importlib.import_module("tools.modules.diffusions.diffusion_ddim")
+    return mod.DiffusionDDIM
+
+
 def gligen_attention():
     return load_file("ref_gligen_attention", "modules/GLIGEN/demo/gligen/ldm/modules/attention.py")
 

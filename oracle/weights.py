@@ -18,7 +18,7 @@ def _is_norm_weight(name, shape):
     return n.endswith("weight") and any(k in n for k in ("norm", "ln", "layrnorm", ".gn", "bn"))
 
 
-def seeded_tensor(name, shape, seed):
+def seeded_tensor(name, shape, seed, gain=0.8):
     g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63 - 1))
     shape = tuple(shape)
     if len(shape) == 0:
@@ -28,16 +28,17 @@ def seeded_tensor(name, shape, seed):
     if len(shape) == 1:
         return 0.05 * torch.randn(shape, generator=g)
     n = name.lower()
-    if "embed" in n or "embedding" in n:
-        return 0.5 * torch.randn(shape, generator=g)
+    if any(k in n for k in ("embed_tokens", "position_embedding", "class_embedding", "temporal_embedding",
+                            "query_feat", "query_embed", "level_embed")):
+        return 0.5 * torch.randn(shape, generator=g)  # lookup tables / learned tokens, not projections
     fan_in = 1
     for s in shape[1:]:
         fan_in *= s
-    return torch.randn(shape, generator=g) * (0.8 / fan_in ** 0.5)
+    return torch.randn(shape, generator=g) * (gain / fan_in ** 0.5)
 
 
-def seeded_state_dict(shapes, seed):
-    return {k: seeded_tensor(k, v, seed) for k, v in sorted(shapes.items())}
+def seeded_state_dict(shapes, seed, gain=0.8):
+    return {k: seeded_tensor(k, v, seed, gain) for k, v in sorted(shapes.items())}
 
 
 def shapes_of(module_or_sd):

@@ -100,3 +100,40 @@ def test_cached_decoder_equals_full_recompute(fx, sd):
     lg2 = m.step(tok)
     emb2 = torch.cat([emb, sdf["model.embed_tokens.weight"][tok][:, None]], 1)
     assert torch.allclose(lg2, R.llama_forward(sdf, c["llm"], emb2)[:, -1], atol=1e-4, rtol=1e-4)
+
+
+# ------------------------------------------------------------------ i2vgen-xl UNet3D + DDIM
+@pytest.fixture(scope="module")
+def ufx():
+    return load("unet_tiny.pt")
+
+
+def test_unet_restatement_matches_reference_golden(ufx):
+    from oracle import restate_unet as U
+    sd = seeded_state_dict(ufx["shapes"], ufx["seed"], ufx["gain"])
+    i = ufx["inputs"]
+    out = U.unet_forward(sd, ufx["cfg"], i["x"], i["t"], y=i["y"], image=i["image"], local_image=i["local_image"], fps=i["fps"])
+    ref = ufx["out"]
+    assert out.shape == ref.shape
+    assert torch.allclose(out, ref, atol=1e-3 * ref.abs().max().item(), rtol=1e-3), (out - ref).abs().max()
+
+
+def test_ddim_restatement_matches_reference_golden(ufx):
+    from oracle import restate_unet as U
+    sd = seeded_state_dict(ufx["shapes"], ufx["seed"], ufx["gain"])
+    d = ufx["ddim"]
+    model = lambda xt, t, **kw: U.unet_forward(sd, ufx["cfg"], xt, t, **kw)
+    out = U.ddim_sample_loop(d["noise"], model, [d["cond"], d["uncond"]], d["guide_scale"], d["ddim_timesteps"])
+    assert torch.allclose(out, d["out"], atol=2e-3, rtol=2e-3), (out - d["out"]).abs().max()
+
+
+# ------------------------------------------------------------------ GLIGEN gated self-attention
+def test_gligen_restatement_matches_reference_golden():
+    from oracle import restate_gligen as G
+    fx = load("gligen_tiny.pt")
+    for c in fx["cases"]:
+        sd = seeded_state_dict(c["shapes"], fx["seed"])
+        fo = G.gated_self_attention_dense(sd, "fuser.", c["x"], fx["objs"], c["heads"])
+        assert torch.allclose(fo, c["fuser_out"], atol=1e-4, rtol=1e-4)
+        bo = G.basic_transformer_block(sd, "", c["x"], fx["context"], fx["objs"], c["heads"])
+        assert torch.allclose(bo, c["block_out"], atol=1e-4, rtol=1e-4)
