@@ -241,6 +241,24 @@ def roofline_decode_gemm(model, hbm_peak, peak_kind):
             "algorithmic_bytes_per_launch": per_launch, "avg_launch_us": ms * 1e3 / n_launch}
 
 
+def run_profile():
+    """Same step as the benchmark but short and without the CUDA graph, so that
+    `ncu --metrics gpu__time_duration.sum` lists every kernel once: ViT + projector, prefill
+    (B=8, S=768), then 4 decode tokens (the benchmark runs 127; scale the decode rows by 127/4)."""
+    from vitron_b200 import ops
+    device = torch.device("cuda:0")
+    model = build_model(device)
+    pixels, ids = synth_inputs()
+    pixels, ids = pixels.to(device), ids.to(device)
+    _, _, _, _, emb, _ = model.prepare_inputs_labels_for_multimodal(ids, None, torch.ones_like(ids), None, None, pixels)
+    eng = model.engine
+    first = ops.argmax_rows(eng.prefill(emb))
+    eng.start_decode(first, NEW)
+    eng.decode_steps(BATCH, 4, use_graph=False)
+    torch.cuda.synchronize()
+    print(json.dumps({"profile": "ok", "tokens": eng.token_log[:BATCH, :5].tolist()}))
+
+
 def run_ours(args, rank, world):
     from vitron_b200 import _lib, ops
     lib = _lib.load()
@@ -256,13 +274,13 @@ def run_ours(args, rank, world):
     pixels_h, ids_h = synth_inputs(seed_px=1 + rank, seed_ids=2 + rank)
     pixels_pin, ids_pin = pixels_h.pin_memory(), ids_h.pin_memory()
     pixels_d, ids_d = pixels_h.to(device), ids_h.to(device)
-    gathered = torch.zeros((world * BATCH, NEW), dtype=torch.int64, device=device) if world > 1 else None
+    from vitron_b200.dist import gather_results
 
     def step(px, ids):
         out = model.generate(ids, images=px, do_sample=False, max_new_tokens=NEW, use_cache=True, sync_every=NEW)
         new = out[:, ids.shape[1]:]
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, new.contiguous())  # the only collective on the path
+        if world > 1:  # the only collective on the path: per-request results, NCCL all_gather
+            return gather_results(new.contiguous(), world * BATCH)
         return new
 
     def step_resident():
@@ -345,6 +363,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile", action="store_true",
+                    help="ncu launch-list mode: one un-graphed step with 4 decode tokens, no timing loops")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -354,7 +374,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     with torch.no_grad():
-        run_ours(args, rank, world)
+        if args.profile:
+            run_profile()
+        else:
+            run_ours(args, rank, world)
 
 
 if __name__ == "__main__":

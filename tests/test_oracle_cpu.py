@@ -137,3 +137,81 @@ def test_gligen_restatement_matches_reference_golden():
         assert torch.allclose(fo, c["fuser_out"], atol=1e-4, rtol=1e-4)
         bo = G.basic_transformer_block(sd, "", c["x"], fx["context"], fx["objs"], c["heads"])
         assert torch.allclose(bo, c["block_out"], atol=1e-4, rtol=1e-4)
+
+
+# ------------------------------------------------------------------ SEEM (piecewise pin; detectron2 absent)
+REF_SEEM = "/root/reference/modules/SEEM/demo_code/xdecoder"
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF_SEEM), reason="reference tree not present")
+
+
+@needs_ref
+def test_seem_position_embedding_matches_reference():
+    from oracle import refshim, restate_seem as S
+    pe = refshim.load_file("ref_seem_pe", "modules/SEEM/demo_code/xdecoder/modules/position_encoding.py")
+    x = torch.zeros((2, 8, 5, 7))
+    ref = pe.PositionEmbeddingSine(32, normalize=True)(x)
+    assert torch.allclose(S.position_embedding_sine(x, 32), ref, atol=1e-6)
+    # the product's own closed form (device-side cache) must agree too
+    from vitron_b200.seem import position_embedding_sine as prod_pe
+    got = prod_pe(5, 7, 32, torch.device("cpu")).view(5, 7, 64).permute(2, 0, 1)
+    assert torch.allclose(got, ref[0], atol=1e-6)
+
+
+@needs_ref
+def test_seem_attention_matches_reference_mha():
+    from oracle import refshim, restate_seem as S
+    att = refshim.load_file("ref_seem_attn", "modules/SEEM/demo_code/xdecoder/body/decoder/utils/attn.py")
+    torch.manual_seed(0)
+    C, H, L, S_, B = 64, 4, 5, 9, 2
+    m = att.MultiheadAttention(C, H, dropout=0.0).eval()
+    sd = {"x." + k: v for k, v in m.state_dict().items()}
+    q, k, v = torch.randn(L, B, C), torch.randn(S_, B, C), torch.randn(S_, B, C)
+    mask = torch.rand(B * H, L, S_) < 0.5
+    mask[3] = True  # fully masked head-rows -> nan_to_num() -> zeros
+    with torch.no_grad():
+        ref = m(q, k, v, attn_mask=mask)[0]
+    assert torch.allclose(S.mha(q, k, v, sd, "x.", H, mask), ref, atol=1e-5)
+
+
+@needs_ref
+def test_seem_mask_rule_and_prepare_features_match_reference():
+    from oracle import refshim, restate_seem as S
+    ads = refshim.load_file("ref_seem_ads", "modules/SEEM/demo_code/xdecoder/body/decoder/utils/attention_data_struct.py")
+    utl = refshim.load_file("ref_seem_utils", "modules/SEEM/demo_code/xdecoder/body/decoder/utils/utils.py")
+    pe = refshim.load_file("ref_seem_pe2", "modules/SEEM/demo_code/xdecoder/modules/position_encoding.py")
+    arch = {"VARIABLE": {"queries": ["object"]}, "SELF_ATTENTION": {"queries": {"object": ["queries_object"]}},
+            "CROSS_ATTENTION": {"queries": {"object": True}}, "MASKING": [], "DUPLICATION": {}, "NUM_LAYERS": 1}
+    d = ads.AttentionDataStruct(arch, {"mask": True, "bbox": False, "spatial": False, "grounding": False, "audio": False, "visual": False})
+    d.reset({}, "seg", {})
+    Q, N = 6, 12
+    d.set("queries_object", "queries", torch.zeros(Q, 1, 4), torch.zeros(Q, 1, 4))
+    d.cross_attn_variables()
+    am = torch.rand(2, Q, N) < 0.6
+    am[1, 2] = True
+    d.set_results({"attn_mask": am.clone(), "predictions_class": None, "predictions_mask": None, "predictions_maskemb": None})
+    ref = d.cross_attn_mask((3, 4), 2)
+    mine = am.clone()
+    mine[torch.where(mine.sum(-1) == mine.shape[-1])] = False
+    assert torch.equal(ref, mine) and not ref[1, 2].any()
+    # prepare_features
+    import torch.nn as nn
+    xs = [torch.randn(1, 8, 3, 4), torch.randn(1, 8, 6, 8), torch.randn(1, 8, 12, 16)]
+    lvl = nn.Embedding(3, 8)
+    src, pos, sizes = utl.prepare_features(xs, 3, pe.PositionEmbeddingSine(4, normalize=True), [nn.Sequential()] * 3, lvl)
+    for i in range(3):
+        assert torch.allclose(pos[i], S.position_embedding_sine(xs[i], 4).flatten(2).permute(2, 0, 1), atol=1e-6)
+        assert torch.allclose(src[i], (xs[i].flatten(2) + lvl.weight[i][None, :, None]).permute(2, 0, 1))
+
+
+def test_seem_restatement_runs_and_is_self_consistent():
+    """Shapes / key names of the seg-path output dict (attention_data_struct.py:12-28,250-264)."""
+    from oracle import restate_seem as S
+    shapes = S.seem_shapes(in_channels=(16, 24, 32, 40), C=64, ffn=96, Q=7, enc_layers=1, dec_layers=3, dim_proj=32)
+    sd = seeded_state_dict(shapes, 1)
+    g = torch.Generator().manual_seed(0)
+    feats = {f"res{i + 2}": torch.randn((1, c, 32 >> i, 48 >> i), generator=g) for i, c in enumerate((16, 24, 32, 40))}
+    mf, enc, multi = S.pixel_decoder_forward(sd, feats, "pixel_decoder.", nheads=2, enc_layers=1)
+    assert mf.shape == (1, 64, 32, 48) and [tuple(m.shape[-2:]) for m in multi] == [(4, 6), (8, 12), (16, 24)]
+    out = S.mask_decoder_forward(sd, multi, mf, "predictor.", heads=2, num_layers=3, t_emb=torch.randn(5, 32), logit_scale=1.0)
+    assert out["pred_logits"].shape == (1, 7, 5) and out["pred_masks"].shape == (1, 7, 32, 48)
+    assert len(out["aux_outputs"]) == 3 and out["pred_maskembs"].shape == (1, 7, 64)
