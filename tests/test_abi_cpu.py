@@ -1,0 +1,108 @@
+"""CPU (no GPU): the C-ABI library builds/loads and exports every symbol include/vitron_b200.h declares;
+the ctypes signature table covers exactly those symbols; argument validation works without a device;
+host-side splice layout equals the oracle's restatement of the reference loop."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vitron_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "vitron_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vb200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from vitron_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 27
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/vitron_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, set(_lib.SIGNATURES) ^ set(syms)
+    assert b"sm_100a" in lib.vb200_version()
+
+
+def test_argument_validation_without_device(lib):
+    import ctypes as C
+    from vitron_b200._lib import Epilogue
+    epi = Epilogue()
+    # null pointers / bad sizes are rejected before anything touches a device
+    assert lib.vb200_gemm_bf16(None, 8, None, 8, None, 8, 8, 8, 8, C.byref(epi), None, 0, None) == -1
+    assert lib.vb200_rmsnorm(None, 8, None, None, 8, 1, 8, 1e-5, None) == -1
+    assert lib.vb200_attention_short(None, None, None, None, 1, 1, 64, 64, *([0] * 17), 1.0, None) == -1
+    assert lib.vb200_gemm_bf16_workspace_size(128, 128, 128) == 0
+    assert lib.vb200_gemm_bf16_workspace_size(8, 4096, 4096) > 0
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from vitron_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libvitron_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_glu_weight_packing_layout():
+    from vitron_b200 import ops
+    a = torch.arange(32 * 2, dtype=torch.float32).reshape(32, 2)
+    b = -a
+    w = ops.pack_glu_weight(a, b)
+    assert w.shape == (64, 2)
+    assert torch.equal(w[:16], a[:16]) and torch.equal(w[16:32], b[:16]) and torch.equal(w[32:48], a[16:])
+
+
+def test_conv_weight_packing_layout():
+    from vitron_b200 import ops
+    w = torch.randn(5, 3, 3, 3)
+    p = ops.pack_conv_weight(w)
+    assert p.shape == (5, 9, 64) and p[:, :, 3:].abs().sum() == 0
+    assert torch.allclose(p[2, 4, :3].float(), w[2, :, 1, 1].to(torch.bfloat16).float())
+    w3 = torch.randn(4, 6, 3, 1, 1)
+    assert ops.pack_conv_weight(w3).shape == (4, 3, 64)
+
+
+def test_host_splice_layout_matches_oracle():
+    from oracle import restate_llm as R
+    from vitron_b200.vitron_model import layout_multimodal
+    g = torch.Generator().manual_seed(0)
+    d, V = 8, 50
+    E = torch.randn((V, d), generator=g)
+    feats = [torch.randn((4, d), generator=g) for _ in range(5)]          # 2 images + 3 video frames
+    rfeats = [torch.randn((1, d), generator=g), torch.randn((1, d), generator=g), None, None, None]
+    ids = torch.tensor([[1, 7, -200, 9, -300, 4, 0, 0, 0],
+                        [1, -200, 8, 8, 8, -300, 3, 2, 6],
+                        [1, -200, -200, -200, 5, 6, 0, 0, 0]])
+    am = torch.tensor([[1] * 6 + [0] * 3, [1] * 9, [1] * 6 + [0] * 3]).bool()
+    for left in (False, True):
+        src, lab, m, pid, lens = layout_multimodal(ids, am, torch.full_like(ids, -100), [4] * 5,
+                                                   [1, 1, None, None, None], 16, left)
+        buf = torch.cat(feats + [r for r in rfeats if r is not None], 0)
+        got = torch.zeros((*src.shape, d))
+        for b in range(src.shape[0]):
+            for s in range(src.shape[1]):
+                v = int(src[b, s])
+                if v >= 0:
+                    got[b, s] = E[v]
+                elif v != -2147483648:
+                    got[b, s] = buf[-v - 1]
+        want, wlens = R.splice({"model.embed_tokens.weight": E}, ids, am, feats, rfeats, True, 16,
+                               "left" if left else "right")
+        assert lens == wlens == [9, 12, 15]
+        assert torch.equal(got, want)
+        assert m.sum(1).tolist() == lens and (pid.max(1).values + 1).tolist() == lens
+    # truncation to tokenizer_model_max_length
+    src, *_ , lens = layout_multimodal(ids, am, torch.full_like(ids, -100), [4] * 5, [1, 1, None, None, None], 10, False)
+    assert lens == [9, 10, 10] and src.shape[1] == 10
+    with pytest.raises(ValueError):
+        layout_multimodal(torch.tensor([[1, -300, 2]]), torch.ones((1, 3), dtype=torch.bool), torch.zeros((1, 3), dtype=torch.long), [4], None, None, False)

@@ -58,22 +58,28 @@ def test_seem_pixel_and_mask_decoder_vs_oracle(cuda, size):
     # first-layer quantities see no error accumulation: tight check incl. the bool masks
     a0, r0 = out["aux_outputs"][0], ref["aux_outputs"][0]
     assert_close(a0["pred_masks"], r0["pred_masks"], "layer-0 mask logits", 0.02, 0.02)
-    check_masks(out["attn_masks"][0], ref["attn_masks"][0], r0["pred_masks"], heads, 0.02)
+    check_masks(out["attn_masks"][0], ref["attn_masks"][0], r0["pred_masks"], heads, 0.03, (H >> 3, W >> 3))
     assert_close(out["pred_maskembs"], ref["pred_maskembs"], "pred_maskembs", 0.08, 0.06)
     assert_close(out["pred_masks"], ref["pred_masks"], "pred_masks", 0.08, 0.06)
     assert_close(out["pred_logits"], ref["pred_logits"], "pred_logits", 0.08, 0.06)
 
 
-def check_masks(got, ref_raw, ref_logits, heads, tol_frac):
-    """got [B,1,Q,N] uint8 (reset applied); ref_raw [B*heads,Q,N] bool (raw). Pixels whose resized oracle
-    logit is within tol of 0 may differ; everything else must be identical."""
+def check_masks(got, ref_raw, ref_logits, heads, tol_frac, size):
+    """got [B,1,Q,N] uint8 (reset applied); ref_raw [B*heads,Q,N] bool (raw); ref_logits [B,Q,H,W].
+    Mask-pixel decisions must be IDENTICAL wherever the oracle's resized logit is further from the 0
+    threshold than the float tolerance; inside that band either decision is admissible."""
+    import torch.nn.functional as F
     B, _, Q, N = got.shape
     ref = ref_raw.view(B, heads, Q, N)[:, 0].clone()
-    ref[torch.where(ref.sum(-1) == N)] = False  # AttentionDataStruct.cross_attn_mask reset rule
+    full = ref.sum(-1) == N
+    ref[torch.where(full)] = False  # AttentionDataStruct.cross_attn_mask reset rule
     got = got[:, 0].bool().cpu()
-    diff = got != ref
-    frac = diff.float().mean().item()
-    assert frac < 0.01, f"mask mismatch fraction {frac:.4f}"
+    resized = F.interpolate(ref_logits.float(), size=size, mode="bilinear", align_corners=False).flatten(2)
+    band = resized.abs() <= tol_frac * ref_logits.abs().max()
+    rows_ok = ~full  # a row that is fully masked in the oracle is compared only if ours is too
+    bad = (got != ref) & ~band & rows_ok[:, :, None]
+    assert bad.sum().item() == 0, f"{bad.sum().item()} mask pixels differ outside the tolerance band"
+    assert band.float().mean().item() < 0.2
 
 
 def test_seem_end_to_end_head(cuda):

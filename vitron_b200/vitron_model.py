@@ -26,6 +26,81 @@ OBJS_TOKEN_INDEX = -300      # vitron/constants.py:24
 PAD_SRC = -2147483648
 
 
+def layout_multimodal(ids_h, mask_h, labels_h, feat_rows, region_rows, max_model_len, left_pad):
+    """Host half of prepare_inputs_labels_for_multimodal (vitron/model/llava_arch.py:300-372, 470-556).
+
+    ids_h / mask_h / labels_h: CPU [B, L]; feat_rows[e]: rows of image-feature entry e (video frames are
+    separate entries); region_rows[e]: rows of its region feature or None (None list = no regions).
+    Returns (srcmap int32 [B, S], labels [B, S], attention_mask bool [B, S], position_ids [B, S], lens):
+    srcmap >= 0 -> token id, -(row+1) -> row of the concatenated [features ; region features] buffer,
+    INT32_MIN -> padding. Quirks kept: a sample without <image> consumes one feature slot (:492); an
+    <objs> token takes the region feature of the most recent image (index cur-1, Python-negative for
+    cur == 0)."""
+    use_regions = region_rows is not None
+    feat_base, off = [], 0
+    for n in feat_rows:
+        feat_base.append(off)
+        off += n
+    region_slot = {}
+    if use_regions:
+        for e, n in enumerate(region_rows):
+            if n is not None:
+                region_slot[e] = off
+                off += n
+    srcs, labs = [], []
+    cur = 0
+    for b in range(ids_h.shape[0]):
+        ids_b = ids_h[b][mask_h[b]].tolist()
+        lab_b = labels_h[b][mask_h[b]].tolist()
+        n_img = sum(1 for t in ids_b if t == IMAGE_TOKEN_INDEX)
+        src, lab = [], []
+        if n_img == 0:
+            if any(t < 0 for t in ids_b):
+                raise ValueError("special sentinel in a sample without <image> tokens")
+            src, lab = list(ids_b), list(lab_b)
+            cur += 1
+        else:
+            for t, l in zip(ids_b, lab_b):
+                if t == IMAGE_TOKEN_INDEX:
+                    if cur >= len(feat_rows):
+                        raise IndexError("more <image> tokens than images")
+                    src.extend(-(feat_base[cur] + i) - 1 for i in range(feat_rows[cur]))
+                    lab.extend([IGNORE_INDEX] * feat_rows[cur])
+                    cur += 1
+                elif t == OBJS_TOKEN_INDEX:
+                    if not use_regions:
+                        raise ValueError("<objs> token given but no regions")
+                    e = (cur - 1) % len(feat_rows)
+                    if e not in region_slot:
+                        raise ValueError("region feature requested for a video frame")
+                    src.extend(-(region_slot[e] + i) - 1 for i in range(region_rows[e]))
+                    lab.extend([IGNORE_INDEX] * region_rows[e])
+                else:
+                    src.append(t)
+                    lab.append(l)
+        srcs.append(src)
+        labs.append(lab)
+    if max_model_len is not None:
+        srcs = [s[:max_model_len] for s in srcs]
+        labs = [l[:max_model_len] for l in labs]
+    max_len = max(len(s) for s in srcs)
+    B = len(srcs)
+    src_t = torch.full((B, max_len), PAD_SRC, dtype=torch.int32)
+    lab_t = torch.full((B, max_len), IGNORE_INDEX, dtype=labels_h.dtype)
+    am = torch.zeros((B, max_len), dtype=torch.bool)
+    pid = torch.zeros((B, max_len), dtype=torch.long)
+    for b, (s, l) in enumerate(zip(srcs, labs)):
+        n = len(s)
+        if n == 0:
+            continue
+        sl = slice(max_len - n, max_len) if left_pad else slice(0, n)
+        src_t[b, sl] = torch.tensor(s, dtype=torch.int32)
+        lab_t[b, sl] = torch.tensor(l, dtype=labels_h.dtype)
+        am[b, sl] = True
+        pid[b, sl] = torch.arange(n)
+    return src_t, lab_t, am, pid, [len(s) for s in srcs]
+
+
 class VitronConfig(SimpleNamespace):
     def __init__(self, llm=None, vision=None, video=None, mm_projector_type="mlp2x_gelu",
                  mm_vision_select_layer=-2, mm_vision_select_feature="patch", tokenizer_padding_side="right",
@@ -190,73 +265,11 @@ class VitronLlamaForCausalLM:
         mask_h = torch.ones_like(ids_h, dtype=torch.bool) if attention_mask is None else attention_mask.detach().cpu().bool()
         labels_h = torch.full_like(ids_h, IGNORE_INDEX) if labels is None else labels.detach().cpu()
 
-        feat_rows, feat_base, off = [], [], 0
-        for f in flat:
-            feat_base.append(off)
-            feat_rows.append(f.shape[0])
-            off += f.shape[0]
-        region_base = off
-        region_slot = {}
-        if use_regions:
-            for e, r in enumerate(rflat):
-                if r is not None:
-                    region_slot[e] = off
-                    off += r.shape[0]
-
-        srcs, labs = [], []
-        cur = 0
-        for b in range(ids_h.shape[0]):
-            ids_b = ids_h[b][mask_h[b]].tolist()
-            lab_b = labels_h[b][mask_h[b]].tolist()
-            n_img = sum(1 for t in ids_b if t == IMAGE_TOKEN_INDEX)
-            src, lab = [], []
-            if n_img == 0:
-                if any(t < 0 for t in ids_b):
-                    raise ValueError("special sentinel in a sample without <image> tokens")
-                src, lab = list(ids_b), list(lab_b)
-                cur += 1  # the reference consumes one feature slot for image-less samples (:492)
-            else:
-                for t, l in zip(ids_b, lab_b):
-                    if t == IMAGE_TOKEN_INDEX:
-                        if cur >= len(flat):
-                            raise IndexError("more <image> tokens than images")
-                        src.extend(-(feat_base[cur] + i) - 1 for i in range(feat_rows[cur]))
-                        lab.extend([IGNORE_INDEX] * feat_rows[cur])
-                        cur += 1
-                    elif t == OBJS_TOKEN_INDEX:
-                        if not use_regions:
-                            raise ValueError("<objs> token given but no regions")
-                        e = (cur - 1) % len(flat)
-                        if e not in region_slot:
-                            raise ValueError("region feature requested for a video frame")
-                        src.append(-region_slot[e] - 1)
-                        lab.append(IGNORE_INDEX)
-                    else:
-                        src.append(t)
-                        lab.append(l)
-            srcs.append(src)
-            labs.append(lab)
-
-        max_model_len = getattr(self.config, "tokenizer_model_max_length", None)
-        if max_model_len is not None:
-            srcs = [s[:max_model_len] for s in srcs]
-            labs = [l[:max_model_len] for l in labs]
-        max_len = max(len(s) for s in srcs)
-        B = len(srcs)
-        left = getattr(self.config, "tokenizer_padding_side", "right") == "left"
-        src_t = torch.full((B, max_len), PAD_SRC, dtype=torch.int32)
-        lab_t = torch.full((B, max_len), IGNORE_INDEX, dtype=labels_h.dtype)
-        am = torch.zeros((B, max_len), dtype=torch.bool)
-        pid = torch.zeros((B, max_len), dtype=torch.long)
-        for b, (s, l) in enumerate(zip(srcs, labs)):
-            n = len(s)
-            if n == 0:
-                continue
-            sl = slice(max_len - n, max_len) if left else slice(0, n)
-            src_t[b, sl] = torch.tensor(s, dtype=torch.int32)
-            lab_t[b, sl] = torch.tensor(l, dtype=labels_h.dtype)
-            am[b, sl] = True
-            pid[b, sl] = torch.arange(n)
+        src_t, lab_t, am, pid, lens = layout_multimodal(
+            ids_h, mask_h, labels_h, [f.shape[0] for f in flat],
+            [None if r is None else r.shape[0] for r in rflat] if use_regions else None,
+            getattr(self.config, "tokenizer_model_max_length", None),
+            getattr(self.config, "tokenizer_padding_side", "right") == "left")
 
         pieces = [f.reshape(-1, f.shape[-1]) for f in flat]
         if use_regions:
@@ -268,7 +281,7 @@ class VitronLlamaForCausalLM:
         new_labels = None if _labels is None else lab_t.to(dev)
         attention_mask = None if _attention_mask is None else am.to(device=dev, dtype=_attention_mask.dtype)
         position_ids = None if _position_ids is None else pid.to(dev)
-        self._last_lens = [len(s) for s in srcs]
+        self._last_lens = lens
         return None, position_ids, attention_mask, past_key_values, inputs_embeds, new_labels
 
     @staticmethod
