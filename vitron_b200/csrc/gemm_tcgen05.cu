@@ -58,6 +58,8 @@ struct GemmParams {
   float* ws;          // split-K / swap workspace [splits, rows_c, cols_c] fp32
   long long ws_split_stride;
   long long ws_ld;
+  int* counters;      // one arrival counter per output tile (zero on entry, zero again on exit)
+  int rows_c, cols_c; // extent of the output in C orientation (rows = tokens, cols = features)
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -67,6 +69,87 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case VB_ACT_RELU: return fmaxf(x, 0.f);
     case VB_ACT_SILU: return silu(x);
     default: return x;
+  }
+}
+
+// One 8-wide output item of the split-K finalisation: out[row, oc..oc+8) = epi(sum_s ws[s, row, cols]).
+// Partials are read with ld.global.cg (L2) because they were written by other CTAs.
+__device__ __forceinline__ void reduce_item(const float* __restrict__ ws, int splits, long long split_stride,
+                                            long long ws_ld, int row, int oc, int ncols, void* out, long long ldo,
+                                            const bf16* __restrict__ bias, const bf16* __restrict__ rowbias,
+                                            int rowbias_rows, const bf16* __restrict__ residual, long long ldr,
+                                            float alpha, int act, int glu, int out_fp32) {
+  const int n_out_total = glu != VB_GLU_NONE ? ncols / 2 : ncols;
+  int ca = oc, cb = -1;
+  if (glu != VB_GLU_NONE) {
+    ca = (oc / 16) * 32 + (oc % 16);
+    cb = ca + 16;
+  }
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  const bool vec = (oc + 8 <= n_out_total) && ((ws_ld & 3) == 0);
+  for (int s = 0; s < splits; ++s) {
+    const float* src = ws + s * split_stride + row * ws_ld;
+    if (vec) {
+      const float4 x0 = __ldcg(reinterpret_cast<const float4*>(src + ca));
+      const float4 x1 = __ldcg(reinterpret_cast<const float4*>(src + ca + 4));
+      a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w;
+      a[4] += x1.x; a[5] += x1.y; a[6] += x1.z; a[7] += x1.w;
+      if (cb >= 0) {
+        const float4 y0 = __ldcg(reinterpret_cast<const float4*>(src + cb));
+        const float4 y1 = __ldcg(reinterpret_cast<const float4*>(src + cb + 4));
+        b[0] += y0.x; b[1] += y0.y; b[2] += y0.z; b[3] += y0.w;
+        b[4] += y1.x; b[5] += y1.y; b[6] += y1.z; b[7] += y1.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (oc + j < n_out_total) {
+          a[j] += __ldcg(src + ca + j);
+          if (cb >= 0) b[j] += __ldcg(src + cb + j);
+        }
+      }
+    }
+  }
+  const bf16* rb = rowbias ? rowbias + (row / rowbias_rows) * static_cast<long long>(ncols) : nullptr;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = 0.f;
+    if (oc + j >= n_out_total) continue;
+    float va = a[j], vb_ = b[j];
+    if (bias) {
+      va += __bfloat162float(bias[ca + j]);
+      if (cb >= 0) vb_ += __bfloat162float(bias[cb + j]);
+    }
+    if (rb) {
+      va += __bfloat162float(rb[ca + j]);
+      if (cb >= 0) vb_ += __bfloat162float(rb[cb + j]);
+    }
+    float r;
+    if (glu == VB_GLU_SWIGLU) r = silu(va) * vb_;
+    else if (glu == VB_GLU_GEGLU) r = va * gelu_erf(vb_);
+    else r = apply_act(va, act);
+    if (residual) r = __bfloat162float(residual[row * ldr + oc + j]) + alpha * r;
+    else r *= alpha;
+    v[j] = r;
+  }
+  if (out_fp32) {
+    float* dst = reinterpret_cast<float*>(out) + row * ldo + oc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (oc + j < n_out_total) dst[j] = v[j];
+  } else {
+    bf16* dst = reinterpret_cast<bf16*>(out) + row * ldo + oc;
+    if (oc + 8 <= n_out_total && (ldo & 7) == 0) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                  pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (oc + j < n_out_total) dst[j] = __float2bfloat16(v[j]);
+    }
   }
 }
 
@@ -117,6 +200,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+  volatile int* fin_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -378,6 +462,37 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+
+      if (p.ws != nullptr && p.counters != nullptr) {
+        // -------- split-K finalisation without a second kernel: the CTA that completes a tile last
+        // sums the partials in split order (deterministic) and applies the fused epilogue.
+        const int tile = unit / p.splits;
+        const int et = threadIdx.x - 64;  // 0..127 among the epilogue warps
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const int prev = atomicAdd(&p.counters[tile], 1);
+          *fin_flag = (prev == p.splits - 1) ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*fin_flag) {
+          __threadfence();
+          int r0, r1, c0, c1;  // tile extent in C orientation
+          if (p.swap) { r0 = 0; r1 = p.rows_c; c0 = t.m_blk * BLOCK_M; c1 = min(p.cols_c, c0 + BLOCK_M); }
+          else { r0 = t.m_blk * BLOCK_M; r1 = min(p.rows_c, r0 + BLOCK_M); c0 = col0; c1 = min(p.cols_c, c0 + BLOCK_N); }
+          const bool g = p.glu != VB_GLU_NONE;
+          const int oc0 = g ? c0 / 2 : c0, oc1 = g ? c1 / 2 : c1;
+          const int chunks = (oc1 - oc0 + 7) / 8;
+          const int items = (r1 - r0) * chunks;
+          for (int it = et; it < items; it += 128) {
+            const int row = r0 + it / chunks, oc = oc0 + (it % chunks) * 8;
+            reduce_item(p.ws, p.splits, p.ws_split_stride, p.ws_ld, row, oc, p.cols_c, p.out, p.ldo, p.bias,
+                        p.rowbias, p.rowbias_rows, p.residual, p.ldr, p.alpha, p.act, p.glu, p.out_fp32);
+          }
+          if (et == 0) p.counters[tile] = 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // fin_flag is reused by the next unit
+      }
     }
   }
 
@@ -401,48 +516,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits,
   const int groups = (n_out_total + 7) / 8;
   long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * groups) return;
-  const int row = static_cast<int>(idx / groups);
-  const int oc = static_cast<int>(idx % groups) * 8;
-  int ca = oc, cb = -1;
-  if (glu != VB_GLU_NONE) {
-    ca = (oc / 16) * 32 + (oc % 16);
-    cb = ca + 16;
-  }
-  float a[8], b[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
-  for (int s = 0; s < splits; ++s) {
-    const float* src = ws + s * split_stride + row * ws_ld;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (oc + j < n_out_total) {
-        a[j] += src[ca + j];
-        if (cb >= 0) b[j] += src[cb + j];
-      }
-    }
-  }
-  const bf16* rb = rowbias ? rowbias + (row / rowbias_rows) * static_cast<long long>(ncols) : nullptr;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (oc + j >= n_out_total) continue;
-    float va = a[j], vb_ = b[j];
-    if (bias) {
-      va += __bfloat162float(bias[ca + j]);
-      if (cb >= 0) vb_ += __bfloat162float(bias[cb + j]);
-    }
-    if (rb) {
-      va += __bfloat162float(rb[ca + j]);
-      if (cb >= 0) vb_ += __bfloat162float(rb[cb + j]);
-    }
-    float v;
-    if (glu == VB_GLU_SWIGLU) v = silu(va) * vb_;
-    else if (glu == VB_GLU_GEGLU) v = va * gelu_erf(vb_);
-    else v = apply_act(va, act);
-    if (residual) v = __bfloat162float(residual[row * ldr + oc + j]) + alpha * v;
-    else v *= alpha;
-    if (out_fp32) reinterpret_cast<float*>(out)[row * ldo + oc + j] = v;
-    else reinterpret_cast<bf16*>(out)[row * ldo + oc + j] = __float2bfloat16(v);
-  }
+  reduce_item(ws, splits, split_stride, ws_ld, static_cast<int>(idx / groups), static_cast<int>(idx % groups) * 8,
+              ncols, out, ldo, bias, rowbias, rowbias_rows, residual, ldr, alpha, act, glu, out_fp32);
 }
 
 // ------------------------------------------------------------------ host side
@@ -529,15 +604,27 @@ static int pick_block_n(long long M, long long N, int glu) {
   return best;
 }
 
+constexpr size_t GEMM_COUNTER_BYTES = 16384;  // 4096 tile counters at the head of the workspace
+
 static int swap_splits(long long M, long long N, long long K) {
-  (void)M;
+  // maximise (CTA wave utilisation) x (k-block balance across splits); fewer splits win ties
+  const int sms = vb_num_sms();
   const int m_blocks = static_cast<int>((N + BLOCK_M - 1) / BLOCK_M);
   const int kblocks = static_cast<int>((K + BLOCK_K - 1) / BLOCK_K);
-  int splits = (2 * vb_num_sms() + m_blocks - 1) / m_blocks;  // ~2 waves of CTAs stream W
-  if (splits > 16) splits = 16;
-  if (splits > kblocks) splits = kblocks;
-  if (splits < 1) splits = 1;
-  return splits;
+  int best = 1;
+  float best_score = -1.f;
+  for (int s = 1; s <= 32 && s <= kblocks; ++s) {
+    if (static_cast<size_t>(s) * M * N * sizeof(float) > (static_cast<size_t>(96) << 20)) break;
+    const long long units = static_cast<long long>(m_blocks) * s;
+    const long long waves = (units + sms - 1) / sms;
+    const float util = static_cast<float>(units) / static_cast<float>(waves * sms);
+    const int per = (kblocks + s - 1) / s;
+    const float bal = static_cast<float>(kblocks) / static_cast<float>(s * per);
+    // every extra wave / split costs a fixed ramp (pipeline fill, partial write + reduction)
+    const float score = util * bal - 0.01f * static_cast<float>(s);
+    if (score > best_score + 1e-6f) { best_score = score; best = s; }
+  }
+  return best;
 }
 
 static int run_reduce(const GemmParams& p, int rows, int ncols, void* out, long long ldo,
@@ -568,8 +655,9 @@ using namespace vb;
 
 extern "C" size_t vb200_gemm_bf16_workspace_size(int64_t M, int64_t N, int64_t K) {
   if (M <= 0 || N <= 0 || K <= 0 || M > 64) return 0;  // only the swap-AB (tiny-M) path needs one
-  return static_cast<size_t>(swap_splits(M, N, K)) * static_cast<size_t>(M) *
-         static_cast<size_t>(N) * sizeof(float);
+  // [tile counters | fp32 partials]; the caller zero-fills it ONCE, the kernels leave the counters zeroed
+  return GEMM_COUNTER_BYTES + static_cast<size_t>(swap_splits(M, N, K)) * static_cast<size_t>(M) *
+                                  static_cast<size_t>(N) * sizeof(float);
 }
 
 extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
@@ -611,10 +699,14 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
     p.n_blocks = 1;
     const int splits = swap_splits(M, N, K);
     p.splits = splits;
-    size_t need = static_cast<size_t>(splits) * M * N * sizeof(float);
+    size_t need = GEMM_COUNTER_BYTES + static_cast<size_t>(splits) * M * N * sizeof(float);
     if (workspace == nullptr || workspace_bytes < need) return VB_ERR_WORKSPACE;
+    if (static_cast<size_t>(p.m_blocks) * sizeof(int) > GEMM_COUNTER_BYTES) return VB_ERR_UNSUPPORTED;
     p.swap = 1;
-    p.ws = reinterpret_cast<float*>(workspace);
+    p.counters = reinterpret_cast<int*>(workspace);
+    p.rows_c = static_cast<int>(M);
+    p.cols_c = static_cast<int>(N);
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + GEMM_COUNTER_BYTES);
     p.ws_ld = N;
     p.ws_split_stride = M * N;
     uint64_t dA[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
@@ -625,8 +717,7 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
     uint64_t sB[1] = {static_cast<uint64_t>(lda) * 2};
     uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
     if (int r = make_tmap(&tb, A, 2, dB, sB, bB, estr2)) return r;
-    if (int r = launch_gemm(bn, ta, tb, p, stream)) return r;
-    return run_reduce(p, static_cast<int>(M), static_cast<int>(N), out, ldo, epi, stream);
+    return launch_gemm(bn, ta, tb, p, stream);  // the last CTA of every tile finalises it
   }
 
   int bn = pick_block_n(M, N, epi->glu);

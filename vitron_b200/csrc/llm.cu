@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, const bf16* __restrict__ k_pages,
                    const bf16* __restrict__ v_pages, const int32_t* __restrict__ block_table, int max_pages,
                    const int32_t* __restrict__ kv_len, int H, int page_size, float scale, int splits,
-                   float* __restrict__ ws_ml, float* __restrict__ ws_o, bf16* __restrict__ out, long long ld_o) {
+                   float* __restrict__ ws_ml, float* __restrict__ ws_o, int* __restrict__ counters,
+                   bf16* __restrict__ out, long long ld_o) {
   constexpr int HD = 128;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -169,28 +170,31 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, const bf16* __res
   if (splits == 1) {
     out[static_cast<long long>(b) * ld_o + h * HD + d] = __float2bfloat16(L > 0.f ? O / L : 0.f);
   } else {
-    const long long idx = (static_cast<long long>(b) * H + h) * splits + split;
+    const long long base = (static_cast<long long>(b) * H + h) * splits;
+    const long long idx = base + split;
     if (d == 0) { ws_ml[idx * 2] = M; ws_ml[idx * 2 + 1] = L; }
     ws_o[idx * HD + d] = O;
+    // the CTA that finishes this (batch, head) last merges the split partials (fixed order)
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (d == 0) is_last = (atomicAdd(&counters[b * H + h], 1) == splits - 1) ? 1 : 0;
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      float Mx = -INFINITY;
+      for (int s = 0; s < splits; ++s) Mx = fmaxf(Mx, __ldcg(&ws_ml[(base + s) * 2]));
+      float Ls = 0.f, Os = 0.f;
+      for (int s = 0; s < splits; ++s) {
+        const float ms = __ldcg(&ws_ml[(base + s) * 2]);
+        const float w = (ms == -INFINITY) ? 0.f : __expf(ms - Mx);
+        Ls += __ldcg(&ws_ml[(base + s) * 2 + 1]) * w;
+        Os += __ldcg(&ws_o[(base + s) * HD + d]) * w;
+      }
+      out[static_cast<long long>(b) * ld_o + h * HD + d] = __float2bfloat16(Ls > 0.f ? Os / Ls : 0.f);
+      if (d == 0) counters[b * H + h] = 0;
+    }
   }
-}
-
-__global__ void __launch_bounds__(128)
-attn_decode_combine_kernel(const float* __restrict__ ws_ml, const float* __restrict__ ws_o, int H, int splits,
-                           bf16* __restrict__ out, long long ld_o) {
-  constexpr int HD = 128;
-  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
-  const long long base = (static_cast<long long>(b) * H + h) * splits;
-  float M = -INFINITY;
-  for (int s = 0; s < splits; ++s) M = fmaxf(M, ws_ml[(base + s) * 2]);
-  float L = 0.f, O = 0.f;
-  for (int s = 0; s < splits; ++s) {
-    const float ms = ws_ml[(base + s) * 2];
-    const float w = (ms == -INFINITY) ? 0.f : __expf(ms - M);
-    L += ws_ml[(base + s) * 2 + 1] * w;
-    O += ws_o[(base + s) * HD + d] * w;
-  }
-  out[static_cast<long long>(b) * ld_o + h * HD + d] = __float2bfloat16(L > 0.f ? O / L : 0.f);
 }
 
 // ------------------------------------------------------------------ multimodal splice
@@ -337,8 +341,10 @@ static int decode_splits(int64_t max_kv_len) {
 
 extern "C" size_t vb200_attn_decode_workspace_size(int64_t B, int64_t n_heads, int64_t head_dim,
                                                    int64_t max_splits) {
+  // [B*H arrival counters | (m, l) per split | unnormalised o per split]; zero-fill ONCE before first use
   if (max_splits < 1) max_splits = 32;
-  return static_cast<size_t>(B) * n_heads * max_splits * (head_dim + 2) * sizeof(float);
+  return static_cast<size_t>(B) * n_heads * sizeof(int) +
+         static_cast<size_t>(B) * n_heads * max_splits * (head_dim + 2) * sizeof(float);
 }
 
 extern "C" int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* k_pages,
@@ -354,25 +360,21 @@ extern "C" int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* 
   const int splits = decode_splits(max_kv_len);
   float* ws_ml = nullptr;
   float* ws_o = nullptr;
+  int* counters = nullptr;
   if (splits > 1) {
     size_t need = vb200_attn_decode_workspace_size(B, n_heads, head_dim, splits);
     if (!workspace || workspace_bytes < need) return VB_ERR_WORKSPACE;
-    ws_ml = reinterpret_cast<float*>(workspace);
+    counters = reinterpret_cast<int*>(workspace);
+    ws_ml = reinterpret_cast<float*>(counters + B * n_heads);
     ws_o = ws_ml + static_cast<size_t>(B) * n_heads * splits * 2;
   }
   dim3 grid(splits, static_cast<unsigned>(n_heads), static_cast<unsigned>(B));
   attn_decode_kernel<<<grid, DEC_THREADS, 0, stream>>>(
       reinterpret_cast<const bf16*>(q), ld_q, reinterpret_cast<const bf16*>(k_pages),
       reinterpret_cast<const bf16*>(v_pages), block_table, static_cast<int>(max_pages), kv_len,
-      static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, ws_ml, ws_o,
+      static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, ws_ml, ws_o, counters,
       reinterpret_cast<bf16*>(out), ld_o);
   VB_LAUNCH_CHECK();
-  if (splits > 1) {
-    dim3 g2(static_cast<unsigned>(n_heads), static_cast<unsigned>(B));
-    attn_decode_combine_kernel<<<g2, 128, 0, stream>>>(ws_ml, ws_o, static_cast<int>(n_heads), splits,
-                                                       reinterpret_cast<bf16*>(out), ld_o);
-    VB_LAUNCH_CHECK();
-  }
   return VB_OK;
 }
 

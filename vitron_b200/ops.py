@@ -35,11 +35,12 @@ def _ptr(t):
 
 
 def workspace(nbytes, device, tag="main"):
-    """Grow-only per-(device, tag) scratch buffer; contents are only valid within one op."""
+    """Grow-only per-(device, tag) scratch buffer, zero-filled at allocation (the split-K / split-KV
+    arrival counters at its head must start at zero; the kernels leave them zeroed)."""
     key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
     buf = _ws.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _ws[key] = buf
     return buf
 
@@ -106,7 +107,7 @@ def gemm(a, w, bias=None, act=ACT_NONE, glu=GLU_NONE, residual=None, alpha=1.0, 
     ws = workspace(need, a.device) if need else None
     check(lib.vb200_gemm_bf16(a2.data_ptr(), lda, w.data_ptr(), w.stride(0), out2.data_ptr(), ldo, M, N, K,
                               C.byref(epi), _ptr(ws), need, _stream()), "vb200_gemm_bf16")
-    _launches[0] += 2 if M <= 64 else 1
+    _launches[0] += 1
     return out.reshape(*a.shape[:-1], n_out) if a.dim() != 2 else out
 
 
@@ -306,7 +307,7 @@ def attn_decode_paged(q, k_pages, v_pages, block_table, kv_len, n_heads, head_di
                                       block_table.data_ptr(), block_table.shape[1], kv_len.data_ptr(),
                                       out.data_ptr(), out.stride(0), B, n_heads, head_dim, page_size, max_kv_len,
                                       float(scale), ws.data_ptr(), need, _stream()), "vb200_attn_decode_paged")
-    _launches[0] += 1 if max_kv_len <= 256 else 2
+    _launches[0] += 1
     return out
 
 
