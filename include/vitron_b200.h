@@ -60,7 +60,7 @@ int vb200_device_ok(void);          /* 1 iff the current device is sm_100 (B200)
  * call sites vitron/model/language_model/llava_llama.py:91-102), CLIPAttention/CLIPMLP
  * (languagebind/image/modeling_image.py:136-151), mm_projector (multimodal_projector/
  * builder.py:33-51), region MLP (region_extractor/layer.py:17-20), UNet/SEEM/GLIGEN linears.
- * M <= 64 runs swap-AB + split-K (weights stream through the 128-row MMA slot; the CTA that completes
+ * M <= 16 runs the weight-streaming kernel (gemv.cu: HBM-bound, no workspace). 16 < M <= 64 runs swap-AB + split-K (weights stream through the 128-row MMA slot; the CTA that completes
  * a tile last reduces the partials in split order and applies the epilogue) and needs the workspace
  * reported by vb200_gemm_bf16_workspace_size, zero-filled once by the caller before its first use. lda/ldw/ldo in elements, multiples of 8. */
 size_t vb200_gemm_bf16_workspace_size(int64_t M, int64_t N, int64_t K);

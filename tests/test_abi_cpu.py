@@ -42,7 +42,8 @@ def test_argument_validation_without_device(lib):
     assert lib.vb200_rmsnorm(None, 8, None, None, 8, 1, 8, 1e-5, None) == -1
     assert lib.vb200_attention_short(None, None, None, None, 1, 1, 64, 64, *([0] * 17), 1.0, None) == -1
     assert lib.vb200_gemm_bf16_workspace_size(128, 128, 128) == 0
-    assert lib.vb200_gemm_bf16_workspace_size(8, 4096, 4096) > 0
+    assert lib.vb200_gemm_bf16_workspace_size(8, 4096, 4096) == 0  # streaming kernel
+    assert lib.vb200_gemm_bf16_workspace_size(32, 4096, 4096) > 0
 
 
 def test_missing_library_fails_loudly(monkeypatch):

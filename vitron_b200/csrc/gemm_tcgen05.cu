@@ -653,8 +653,12 @@ static int validate_epi(const vb_epilogue* e, long long N) {
 
 using namespace vb;
 
+int vb_launch_gemv(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int64_t M,
+                   int64_t N, int64_t K, const vb_epilogue* e, cudaStream_t stream);  // gemv.cu
+
 extern "C" size_t vb200_gemm_bf16_workspace_size(int64_t M, int64_t N, int64_t K) {
-  if (M <= 0 || N <= 0 || K <= 0 || M > 64) return 0;  // only the swap-AB (tiny-M) path needs one
+  // M <= 16: weight-streaming kernel (gemv.cu), no workspace; 16 < M <= 64: swap-AB + split-K
+  if (M <= 16 || N <= 0 || K <= 0 || M > 64) return 0;
   // [tile counters | fp32 partials]; the caller zero-fills it ONCE, the kernels leave the counters zeroed
   return GEMM_COUNTER_BYTES + static_cast<size_t>(swap_splits(M, N, K)) * static_cast<size_t>(M) *
                                   static_cast<size_t>(N) * sizeof(float);
@@ -669,6 +673,7 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   VB_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && lda >= K && ldw >= K);
   VB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   if (int r = validate_epi(epi, N)) return r;
+  if (M <= 16) return vb_launch_gemv(A, lda, W, ldw, out, ldo, M, N, K, epi, stream);
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -689,7 +694,7 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
 
   CUtensorMap ta, tb;
   const uint32_t estr2[2] = {1, 1};
-  const bool swap = (M <= 64);  // tiny-M (decode, region MLP): weights take the 128-row MMA slot
+  const bool swap = (M <= 64);  // small M: weights take the 128-row MMA slot
   if (swap) {
     // kernel-M = N (weight rows), kernel-N = M (tokens); partials -> workspace -> reduce kernel
     const int bn = M <= 16 ? 16 : (M <= 32 ? 32 : 64);

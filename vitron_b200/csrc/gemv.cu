@@ -1,0 +1,191 @@
+// vitron_b200 — weight-streaming GEMM for M <= 16 tokens (the decode step, region MLP, time embeds).
+//
+//   out[M, N'] = epilogue( X[M, K] · W[N, K]^T ),  M <= 16
+//
+// At M = 8 every weight byte is used for 8 FMAs: the op is HBM-bound (13 GB of Vicuna-7B weights per
+// decoded token), so the design goal is bytes in flight, not tensor throughput: no TMEM/TMA
+// prologue, no split-K workspace, one launch with the epilogue fused. Each CTA owns 16 (or 32, for
+// the packed-GLU layout) consecutive output features and the whole K range; its 8 warps split K,
+// stream their weight rows straight from global memory with 16-byte loads (2 x 64-byte segments
+// per row per step, 8 loads in flight per thread), multiply on the legacy m16n8k16 tensor path
+// (weights = A, tokens = B; the k order inside a 64-chunk is permuted identically on both
+// operands so that each thread's fragment is contiguous in memory), and reduce across warps in smem.
+// Replaces the same nn.Linear call sites as gemm_tcgen05.cu for tiny M.
+#include "common.cuh"
+#include "vitron_b200.h"
+
+namespace vb {
+
+struct GemvParams {
+  const bf16* W; long long ldw;
+  const bf16* X; long long ldx;
+  void* out; long long ldo;
+  int M, N, K;
+  const bf16* bias; const bf16* rowbias; int rowbias_rows;
+  const bf16* residual; long long ldr;
+  float alpha; int act, glu, out_fp32;
+};
+
+__device__ __forceinline__ float gemv_act(float x, int act) {
+  switch (act) {
+    case VB_ACT_GELU: return gelu_erf(x);
+    case VB_ACT_QUICK_GELU: return quick_gelu(x);
+    case VB_ACT_RELU: return fmaxf(x, 0.f);
+    case VB_ACT_SILU: return silu(x);
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const bf16* p, bool ok) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (ok) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_cached(const bf16* p, bool ok) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (ok) v = __ldg(reinterpret_cast<const uint4*>(p));
+  return v;
+}
+
+// ROWS = 16 or 32 output features per CTA; NT = 1 (M <= 8) or 2 (M <= 16) token tiles of 8.
+template <int ROWS, int NT>
+__global__ void __launch_bounds__(256) gemv_bf16_kernel(const GemvParams p) {
+  constexpr int WARPS = 8;
+  constexpr int RG = ROWS / 16;        // row groups per CTA
+  constexpr int KS = WARPS / RG;       // k-slices per row group
+  __shared__ float red[WARPS][16][NT * 8 + 1];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int rg = warp % RG, ks = warp / RG;
+  const int row0 = blockIdx.x * ROWS + rg * 16;
+  const int ra = min(row0 + g, p.N - 1), rb = min(row0 + g + 8, p.N - 1);  // clamped (masked in the epilogue)
+  const bf16* wa = p.W + static_cast<long long>(ra) * p.ldw;
+  const bf16* wb = p.W + static_cast<long long>(rb) * p.ldw;
+  const bf16* x0 = p.X + static_cast<long long>(min(g, p.M - 1)) * p.ldx;
+  const bf16* x1 = p.X + static_cast<long long>(min(g + 8, p.M - 1)) * p.ldx;
+  const bool x0ok = g < p.M, x1ok = (NT == 2) && (g + 8 < p.M);
+
+  const int chunks = (p.K + 63) / 64;
+  const int base = chunks / KS, rem = chunks % KS;
+  const int c0 = ks * base + min(ks, rem);
+  const int c1 = c0 + base + (ks < rem ? 1 : 0);
+
+  float acc[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+  // thread t owns k in [8t, 8t+8) and [32+8t, 32+8t+8) of every 64-chunk (same permutation for W and X)
+  auto step = [&](int c) {
+    const int k0 = c * 64 + 8 * t, k1 = k0 + 32;
+    const bool ok0 = k0 < p.K, ok1 = k1 < p.K;
+    const uint4 a_lo0 = ldg_stream(wa + k0, ok0), a_lo1 = ldg_stream(wa + k1, ok1);
+    const uint4 a_hi0 = ldg_stream(wb + k0, ok0), a_hi1 = ldg_stream(wb + k1, ok1);
+    const uint4 b00 = ldg_cached(x0 + k0, ok0 && x0ok), b01 = ldg_cached(x0 + k1, ok1 && x0ok);
+    uint4 b10 = make_uint4(0, 0, 0, 0), b11 = b10;
+    if (NT == 2) { b10 = ldg_cached(x1 + k0, ok0 && x1ok); b11 = ldg_cached(x1 + k1, ok1 && x1ok); }
+    const uint32_t al[8] = {a_lo0.x, a_lo0.y, a_lo0.z, a_lo0.w, a_lo1.x, a_lo1.y, a_lo1.z, a_lo1.w};
+    const uint32_t ah[8] = {a_hi0.x, a_hi0.y, a_hi0.z, a_hi0.w, a_hi1.x, a_hi1.y, a_hi1.z, a_hi1.w};
+    const uint32_t b0[8] = {b00.x, b00.y, b00.z, b00.w, b01.x, b01.y, b01.z, b01.w};
+    const uint32_t b1[8] = {b10.x, b10.y, b10.z, b10.w, b11.x, b11.y, b11.z, b11.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mma16816(acc[0], al[2 * j], ah[2 * j], al[2 * j + 1], ah[2 * j + 1], b0[2 * j], b0[2 * j + 1]);
+      if (NT == 2) mma16816(acc[1], al[2 * j], ah[2 * j], al[2 * j + 1], ah[2 * j + 1], b1[2 * j], b1[2 * j + 1]);
+    }
+  };
+  int c = c0;
+  for (; c + 3 < c1; c += 4) {  // four chunks per trip: 16 weight loads (256 B) in flight per thread
+    step(c);
+    step(c + 1);
+    step(c + 2);
+    step(c + 3);
+  }
+  for (; c < c1; ++c) step(c);
+
+  // ---- cross-warp (k-slice) reduction: red[warp][feature 0..15][token]
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    red[warp][g][i * 8 + 2 * t] = acc[i][0];
+    red[warp][g][i * 8 + 2 * t + 1] = acc[i][1];
+    red[warp][g + 8][i * 8 + 2 * t] = acc[i][2];
+    red[warp][g + 8][i * 8 + 2 * t + 1] = acc[i][3];
+  }
+  __syncthreads();
+
+  // ---- epilogue: one thread per (token, output column of this CTA)
+  const bool glu = p.glu != VB_GLU_NONE;
+  const int out_cols = glu ? ROWS / 2 : ROWS;            // ROWS == 32 when glu
+  const int n_out_total = glu ? p.N / 2 : p.N;
+  for (int item = threadIdx.x; item < p.M * out_cols; item += 256) {
+    const int tok = item / out_cols, j = item % out_cols;
+    int fa = j, fb = -1;                                  // feature rows inside the CTA tile
+    if (glu) fb = j + 16;                                 // packed layout: [16 x a | 16 x b]
+    const int na = blockIdx.x * ROWS + fa;                // accumulator column (weight row)
+    const int oc = glu ? blockIdx.x * (ROWS / 2) + j : na;
+    if (oc >= n_out_total) continue;
+    float va = 0.f, vb_ = 0.f;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      va += red[s * RG + fa / 16][fa % 16][tok];
+      if (glu) vb_ += red[s * RG + fb / 16][fb % 16][tok];
+    }
+    if (p.bias) {
+      va += __bfloat162float(p.bias[na]);
+      if (glu) vb_ += __bfloat162float(p.bias[na + 16]);
+    }
+    if (p.rowbias) {
+      const bf16* rbp = p.rowbias + (tok / p.rowbias_rows) * static_cast<long long>(p.N);
+      va += __bfloat162float(rbp[na]);
+      if (glu) vb_ += __bfloat162float(rbp[na + 16]);
+    }
+    float r;
+    if (p.glu == VB_GLU_SWIGLU) r = silu(va) * vb_;
+    else if (p.glu == VB_GLU_GEGLU) r = va * gelu_erf(vb_);
+    else r = gemv_act(va, p.act);
+    if (p.residual) r = __bfloat162float(p.residual[tok * p.ldr + oc]) + p.alpha * r;
+    else r *= p.alpha;
+    if (p.out_fp32) reinterpret_cast<float*>(p.out)[tok * p.ldo + oc] = r;
+    else reinterpret_cast<bf16*>(p.out)[tok * p.ldo + oc] = __float2bfloat16(r);
+  }
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+// internal entry used by vb200_gemm_bf16 (gemm_tcgen05.cu) for M <= 16
+int vb_launch_gemv(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int64_t M,
+                   int64_t N, int64_t K, const vb_epilogue* e, cudaStream_t stream) {
+  GemvParams p;
+  p.W = reinterpret_cast<const bf16*>(W); p.ldw = ldw;
+  p.X = reinterpret_cast<const bf16*>(A); p.ldx = lda;
+  p.out = out; p.ldo = ldo;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.bias = reinterpret_cast<const bf16*>(e->bias);
+  p.rowbias = reinterpret_cast<const bf16*>(e->rowbias);
+  p.rowbias_rows = e->rowbias_rows > 0 ? static_cast<int>(e->rowbias_rows) : 1;
+  p.residual = reinterpret_cast<const bf16*>(e->residual); p.ldr = e->ldr;
+  p.alpha = e->alpha; p.act = e->act; p.glu = e->glu; p.out_fp32 = e->out_fp32;
+  const bool glu = e->glu != VB_GLU_NONE;
+  // 32-row CTAs when the packed GLU layout requires it or when 16-row CTAs would exceed ~4 per SM
+  const bool rows32 = glu || (N / 16 > 6LL * vb_num_sms());
+  const unsigned grid = static_cast<unsigned>((N + (rows32 ? 31 : 15)) / (rows32 ? 32 : 16));
+  if (M <= 8) {
+    if (rows32) gemv_bf16_kernel<32, 1><<<grid, 256, 0, stream>>>(p);
+    else gemv_bf16_kernel<16, 1><<<grid, 256, 0, stream>>>(p);
+  } else {
+    if (rows32) gemv_bf16_kernel<32, 2><<<grid, 256, 0, stream>>>(p);
+    else gemv_bf16_kernel<16, 2><<<grid, 256, 0, stream>>>(p);
+  }
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
