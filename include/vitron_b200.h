@@ -35,7 +35,9 @@ typedef struct CUstream_st* cudaStream_t;
 #define VB_GLU_SWIGLU 1 /* silu(a) * b   — LlamaMLP: a = gate_proj, b = up_proj     */
 #define VB_GLU_GEGLU 2  /* a * gelu(b)   — GEGLU: x, gate = proj(x).chunk(2)       */
 
-/* Fused GEMM / conv epilogue:  v = acc + bias[col] + rowbias[row / rowbias_rows][col];
+/* Fused GEMM / conv epilogue:  v = rowscale[row] * acc + bias[col] + rowbias[row / rowbias_rows][col];
+ *   (rowscale = 1/rms(x_row) turns a GEMM on un-normalised rows against RMSNorm-weight-folded weights
+ *    into LlamaRMSNorm -> Linear; M <= 16: rms_eps > 0 makes the kernel compute it from A itself)
  *   GLU: columns are packed in blocks of 32 = [16 x a | 16 x b] -> 16 outputs; else v = act(v);
  *   out = residual ? residual[row, col] + alpha * v : alpha * v;   stored as bf16 (or fp32). */
 typedef struct vb_epilogue {
@@ -48,6 +50,8 @@ typedef struct vb_epilogue {
   int32_t act;
   int32_t glu;
   int32_t out_fp32;
+  const float* rowscale; /* fp32 [M] or NULL */
+  float rms_eps;         /* > 0 (M <= 16 only, rowscale NULL): rowscale = rsqrt(mean(A_row^2) + rms_eps) */
 } vb_epilogue;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -87,6 +91,9 @@ int vb200_conv_nhwc_direct(const void* X, const void* Wt, const void* bias, void
  * over NHWC [n, spatial, c] (+ optional SiLU / ReLU), i2vgen util.py:640-655,1358-1375. */
 int vb200_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out, int64_t ldo,
                   int64_t rows, int64_t d, float eps, cudaStream_t stream);
+/* out[row] = rsqrt(mean(x_row^2) + eps), fp32: the rowscale of the RMSNorm-folded GEMMs (prefill) */
+int vb200_row_rstd(const void* x, int64_t ldx, float* out, int64_t rows, int64_t d, float eps,
+                   cudaStream_t stream);
 int vb200_layernorm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out,
                     int64_t ldo, int64_t rows, int64_t d, float eps, cudaStream_t stream);
 size_t vb200_groupnorm_workspace_size(int64_t n, int64_t groups);
@@ -133,6 +140,15 @@ int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* k_pages, co
                             void* out, int64_t ld_o, int64_t B, int64_t n_heads, int64_t head_dim,
                             int64_t page_size, int64_t max_kv_len, float scale, void* workspace,
                             size_t workspace_bytes, cudaStream_t stream);
+/* decode step with RoPE + KV append fused in: qkv rows [B, 3*H*hd] hold the UN-rotated q | k | v of the
+ * new token at position positions[b] (= kv_len[b]-1): q and k are rotated on the fly, k/v are written to
+ * their page, then attention runs over kv_len[b] keys. Replaces rope_kv_append + attn_decode_paged. */
+int vb200_attn_decode_rope(const void* qkv, int64_t ld_qkv, const int32_t* positions, void* k_pages,
+                           void* v_pages, const int32_t* block_table, int64_t max_pages,
+                           const int32_t* kv_len, void* out, int64_t ld_o, int64_t B, int64_t n_heads,
+                           int64_t head_dim, int64_t page_size, int64_t max_kv_len, float scale,
+                           float rope_theta, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream);
 /* inputs_embeds[b, s] = srcmap >= 0 ? embed[srcmap] : feats[-srcmap-1] : the device half of
  * prepare_inputs_labels_for_multimodal (vitron/model/llava_arch.py:478-521); pad rows (srcmap ==
  * INT32_MIN) are zero-filled. */

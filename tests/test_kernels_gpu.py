@@ -344,3 +344,47 @@ def test_region_pool_and_seem_mask(cuda):
     refm = (r.sigmoid() < 0.5).flatten(1)
     refm[refm.sum(-1) == refm.shape[-1]] = False
     assert torch.equal(mk.bool(), refm)
+
+
+@pytest.mark.parametrize("M", [1, 8, 13, 16, 40, 300])
+def test_gemm_fused_rmsnorm(cuda, M):
+    """LlamaRMSNorm -> Linear as ONE GEMM on gain-folded weights with a 1/rms row scale."""
+    from vitron_b200 import ops
+    K, N = 4096, 1024
+    x, w, g = rnd((M, K), cuda, 1, 3.0), rnd((N, K), cuda, 2, 0.02), rnd((K,), cuda, 3)
+    wf = (w.float() * g.float()[None, :]).to(BF)
+    xf = x.float()
+    ref = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * g.float()) @ w.float().t()
+    close(ops.gemm(x, wf, rms_eps=1e-5), ref, 3e-2, 2e-2, f"fused rms gemm M={M}")
+    ga, gb = rnd((512, K), cuda, 4, 0.02), rnd((512, K), cuda, 5, 0.02)
+    wp = ops.pack_glu_weight((ga.float() * g.float()).to(BF), (gb.float() * g.float()).to(BF))
+    xn = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * g.float()
+    refg = F.silu(xn @ ga.float().t()) * (xn @ gb.float().t())
+    close(ops.gemm(x, wp, glu=ops.GLU_SWIGLU, rms_eps=1e-5), refg, 3e-2, 3e-2, f"fused rms swiglu M={M}")
+    rs = ops.row_rstd(x, 1e-5)
+    close(rs, torch.rsqrt(xf.pow(2).mean(-1) + 1e-5), 1e-5, 1e-4, "row_rstd")
+
+
+def test_attn_decode_rope_fused_equals_unfused(cuda):
+    from vitron_b200 import ops
+    B, H, D, PS = 4, 32, 128, 64
+    lens = [130, 65, 777, 1]          # kv_len INCLUDING the new token
+    max_pages = 16
+    g = torch.Generator().manual_seed(0)
+    perm = torch.randperm(B * max_pages, generator=g).to(torch.int32).view(B, max_pages).to(cuda)
+    kp = rnd((B * max_pages, H, PS, D), cuda, 1)
+    vp = rnd((B * max_pages, H, PS, D), cuda, 2)
+    kp2, vp2 = kp.clone(), vp.clone()
+    qkv = rnd((B, 3 * H * D), cuda, 3)
+    kvl = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    pos = kvl - 1
+    bot = torch.arange(B, dtype=torch.int32, device=cuda)
+    # unfused: rope + append, then paged attention
+    q1 = qkv.clone()
+    ops.rope_kv_append(q1, pos, H, D, 10000.0, kp, vp, perm, bot, None, PS)
+    o1 = ops.attn_decode_paged(q1, kp, vp, perm, kvl, H, D, PS, 1024)
+    # fused
+    o2 = ops.attn_decode_rope(qkv.clone(), pos, kp2, vp2, perm, kvl, H, D, PS, 1024, 10000.0)
+    close(o2, o1, 1e-2, 1e-2, "fused decode attention")
+    close(kp2, kp, 1e-2, 1e-2, "k cache append")
+    assert torch.equal(vp2, vp)

@@ -20,6 +20,7 @@ class Epilogue(C.Structure):
         ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_rows", C.c_int64),
         ("residual", C.c_void_p), ("ldr", C.c_int64), ("alpha", C.c_float),
         ("act", C.c_int32), ("glu", C.c_int32), ("out_fp32", C.c_int32),
+        ("rowscale", C.c_void_p), ("rms_eps", C.c_float),
     ]
 
 
@@ -36,6 +37,7 @@ SIGNATURES = {
                                     C.POINTER(Epilogue), _p]),
     "vb200_conv_nhwc_direct": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
     "vb200_rmsnorm": (_i32, [_p, _i64, _p, _p, _i64, _i64, _i64, _f, _p]),
+    "vb200_row_rstd": (_i32, [_p, _i64, _p, _i64, _i64, _f, _p]),
     "vb200_layernorm": (_i32, [_p, _i64, _p, _p, _p, _i64, _i64, _i64, _f, _p]),
     "vb200_groupnorm_workspace_size": (_sz, [_i64, _i64]),
     "vb200_groupnorm_nhwc": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _i32, _p, _sz, _p]),
@@ -47,6 +49,8 @@ SIGNATURES = {
     "vb200_attn_decode_workspace_size": (_sz, [_i64, _i64, _i64, _i64]),
     "vb200_attn_decode_paged": (_i32, [_p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64,
                                        _f, _p, _sz, _p]),
+    "vb200_attn_decode_rope": (_i32, [_p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64,
+                                      _f, _f, _p, _sz, _p]),
     "vb200_splice_multimodal": (_i32, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _p]),
     "vb200_argmax_rows": (_i32, [_p, _i32, _i64, _i64, _i64, _p, _p]),
     "vb200_argmax_advance": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p, _p]),

@@ -51,6 +51,7 @@ struct GemmParams {
   const bf16* residual;  // [rows, ldr] or null; out = residual + alpha * v
   long long ldr;
   float alpha;
+  const float* rowscale;  // fp32 per output row (C orientation) or null
   int act;            // VB_ACT_*
   int glu;            // VB_GLU_*
   int out_fp32;
@@ -78,7 +79,8 @@ __device__ __forceinline__ void reduce_item(const float* __restrict__ ws, int sp
                                             long long ws_ld, int row, int oc, int ncols, void* out, long long ldo,
                                             const bf16* __restrict__ bias, const bf16* __restrict__ rowbias,
                                             int rowbias_rows, const bf16* __restrict__ residual, long long ldr,
-                                            float alpha, int act, int glu, int out_fp32) {
+                                            float alpha, int act, int glu, int out_fp32,
+                                            const float* __restrict__ rowscale = nullptr) {
   const int n_out_total = glu != VB_GLU_NONE ? ncols / 2 : ncols;
   int ca = oc, cb = -1;
   if (glu != VB_GLU_NONE) {
@@ -119,6 +121,7 @@ __device__ __forceinline__ void reduce_item(const float* __restrict__ ws, int sp
     v[j] = 0.f;
     if (oc + j >= n_out_total) continue;
     float va = a[j], vb_ = b[j];
+    if (rowscale) { const float rs = rowscale[row]; va *= rs; vb_ *= rs; }
     if (bias) {
       va += __bfloat162float(bias[ca + j]);
       if (cb >= 0) vb_ += __bfloat162float(bias[cb + j]);
@@ -392,6 +395,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (orow < 0) continue;
           const int gc = col0 + c;  // first accumulator column of this chunk
           if (gc >= p.N) continue;
+          if (p.rowscale != nullptr) {
+            const float rs = p.rowscale[orow];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) f[j] *= rs;
+          }
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < CH; ++j)
@@ -487,7 +495,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int it = et; it < items; it += 128) {
             const int row = r0 + it / chunks, oc = oc0 + (it % chunks) * 8;
             reduce_item(p.ws, p.splits, p.ws_split_stride, p.ws_ld, row, oc, p.cols_c, p.out, p.ldo, p.bias,
-                        p.rowbias, p.rowbias_rows, p.residual, p.ldr, p.alpha, p.act, p.glu, p.out_fp32);
+                        p.rowbias, p.rowbias_rows, p.residual, p.ldr, p.alpha, p.act, p.glu, p.out_fp32, p.rowscale);
           }
           if (et == 0) p.counters[tile] = 0;
         }
@@ -689,6 +697,8 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   p.act = epi->act;
   p.glu = epi->glu;
   p.out_fp32 = epi->out_fp32;
+  p.rowscale = epi->rowscale;
+  VB_CHECK_ARG(epi->rms_eps <= 0.f || epi->rowscale != nullptr);  // in-kernel rstd exists for M <= 16 only
   p.out = out;
   p.ldo = ldo;
 

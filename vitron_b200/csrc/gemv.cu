@@ -24,6 +24,7 @@ struct GemvParams {
   const bf16* bias; const bf16* rowbias; int rowbias_rows;
   const bf16* residual; long long ldr;
   float alpha; int act, glu, out_fp32;
+  const float* rowscale; float rms_eps;
 };
 
 __device__ __forceinline__ float gemv_act(float x, int act) {
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(256) gemv_bf16_kernel(const GemvParams p) {
   constexpr int RG = ROWS / 16;        // row groups per CTA
   constexpr int KS = WARPS / RG;       // k-slices per row group
   __shared__ float red[WARPS][16][NT * 8 + 1];
+  __shared__ float red_sq[WARPS][NT * 8];  // per-warp partial sum of squares of the token rows (fused RMSNorm)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -82,6 +84,8 @@ __global__ void __launch_bounds__(256) gemv_bf16_kernel(const GemvParams p) {
   float acc[NT][4];
 #pragma unroll
   for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const bool do_rms = p.rms_eps > 0.f && p.rowscale == nullptr;
+  float sq0 = 0.f, sq1 = 0.f;
 
   // thread t owns k in [8t, 8t+8) and [32+8t, 32+8t+8) of every 64-chunk (same permutation for W and X)
   auto step = [&](int c) {
@@ -96,6 +100,14 @@ __global__ void __launch_bounds__(256) gemv_bf16_kernel(const GemvParams p) {
     const uint32_t ah[8] = {a_hi0.x, a_hi0.y, a_hi0.z, a_hi0.w, a_hi1.x, a_hi1.y, a_hi1.z, a_hi1.w};
     const uint32_t b0[8] = {b00.x, b00.y, b00.z, b00.w, b01.x, b01.y, b01.z, b01.w};
     const uint32_t b1[8] = {b10.x, b10.y, b10.z, b10.w, b11.x, b11.y, b11.z, b11.w};
+    if (do_rms && rg == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float2 f = unpack_bf16(b0[j]);
+        sq0 += f.x * f.x + f.y * f.y;
+        if (NT == 2) { float2 h2 = unpack_bf16(b1[j]); sq1 += h2.x * h2.x + h2.y * h2.y; }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       mma16816(acc[0], al[2 * j], ah[2 * j], al[2 * j + 1], ah[2 * j + 1], b0[2 * j], b0[2 * j + 1]);
@@ -119,6 +131,11 @@ __global__ void __launch_bounds__(256) gemv_bf16_kernel(const GemvParams p) {
     red[warp][g + 8][i * 8 + 2 * t] = acc[i][2];
     red[warp][g + 8][i * 8 + 2 * t + 1] = acc[i][3];
   }
+  if (do_rms) {
+    sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
+    if (NT == 2) { sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2); }
+    if (t == 0) { red_sq[warp][g] = sq0; if (NT == 2) red_sq[warp][8 + g] = sq1; }
+  }
   __syncthreads();
 
   // ---- epilogue: one thread per (token, output column of this CTA)
@@ -137,6 +154,16 @@ __global__ void __launch_bounds__(256) gemv_bf16_kernel(const GemvParams p) {
     for (int s = 0; s < KS; ++s) {
       va += red[s * RG + fa / 16][fa % 16][tok];
       if (glu) vb_ += red[s * RG + fb / 16][fb % 16][tok];
+    }
+    if (do_rms) {
+      float ss = 0.f;
+#pragma unroll
+      for (int s = 0; s < KS; ++s) ss += red_sq[s * RG][tok];  // row-group-0 warps cover every k once
+      const float rs = rsqrtf(ss / p.K + p.rms_eps);
+      va *= rs; vb_ *= rs;
+    } else if (p.rowscale) {
+      const float rs = p.rowscale[tok];
+      va *= rs; vb_ *= rs;
     }
     if (p.bias) {
       va += __bfloat162float(p.bias[na]);
@@ -175,6 +202,7 @@ int vb_launch_gemv(const void* A, int64_t lda, const void* W, int64_t ldw, void*
   p.rowbias_rows = e->rowbias_rows > 0 ? static_cast<int>(e->rowbias_rows) : 1;
   p.residual = reinterpret_cast<const bf16*>(e->residual); p.ldr = e->ldr;
   p.alpha = e->alpha; p.act = e->act; p.glu = e->glu; p.out_fp32 = e->out_fp32;
+  p.rowscale = e->rowscale; p.rms_eps = e->rms_eps;
   const bool glu = e->glu != VB_GLU_NONE;
   // 32-row CTAs when the packed GLU layout requires it or when 16-row CTAs would exceed ~4 per SM
   const bool rows32 = glu || (N / 16 > 6LL * vb_num_sms());

@@ -76,12 +76,29 @@ __global__ void rope_kv_append_kernel(bf16* __restrict__ qkv, long long ld, cons
 constexpr int DEC_THREADS = 128;
 constexpr int DEC_CHUNK = 256;  // keys per split
 
+// rotate_half RoPE of the 16 dims [16*sub, 16*sub+16) held by lane `sub` of an 8-lane group; the partner
+// dims (+-64) live in lane sub^4. x is rounded to bf16 afterwards, like the unfused rope kernel.
+__device__ __forceinline__ void rope16(float (&x)[16], int sub, int pos, float log2_theta) {
+  constexpr int HD = 128;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float partner = __shfl_xor_sync(0xffffffffu, x[j], 4);
+    const int dlo = (sub & 3) * 16 + j;  // index inside the half
+    const float inv_freq = exp2f(-(2.0f * dlo / HD) * log2_theta);
+    float sn, cs;
+    sincosf(static_cast<float>(pos) * inv_freq, &sn, &cs);
+    const float r = (sub < 4) ? x[j] * cs - partner * sn : x[j] * cs + partner * sn;
+    x[j] = __bfloat162float(__float2bfloat16(r));
+  }
+}
+
+template <bool ROPE>
 __global__ void __launch_bounds__(DEC_THREADS)
-attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, const bf16* __restrict__ k_pages,
-                   const bf16* __restrict__ v_pages, const int32_t* __restrict__ block_table, int max_pages,
+attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict__ k_pages,
+                   bf16* __restrict__ v_pages, const int32_t* __restrict__ block_table, int max_pages,
                    const int32_t* __restrict__ kv_len, int H, int page_size, float scale, int splits,
                    float* __restrict__ ws_ml, float* __restrict__ ws_o, int* __restrict__ counters,
-                   bf16* __restrict__ out, long long ld_o) {
+                   bf16* __restrict__ out, long long ld_o, const int32_t* __restrict__ positions, float log2_theta) {
   constexpr int HD = 128;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,6 +106,7 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, const bf16* __res
   const int len = kv_len[b];
   const int per = (len + splits - 1) / splits;
   const int c0 = split * per, c1 = min(len, c0 + per);
+  const int32_t* bt = block_table + static_cast<long long>(b) * max_pages;
 
   float qv[16];
   {
@@ -96,12 +114,44 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, const bf16* __res
     uint4 u0 = *reinterpret_cast<const uint4*>(qp), u1 = *reinterpret_cast<const uint4*>(qp + 8);
     const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { float2 f = unpack_bf16(uu[j]); qv[2 * j] = f.x * scale; qv[2 * j + 1] = f.y * scale; }
+    for (int j = 0; j < 8; ++j) { float2 f = unpack_bf16(uu[j]); qv[2 * j] = f.x; qv[2 * j + 1] = f.y; }
   }
+  if (ROPE) {
+    const int pos = positions[b];
+    rope16(qv, sub, pos, log2_theta);
+    // the split that owns the newest token (slot len-1) rotates k, and appends k / v to their page
+    const int tnew = len - 1;
+    if (tnew >= c0 && tnew < c1) {
+      if (warp == 0) {  // whole warp runs the shuffles; lane group 0 stores
+        float kv_[16];
+        const bf16* kp = q + static_cast<long long>(b) * ld_q + (static_cast<long long>(H) + h) * HD + sub * 16;
+        uint4 u0 = *reinterpret_cast<const uint4*>(kp), u1 = *reinterpret_cast<const uint4*>(kp + 8);
+        const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { float2 f = unpack_bf16(uu[j]); kv_[2 * j] = f.x; kv_[2 * j + 1] = f.y; }
+        rope16(kv_, sub, pos, log2_theta);
+        if (grp == 0) {
+          const long long off = static_cast<long long>(bt[tnew / page_size]) * H * page_size * HD +
+                                static_cast<long long>(h) * page_size * HD + static_cast<long long>(tnew % page_size) * HD + sub * 16;
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = pack_bf16(kv_[2 * j], kv_[2 * j + 1]);
+          *reinterpret_cast<uint4*>(k_pages + off) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(k_pages + off + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+          const bf16* vp = q + static_cast<long long>(b) * ld_q + (2LL * H + h) * HD + sub * 16;
+          *reinterpret_cast<uint4*>(v_pages + off) = *reinterpret_cast<const uint4*>(vp);
+          *reinterpret_cast<uint4*>(v_pages + off + 8) = *reinterpret_cast<const uint4*>(vp + 8);
+        }
+      }
+      __threadfence_block();
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) qv[j] *= scale;
   float m = -INFINITY, l = 0.f, o[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) o[j] = 0.f;
-  const int32_t* bt = block_table + static_cast<long long>(b) * max_pages;
   const long long head_off = static_cast<long long>(h) * page_size * HD + sub * 16;
   const long long page_stride = static_cast<long long>(H) * page_size * HD;
 
@@ -347,12 +397,11 @@ extern "C" size_t vb200_attn_decode_workspace_size(int64_t B, int64_t n_heads, i
          static_cast<size_t>(B) * n_heads * max_splits * (head_dim + 2) * sizeof(float);
 }
 
-extern "C" int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* k_pages,
-                                       const void* v_pages, const int32_t* block_table,
-                                       int64_t max_pages, const int32_t* kv_len, void* out,
-                                       int64_t ld_o, int64_t B, int64_t n_heads, int64_t head_dim,
-                                       int64_t page_size, int64_t max_kv_len, float scale,
-                                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+static int launch_attn_decode(const void* q, int64_t ld_q, void* k_pages, void* v_pages,
+                              const int32_t* block_table, int64_t max_pages, const int32_t* kv_len, void* out,
+                              int64_t ld_o, int64_t B, int64_t n_heads, int64_t head_dim, int64_t page_size,
+                              int64_t max_kv_len, float scale, void* workspace, size_t workspace_bytes,
+                              const int32_t* positions, float rope_theta, cudaStream_t stream) {
   VB_CHECK_ARG(q && k_pages && v_pages && block_table && kv_len && out);
   VB_CHECK_ARG(B > 0 && n_heads > 0 && page_size > 0 && max_pages > 0);
   if (head_dim != 128) return VB_ERR_UNSUPPORTED;
@@ -369,13 +418,41 @@ extern "C" int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* 
     ws_o = ws_ml + static_cast<size_t>(B) * n_heads * splits * 2;
   }
   dim3 grid(splits, static_cast<unsigned>(n_heads), static_cast<unsigned>(B));
-  attn_decode_kernel<<<grid, DEC_THREADS, 0, stream>>>(
-      reinterpret_cast<const bf16*>(q), ld_q, reinterpret_cast<const bf16*>(k_pages),
-      reinterpret_cast<const bf16*>(v_pages), block_table, static_cast<int>(max_pages), kv_len,
-      static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, ws_ml, ws_o, counters,
-      reinterpret_cast<bf16*>(out), ld_o);
+  if (positions != nullptr)
+    attn_decode_kernel<true><<<grid, DEC_THREADS, 0, stream>>>(
+        reinterpret_cast<const bf16*>(q), ld_q, reinterpret_cast<bf16*>(k_pages), reinterpret_cast<bf16*>(v_pages),
+        block_table, static_cast<int>(max_pages), kv_len, static_cast<int>(n_heads), static_cast<int>(page_size),
+        scale, splits, ws_ml, ws_o, counters, reinterpret_cast<bf16*>(out), ld_o, positions, log2f(rope_theta));
+  else
+    attn_decode_kernel<false><<<grid, DEC_THREADS, 0, stream>>>(
+        reinterpret_cast<const bf16*>(q), ld_q, reinterpret_cast<bf16*>(k_pages), reinterpret_cast<bf16*>(v_pages),
+        block_table, static_cast<int>(max_pages), kv_len, static_cast<int>(n_heads), static_cast<int>(page_size),
+        scale, splits, ws_ml, ws_o, counters, reinterpret_cast<bf16*>(out), ld_o, nullptr, 0.f);
   VB_LAUNCH_CHECK();
   return VB_OK;
+}
+
+extern "C" int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* k_pages,
+                                       const void* v_pages, const int32_t* block_table,
+                                       int64_t max_pages, const int32_t* kv_len, void* out,
+                                       int64_t ld_o, int64_t B, int64_t n_heads, int64_t head_dim,
+                                       int64_t page_size, int64_t max_kv_len, float scale,
+                                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return launch_attn_decode(q, ld_q, const_cast<void*>(k_pages), const_cast<void*>(v_pages), block_table, max_pages,
+                            kv_len, out, ld_o, B, n_heads, head_dim, page_size, max_kv_len, scale, workspace,
+                            workspace_bytes, nullptr, 0.f, stream);
+}
+
+extern "C" int vb200_attn_decode_rope(const void* qkv, int64_t ld_qkv, const int32_t* positions, void* k_pages,
+                                      void* v_pages, const int32_t* block_table, int64_t max_pages,
+                                      const int32_t* kv_len, void* out, int64_t ld_o, int64_t B,
+                                      int64_t n_heads, int64_t head_dim, int64_t page_size,
+                                      int64_t max_kv_len, float scale, float rope_theta, void* workspace,
+                                      size_t workspace_bytes, cudaStream_t stream) {
+  VB_CHECK_ARG(positions != nullptr && ld_qkv >= 3 * n_heads * head_dim);
+  return launch_attn_decode(qkv, ld_qkv, k_pages, v_pages, block_table, max_pages, kv_len, out, ld_o, B, n_heads,
+                            head_dim, page_size, max_kv_len, scale, workspace, workspace_bytes, positions, rope_theta,
+                            stream);
 }
 
 extern "C" int vb200_splice_multimodal(const void* embed, int64_t vocab, const void* feats,

@@ -95,6 +95,26 @@ rownorm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict
   }
 }
 
+// out[row] = rsqrt(mean(x^2) + eps): one warp per row
+__global__ void row_rstd_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, long long rows,
+                                int d, float eps) {
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const bf16* xr = x + row * ldx;
+  float s = 0.f;
+  for (int c = lane * 8; c < d; c += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+    float2 f;
+    f = unpack_bf16(u.x); s += f.x * f.x + f.y * f.y;
+    f = unpack_bf16(u.y); s += f.x * f.x + f.y * f.y;
+    f = unpack_bf16(u.z); s += f.x * f.x + f.y * f.y;
+    f = unpack_bf16(u.w); s += f.x * f.x + f.y * f.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = rsqrtf(s / d + eps);
+}
+
 template <bool LAYER>
 static int launch_rownorm(const void* x, long long ldx, const void* w, const void* b, void* out,
                           long long ldo, long long rows, long long d, float eps, cudaStream_t st) {
@@ -210,6 +230,16 @@ extern "C" int vb200_rmsnorm(const void* x, int64_t ldx, const void* weight, voi
                              int64_t rows, int64_t d, float eps, cudaStream_t stream) {
   VB_CHECK_ARG(x && weight && out && d > 0);
   return launch_rownorm<false>(x, ldx, weight, nullptr, out, ldo, rows, d, eps, stream);
+}
+
+extern "C" int vb200_row_rstd(const void* x, int64_t ldx, float* out, int64_t rows, int64_t d, float eps,
+                              cudaStream_t stream) {
+  VB_CHECK_ARG(x && out && rows >= 0 && d > 0 && d % 8 == 0 && ldx % 8 == 0);
+  if (rows == 0) return VB_OK;
+  row_rstd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, out,
+                                                                             rows, static_cast<int>(d), eps);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
 }
 
 extern "C" int vb200_layernorm(const void* x, int64_t ldx, const void* weight, const void* bias,

@@ -108,7 +108,6 @@ class LlamaEngine:
         self.cache = PagedKVCache(self.cfg, max_batch, max_seq_len, self.device, page_size)
         self.layers = []
         self.embed = None
-        self.norm = None
         self.lm_head = None
         c = self.cfg
         B = max_batch
@@ -137,20 +136,22 @@ class LlamaEngine:
         def get(name):
             return sd[prefix + name].detach().to(device=dev, dtype=BF16)
 
+        def folded(name, ln):
+            # RMSNorm gain folded into the consuming projection: (x * rstd * g) W^T == rstd * x (W diag(g))^T
+            w = sd[prefix + name].detach().to(device=dev, dtype=torch.float32)
+            return (w * sd[prefix + ln].detach().to(device=dev, dtype=torch.float32)[None, :]).to(BF16)
+
         self.embed = get("model.embed_tokens.weight").contiguous()
-        self.norm = get("model.norm.weight").contiguous()
-        self.lm_head = get("lm_head.weight").contiguous()
+        self.lm_head = folded("lm_head.weight", "model.norm.weight").contiguous()
         self.layers = []
         for i in range(self.cfg.num_hidden_layers):
             p = f"model.layers.{i}."
-            wqkv = torch.cat([get(p + "self_attn.q_proj.weight"), get(p + "self_attn.k_proj.weight"),
-                              get(p + "self_attn.v_proj.weight")], 0).contiguous()
-            wgu = ops.pack_glu_weight(get(p + "mlp.gate_proj.weight"), get(p + "mlp.up_proj.weight"))
-            self.layers.append(dict(
-                ln1=get(p + "input_layernorm.weight").contiguous(), wqkv=wqkv,
-                wo=get(p + "self_attn.o_proj.weight").contiguous(),
-                ln2=get(p + "post_attention_layernorm.weight").contiguous(), wgu=wgu,
-                wdown=get(p + "mlp.down_proj.weight").contiguous()))
+            ln1, ln2 = p + "input_layernorm.weight", p + "post_attention_layernorm.weight"
+            wqkv = torch.cat([folded(p + "self_attn.q_proj.weight", ln1), folded(p + "self_attn.k_proj.weight", ln1),
+                              folded(p + "self_attn.v_proj.weight", ln1)], 0).contiguous()
+            wgu = ops.pack_glu_weight(folded(p + "mlp.gate_proj.weight", ln2), folded(p + "mlp.up_proj.weight", ln2))
+            self.layers.append(dict(wqkv=wqkv, wo=get(p + "self_attn.o_proj.weight").contiguous(), wgu=wgu,
+                                    wdown=get(p + "mlp.down_proj.weight").contiguous()))
         self._graphs = {}
         return self
 
@@ -162,15 +163,12 @@ class LlamaEngine:
         def w(*shape):
             return (torch.randn(shape, generator=g, device=dev, dtype=torch.float32) * std).to(BF16)
 
-        ones = lambda n: torch.ones((n,), dtype=BF16, device=dev)
         self.embed = w(c.vocab_size, c.hidden_size)
-        self.norm = ones(c.hidden_size)
-        self.lm_head = w(c.vocab_size, c.hidden_size)
+        self.lm_head = w(c.vocab_size, c.hidden_size)  # unit RMSNorm gains: folding is the identity
         self.layers = []
         for _ in range(c.num_hidden_layers):
             self.layers.append(dict(
-                ln1=ones(c.hidden_size), wqkv=w(3 * c.hidden_size, c.hidden_size), wo=w(c.hidden_size, c.hidden_size),
-                ln2=ones(c.hidden_size),
+                wqkv=w(3 * c.hidden_size, c.hidden_size), wo=w(c.hidden_size, c.hidden_size),
                 wgu=ops.pack_glu_weight(w(c.intermediate_size, c.hidden_size), w(c.intermediate_size, c.hidden_size)),
                 wdown=w(c.hidden_size, c.intermediate_size)))
         self._graphs = {}
@@ -184,24 +182,24 @@ class LlamaEngine:
 
     # ------------------------------------------------------------------ layers
     def _layer(self, i, h, positions, bot, slots, prefill_shape=None, kv_len=None, max_kv_len=0):
-        """h [T, d] is updated in place and returned."""
+        """h [T, d] is updated in place and returned. RMSNorm is never a kernel of its own: its gain is
+        folded into wqkv / wgu and 1/rms is a row scale of the GEMM epilogue (computed inside the
+        weight-streaming kernel for T <= 16)."""
         c, L, cache = self.cfg, self.layers[i], self.cache
         H, D = c.num_attention_heads, c.head_dim
-        x = ops.rmsnorm(h, L["ln1"], c.rms_norm_eps)
-        qkv = ops.gemm(x, L["wqkv"])
-        ops.rope_kv_append(qkv, positions, H, D, c.rope_theta, cache.k(i), cache.v(i), cache.block_table, bot, slots,
-                           cache.page_size)
+        qkv = ops.gemm(h, L["wqkv"], rms_eps=c.rms_norm_eps)
         if prefill_shape is not None:
             B, S = prefill_shape
+            ops.rope_kv_append(qkv, positions, H, D, c.rope_theta, cache.k(i), cache.v(i), cache.block_table, bot, slots,
+                               cache.page_size)
             q4 = qkv.view(B, S, 3, H, D)
             att = ops.attention(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], causal=True, kv_len=kv_len)
             att = att.view(B * S, H * D)
-        else:
-            att = ops.attn_decode_paged(qkv, cache.k(i), cache.v(i), cache.block_table, kv_len, H, D, cache.page_size,
-                                        max_kv_len)
+        else:  # decode: RoPE + KV append happen inside the attention kernel
+            att = ops.attn_decode_rope(qkv, positions, cache.k(i), cache.v(i), cache.block_table, kv_len, H, D,
+                                       cache.page_size, max_kv_len, c.rope_theta)
         ops.gemm(att, L["wo"], residual=h, out=h)
-        x = ops.rmsnorm(h, L["ln2"], c.rms_norm_eps)
-        act = ops.gemm(x, L["wgu"], glu=ops.GLU_SWIGLU)
+        act = ops.gemm(h, L["wgu"], glu=ops.GLU_SWIGLU, rms_eps=c.rms_norm_eps)
         ops.gemm(act, L["wdown"], residual=h, out=h)
         return h
 
@@ -239,12 +237,10 @@ class LlamaEngine:
         self.d_prompt[:B].copy_(kv_len)
         self._lens_host = list(lens)
         if all_logits:
-            hn = ops.rmsnorm(h, self.norm, c.rms_norm_eps)
-            return ops.gemm(hn, self.lm_head, out_fp32=True).view(B, S, c.vocab_size)
+            return ops.gemm(h, self.lm_head, out_fp32=True, rms_eps=c.rms_norm_eps).view(B, S, c.vocab_size)
         last = (torch.arange(B) * S + (lens_t.long() - 1)).to(dev)
         hl = h.index_select(0, last)
-        hn = ops.rmsnorm(hl, self.norm, c.rms_norm_eps)
-        return ops.gemm(hn, self.lm_head, out_fp32=True)
+        return ops.gemm(hl, self.lm_head, out_fp32=True, rms_eps=c.rms_norm_eps)
 
     # ------------------------------------------------------------------ decode
     def _decode_body(self, B):
@@ -255,8 +251,7 @@ class LlamaEngine:
         for i in range(c.num_hidden_layers):
             self._layer(i, h, self.d_pos[:B], self.d_bot[:B], None, kv_len=self.d_len[:B],
                         max_kv_len=self.cache.max_seq_len)
-        hn = ops.rmsnorm(h, self.norm, c.rms_norm_eps)
-        ops.gemm(hn, self.lm_head, out=self.d_logits[:B], out_fp32=True)
+        ops.gemm(h, self.lm_head, out=self.d_logits[:B], out_fp32=True, rms_eps=c.rms_norm_eps)
 
     def _step_kernels(self, B):
         self._decode_body(B)

@@ -71,7 +71,7 @@ def pack_glu_weight(w_a, w_b):
 
 
 def gemm(a, w, bias=None, act=ACT_NONE, glu=GLU_NONE, residual=None, alpha=1.0, rowbias=None,
-         rowbias_rows=0, out=None, out_fp32=False):
+         rowbias_rows=0, out=None, out_fp32=False, rowscale=None, rms_eps=0.0):
     """out[M, N'] = epilogue(a[M, K] @ w[N, K]^T) on tcgen05 tensor cores."""
     lib = _lib.load()
     a2, lda = _rows2d(a)
@@ -94,6 +94,15 @@ def gemm(a, w, bias=None, act=ACT_NONE, glu=GLU_NONE, residual=None, alpha=1.0, 
     epi.act = int(act)
     epi.glu = int(glu)
     epi.out_fp32 = 1 if out_fp32 else 0
+    if rowscale is not None:
+        _req(rowscale.dtype == torch.float32 and rowscale.numel() == M and rowscale.is_contiguous(), "bad rowscale")
+        epi.rowscale = rowscale.data_ptr()
+    elif rms_eps > 0:
+        if M <= 16:
+            epi.rms_eps = float(rms_eps)  # computed inside the weight-streaming kernel
+        else:
+            rs = row_rstd(a2, rms_eps)
+            epi.rowscale = rs.data_ptr()
     if residual is not None:
         r2, ldr = _rows2d(residual)
         _req(r2.dtype == BF16 and r2.shape == (M, n_out), "bad residual")
@@ -307,6 +316,36 @@ def attn_decode_paged(q, k_pages, v_pages, block_table, kv_len, n_heads, head_di
                                       block_table.data_ptr(), block_table.shape[1], kv_len.data_ptr(),
                                       out.data_ptr(), out.stride(0), B, n_heads, head_dim, page_size, max_kv_len,
                                       float(scale), ws.data_ptr(), need, _stream()), "vb200_attn_decode_paged")
+    _launches[0] += 1
+    return out
+
+
+def attn_decode_rope(qkv, positions, k_pages, v_pages, block_table, kv_len, n_heads, head_dim, page_size, max_kv_len,
+                     theta, scale=None, out=None):
+    """Decode attention with RoPE + KV append fused in (qkv rows hold the un-rotated q|k|v of the new token)."""
+    lib = _lib.load()
+    B = qkv.shape[0]
+    scale = 1.0 / math.sqrt(head_dim) if scale is None else scale
+    if out is None:
+        out = torch.empty((B, n_heads * head_dim), dtype=BF16, device=qkv.device)
+    need = lib.vb200_attn_decode_workspace_size(B, n_heads, head_dim, 32)
+    ws = workspace(need, qkv.device, "dec")
+    check(lib.vb200_attn_decode_rope(qkv.data_ptr(), qkv.stride(0), positions.data_ptr(), k_pages.data_ptr(),
+                                     v_pages.data_ptr(), block_table.data_ptr(), block_table.shape[1],
+                                     kv_len.data_ptr(), out.data_ptr(), out.stride(0), B, n_heads, head_dim, page_size,
+                                     max_kv_len, float(scale), float(theta), ws.data_ptr(), need, _stream()),
+          "vb200_attn_decode_rope")
+    _launches[0] += 1
+    return out
+
+
+def row_rstd(x, eps):
+    """fp32 [rows] = rsqrt(mean(x_row^2) + eps)."""
+    lib = _lib.load()
+    x2, ldx = _rows2d(x)
+    out = torch.empty((x2.shape[0],), dtype=torch.float32, device=x.device)
+    check(lib.vb200_row_rstd(x2.data_ptr(), ldx, out.data_ptr(), x2.shape[0], x2.shape[1], float(eps), _stream()),
+          "vb200_row_rstd")
     _launches[0] += 1
     return out
 
