@@ -140,15 +140,17 @@ int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* k_pages, co
                             void* out, int64_t ld_o, int64_t B, int64_t n_heads, int64_t head_dim,
                             int64_t page_size, int64_t max_kv_len, float scale, void* workspace,
                             size_t workspace_bytes, cudaStream_t stream);
+/* rope_table[b] = [cos(pos_b f_i) | sin(pos_b f_i)] fp32, i < head_dim/2: once per decode step */
+int vb200_rope_table(const int32_t* positions, float* table, int64_t B, int64_t head_dim, float rope_theta,
+                     cudaStream_t stream);
 /* decode step with RoPE + KV append fused in: qkv rows [B, 3*H*hd] hold the UN-rotated q | k | v of the
- * new token at position positions[b] (= kv_len[b]-1): q and k are rotated on the fly, k/v are written to
- * their page, then attention runs over kv_len[b] keys. Replaces rope_kv_append + attn_decode_paged. */
-int vb200_attn_decode_rope(const void* qkv, int64_t ld_qkv, const int32_t* positions, void* k_pages,
+ * new token (slot kv_len[b]-1): q and k are rotated on the fly with rope_table, k/v are written to their
+ * page, then attention runs over kv_len[b] keys. Replaces rope_kv_append + attn_decode_paged. */
+int vb200_attn_decode_rope(const void* qkv, int64_t ld_qkv, const float* rope_table, void* k_pages,
                            void* v_pages, const int32_t* block_table, int64_t max_pages,
                            const int32_t* kv_len, void* out, int64_t ld_o, int64_t B, int64_t n_heads,
                            int64_t head_dim, int64_t page_size, int64_t max_kv_len, float scale,
-                           float rope_theta, void* workspace, size_t workspace_bytes,
-                           cudaStream_t stream);
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* inputs_embeds[b, s] = srcmap >= 0 ? embed[srcmap] : feats[-srcmap-1] : the device half of
  * prepare_inputs_labels_for_multimodal (vitron/model/llava_arch.py:478-521); pad rows (srcmap ==
  * INT32_MIN) are zero-filled. */

@@ -384,7 +384,7 @@ def test_attn_decode_rope_fused_equals_unfused(cuda):
     ops.rope_kv_append(q1, pos, H, D, 10000.0, kp, vp, perm, bot, None, PS)
     o1 = ops.attn_decode_paged(q1, kp, vp, perm, kvl, H, D, PS, 1024)
     # fused
-    o2 = ops.attn_decode_rope(qkv.clone(), pos, kp2, vp2, perm, kvl, H, D, PS, 1024, 10000.0)
+    o2 = ops.attn_decode_rope(qkv.clone(), ops.rope_table(pos, D, 10000.0), kp2, vp2, perm, kvl, H, D, PS, 1024)
     close(o2, o1, 1e-2, 1e-2, "fused decode attention")
     close(kp2, kp, 1e-2, 1e-2, "k cache append")
     assert torch.equal(vp2, vp)

@@ -49,8 +49,9 @@ SIGNATURES = {
     "vb200_attn_decode_workspace_size": (_sz, [_i64, _i64, _i64, _i64]),
     "vb200_attn_decode_paged": (_i32, [_p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64,
                                        _f, _p, _sz, _p]),
+    "vb200_rope_table": (_i32, [_p, _p, _i64, _i64, _f, _p]),
     "vb200_attn_decode_rope": (_i32, [_p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64,
-                                      _f, _f, _p, _sz, _p]),
+                                      _f, _p, _sz, _p]),
     "vb200_splice_multimodal": (_i32, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _p]),
     "vb200_argmax_rows": (_i32, [_p, _i32, _i64, _i64, _i64, _p, _p]),
     "vb200_argmax_advance": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p, _p]),

@@ -13,6 +13,7 @@
 // Replaces the same nn.Linear call sites as gemm_tcgen05.cu for tiny M.
 #include "common.cuh"
 #include "vitron_b200.h"
+#include <type_traits>
 
 namespace vb {
 
@@ -39,8 +40,7 @@ __device__ __forceinline__ float gemv_act(float x, int act) {
 
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -87,41 +87,49 @@ __global__ void __launch_bounds__(256) gemv_bf16_kernel(const GemvParams p) {
   const bool do_rms = p.rms_eps > 0.f && p.rowscale == nullptr;
   float sq0 = 0.f, sq1 = 0.f;
 
-  // thread t owns k in [8t, 8t+8) and [32+8t, 32+8t+8) of every 64-chunk (same permutation for W and X)
-  auto step = [&](int c) {
-    const int k0 = c * 64 + 8 * t, k1 = k0 + 32;
-    const bool ok0 = k0 < p.K, ok1 = k1 < p.K;
-    const uint4 a_lo0 = ldg_stream(wa + k0, ok0), a_lo1 = ldg_stream(wa + k1, ok1);
-    const uint4 a_hi0 = ldg_stream(wb + k0, ok0), a_hi1 = ldg_stream(wb + k1, ok1);
-    const uint4 b00 = ldg_cached(x0 + k0, ok0 && x0ok), b01 = ldg_cached(x0 + k1, ok1 && x0ok);
-    uint4 b10 = make_uint4(0, 0, 0, 0), b11 = b10;
-    if (NT == 2) { b10 = ldg_cached(x1 + k0, ok0 && x1ok); b11 = ldg_cached(x1 + k1, ok1 && x1ok); }
-    const uint32_t al[8] = {a_lo0.x, a_lo0.y, a_lo0.z, a_lo0.w, a_lo1.x, a_lo1.y, a_lo1.z, a_lo1.w};
-    const uint32_t ah[8] = {a_hi0.x, a_hi0.y, a_hi0.z, a_hi0.w, a_hi1.x, a_hi1.y, a_hi1.z, a_hi1.w};
-    const uint32_t b0[8] = {b00.x, b00.y, b00.z, b00.w, b01.x, b01.y, b01.z, b01.w};
-    const uint32_t b1[8] = {b10.x, b10.y, b10.z, b10.w, b11.x, b11.y, b11.z, b11.w};
-    if (do_rms && rg == 0) {
+  // thread t owns k in [8t, 8t+8) and [32+8t, 32+8t+8) of every 64-chunk (same permutation for W and X).
+  // Loads of a whole group of chunks are issued before any MMA so that G*4 16-byte weight loads per
+  // thread are in flight (bytes in flight, not FLOPs, set the speed of this kernel).
+  auto run_group = [&](int cbeg, auto G_) {
+    constexpr int G = decltype(G_)::value;
+    uint4 wl[G][2], wh[G][2], xa[G][2], xb[G][2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float2 f = unpack_bf16(b0[j]);
-        sq0 += f.x * f.x + f.y * f.y;
-        if (NT == 2) { float2 h2 = unpack_bf16(b1[j]); sq1 += h2.x * h2.x + h2.y * h2.y; }
-      }
+    for (int u = 0; u < G; ++u) {
+      const int k0 = (cbeg + u) * 64 + 8 * t, k1 = k0 + 32;
+      const bool ok0 = k0 < p.K, ok1 = k1 < p.K;
+      wl[u][0] = ldg_stream(wa + k0, ok0); wl[u][1] = ldg_stream(wa + k1, ok1);
+      wh[u][0] = ldg_stream(wb + k0, ok0); wh[u][1] = ldg_stream(wb + k1, ok1);
+      xa[u][0] = ldg_cached(x0 + k0, ok0 && x0ok); xa[u][1] = ldg_cached(x0 + k1, ok1 && x0ok);
+      if (NT == 2) { xb[u][0] = ldg_cached(x1 + k0, ok0 && x1ok); xb[u][1] = ldg_cached(x1 + k1, ok1 && x1ok); }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      mma16816(acc[0], al[2 * j], ah[2 * j], al[2 * j + 1], ah[2 * j + 1], b0[2 * j], b0[2 * j + 1]);
-      if (NT == 2) mma16816(acc[1], al[2 * j], ah[2 * j], al[2 * j + 1], ah[2 * j + 1], b1[2 * j], b1[2 * j + 1]);
+    for (int u = 0; u < G; ++u) {
+      const uint32_t al[8] = {wl[u][0].x, wl[u][0].y, wl[u][0].z, wl[u][0].w, wl[u][1].x, wl[u][1].y, wl[u][1].z, wl[u][1].w};
+      const uint32_t ah[8] = {wh[u][0].x, wh[u][0].y, wh[u][0].z, wh[u][0].w, wh[u][1].x, wh[u][1].y, wh[u][1].z, wh[u][1].w};
+      const uint32_t b0[8] = {xa[u][0].x, xa[u][0].y, xa[u][0].z, xa[u][0].w, xa[u][1].x, xa[u][1].y, xa[u][1].z, xa[u][1].w};
+      uint32_t b1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (NT == 2) {
+        b1[0] = xb[u][0].x; b1[1] = xb[u][0].y; b1[2] = xb[u][0].z; b1[3] = xb[u][0].w;
+        b1[4] = xb[u][1].x; b1[5] = xb[u][1].y; b1[6] = xb[u][1].z; b1[7] = xb[u][1].w;
+      }
+      if (do_rms && rg == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float2 f = unpack_bf16(b0[j]);
+          sq0 += f.x * f.x + f.y * f.y;
+          if (NT == 2) { float2 h2 = unpack_bf16(b1[j]); sq1 += h2.x * h2.x + h2.y * h2.y; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mma16816(acc[0], al[2 * j], ah[2 * j], al[2 * j + 1], ah[2 * j + 1], b0[2 * j], b0[2 * j + 1]);
+        if (NT == 2) mma16816(acc[1], al[2 * j], ah[2 * j], al[2 * j + 1], ah[2 * j + 1], b1[2 * j], b1[2 * j + 1]);
+      }
     }
   };
   int c = c0;
-  for (; c + 3 < c1; c += 4) {  // four chunks per trip: 16 weight loads (256 B) in flight per thread
-    step(c);
-    step(c + 1);
-    step(c + 2);
-    step(c + 3);
-  }
-  for (; c < c1; ++c) step(c);
+  for (; c + 3 < c1; c += 4) run_group(c, std::integral_constant<int, 4>{});
+  for (; c < c1; ++c) run_group(c, std::integral_constant<int, 1>{});
 
   // ---- cross-warp (k-slice) reduction: red[warp][feature 0..15][token]
 #pragma unroll

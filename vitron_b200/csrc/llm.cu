@@ -78,18 +78,36 @@ constexpr int DEC_CHUNK = 256;  // keys per split
 
 // rotate_half RoPE of the 16 dims [16*sub, 16*sub+16) held by lane `sub` of an 8-lane group; the partner
 // dims (+-64) live in lane sub^4. x is rounded to bf16 afterwards, like the unfused rope kernel.
-__device__ __forceinline__ void rope16(float (&x)[16], int sub, int pos, float log2_theta) {
-  constexpr int HD = 128;
+// cs_table: [64 cos | 64 sin] of this sequence's position (vb200_rope_table), fp32
+__device__ __forceinline__ void rope16(float (&x)[16], int sub, const float* __restrict__ cs_table) {
+  const float4* c4 = reinterpret_cast<const float4*>(cs_table + (sub & 3) * 16);
+  const float4* s4 = reinterpret_cast<const float4*>(cs_table + 64 + (sub & 3) * 16);
+  float cs[16], sn[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 c = __ldg(c4 + j), s = __ldg(s4 + j);
+    cs[4 * j] = c.x; cs[4 * j + 1] = c.y; cs[4 * j + 2] = c.z; cs[4 * j + 3] = c.w;
+    sn[4 * j] = s.x; sn[4 * j + 1] = s.y; sn[4 * j + 2] = s.z; sn[4 * j + 3] = s.w;
+  }
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float partner = __shfl_xor_sync(0xffffffffu, x[j], 4);
-    const int dlo = (sub & 3) * 16 + j;  // index inside the half
-    const float inv_freq = exp2f(-(2.0f * dlo / HD) * log2_theta);
-    float sn, cs;
-    sincosf(static_cast<float>(pos) * inv_freq, &sn, &cs);
-    const float r = (sub < 4) ? x[j] * cs - partner * sn : x[j] * cs + partner * sn;
+    const float r = (sub < 4) ? x[j] * cs[j] - partner * sn[j] : x[j] * cs[j] + partner * sn[j];
     x[j] = __bfloat162float(__float2bfloat16(r));
   }
+}
+
+// table[b] = [cos(pos_b * f_i) | sin(pos_b * f_i)], i < hd/2, f_i = theta^(-2i/hd): shared by every head,
+// split and layer of a decode step, so the transcendental work is done once per token.
+__global__ void rope_table_kernel(const int32_t* __restrict__ positions, float* __restrict__ table, int half,
+                                  float log2_theta) {
+  const int b = blockIdx.x, i = threadIdx.x;
+  if (i >= half) return;
+  const float inv_freq = exp2f(-(static_cast<float>(i) / half) * log2_theta);
+  float sn, cs;
+  sincosf(static_cast<float>(positions[b]) * inv_freq, &sn, &cs);
+  table[b * 2 * half + i] = cs;
+  table[b * 2 * half + half + i] = sn;
 }
 
 template <bool ROPE>
@@ -98,7 +116,7 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
                    bf16* __restrict__ v_pages, const int32_t* __restrict__ block_table, int max_pages,
                    const int32_t* __restrict__ kv_len, int H, int page_size, float scale, int splits,
                    float* __restrict__ ws_ml, float* __restrict__ ws_o, int* __restrict__ counters,
-                   bf16* __restrict__ out, long long ld_o, const int32_t* __restrict__ positions, float log2_theta) {
+                   bf16* __restrict__ out, long long ld_o, const float* __restrict__ rope_table) {
   constexpr int HD = 128;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -117,8 +135,8 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
     for (int j = 0; j < 8; ++j) { float2 f = unpack_bf16(uu[j]); qv[2 * j] = f.x; qv[2 * j + 1] = f.y; }
   }
   if (ROPE) {
-    const int pos = positions[b];
-    rope16(qv, sub, pos, log2_theta);
+    const float* cs_table = rope_table + b * HD;
+    rope16(qv, sub, cs_table);
     // the split that owns the newest token (slot len-1) rotates k, and appends k / v to their page
     const int tnew = len - 1;
     if (tnew >= c0 && tnew < c1) {
@@ -129,7 +147,7 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
         const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) { float2 f = unpack_bf16(uu[j]); kv_[2 * j] = f.x; kv_[2 * j + 1] = f.y; }
-        rope16(kv_, sub, pos, log2_theta);
+        rope16(kv_, sub, cs_table);
         if (grp == 0) {
           const long long off = static_cast<long long>(bt[tnew / page_size]) * H * page_size * HD +
                                 static_cast<long long>(h) * page_size * HD + static_cast<long long>(tnew % page_size) * HD + sub * 16;
@@ -401,7 +419,7 @@ static int launch_attn_decode(const void* q, int64_t ld_q, void* k_pages, void* 
                               const int32_t* block_table, int64_t max_pages, const int32_t* kv_len, void* out,
                               int64_t ld_o, int64_t B, int64_t n_heads, int64_t head_dim, int64_t page_size,
                               int64_t max_kv_len, float scale, void* workspace, size_t workspace_bytes,
-                              const int32_t* positions, float rope_theta, cudaStream_t stream) {
+                              const float* rope_table, cudaStream_t stream) {
   VB_CHECK_ARG(q && k_pages && v_pages && block_table && kv_len && out);
   VB_CHECK_ARG(B > 0 && n_heads > 0 && page_size > 0 && max_pages > 0);
   if (head_dim != 128) return VB_ERR_UNSUPPORTED;
@@ -418,16 +436,16 @@ static int launch_attn_decode(const void* q, int64_t ld_q, void* k_pages, void* 
     ws_o = ws_ml + static_cast<size_t>(B) * n_heads * splits * 2;
   }
   dim3 grid(splits, static_cast<unsigned>(n_heads), static_cast<unsigned>(B));
-  if (positions != nullptr)
+  if (rope_table != nullptr)
     attn_decode_kernel<true><<<grid, DEC_THREADS, 0, stream>>>(
         reinterpret_cast<const bf16*>(q), ld_q, reinterpret_cast<bf16*>(k_pages), reinterpret_cast<bf16*>(v_pages),
         block_table, static_cast<int>(max_pages), kv_len, static_cast<int>(n_heads), static_cast<int>(page_size),
-        scale, splits, ws_ml, ws_o, counters, reinterpret_cast<bf16*>(out), ld_o, positions, log2f(rope_theta));
+        scale, splits, ws_ml, ws_o, counters, reinterpret_cast<bf16*>(out), ld_o, rope_table);
   else
     attn_decode_kernel<false><<<grid, DEC_THREADS, 0, stream>>>(
         reinterpret_cast<const bf16*>(q), ld_q, reinterpret_cast<bf16*>(k_pages), reinterpret_cast<bf16*>(v_pages),
         block_table, static_cast<int>(max_pages), kv_len, static_cast<int>(n_heads), static_cast<int>(page_size),
-        scale, splits, ws_ml, ws_o, counters, reinterpret_cast<bf16*>(out), ld_o, nullptr, 0.f);
+        scale, splits, ws_ml, ws_o, counters, reinterpret_cast<bf16*>(out), ld_o, nullptr);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
@@ -440,19 +458,27 @@ extern "C" int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* 
                                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   return launch_attn_decode(q, ld_q, const_cast<void*>(k_pages), const_cast<void*>(v_pages), block_table, max_pages,
                             kv_len, out, ld_o, B, n_heads, head_dim, page_size, max_kv_len, scale, workspace,
-                            workspace_bytes, nullptr, 0.f, stream);
+                            workspace_bytes, nullptr, stream);
 }
 
-extern "C" int vb200_attn_decode_rope(const void* qkv, int64_t ld_qkv, const int32_t* positions, void* k_pages,
+extern "C" int vb200_rope_table(const int32_t* positions, float* table, int64_t B, int64_t head_dim, float rope_theta,
+                                cudaStream_t stream) {
+  VB_CHECK_ARG(positions && table && B > 0 && head_dim > 0 && head_dim % 2 == 0 && head_dim <= 2048);
+  rope_table_kernel<<<static_cast<unsigned>(B), static_cast<unsigned>((head_dim / 2 + 31) / 32 * 32), 0, stream>>>(
+      positions, table, static_cast<int>(head_dim / 2), log2f(rope_theta));
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+extern "C" int vb200_attn_decode_rope(const void* qkv, int64_t ld_qkv, const float* rope_table, void* k_pages,
                                       void* v_pages, const int32_t* block_table, int64_t max_pages,
                                       const int32_t* kv_len, void* out, int64_t ld_o, int64_t B,
                                       int64_t n_heads, int64_t head_dim, int64_t page_size,
-                                      int64_t max_kv_len, float scale, float rope_theta, void* workspace,
+                                      int64_t max_kv_len, float scale, void* workspace,
                                       size_t workspace_bytes, cudaStream_t stream) {
-  VB_CHECK_ARG(positions != nullptr && ld_qkv >= 3 * n_heads * head_dim);
+  VB_CHECK_ARG(rope_table != nullptr && ld_qkv >= 3 * n_heads * head_dim);
   return launch_attn_decode(qkv, ld_qkv, k_pages, v_pages, block_table, max_pages, kv_len, out, ld_o, B, n_heads,
-                            head_dim, page_size, max_kv_len, scale, workspace, workspace_bytes, positions, rope_theta,
-                            stream);
+                            head_dim, page_size, max_kv_len, scale, workspace, workspace_bytes, rope_table, stream);
 }
 
 extern "C" int vb200_splice_multimodal(const void* embed, int64_t vocab, const void* feats,

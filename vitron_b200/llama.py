@@ -120,6 +120,7 @@ class LlamaEngine:
         self.d_bot = torch.arange(B, dtype=torch.int32, device=dev)
         self.d_next = torch.zeros((B,), dtype=torch.int64, device=dev)
         self.d_logits = torch.zeros((B, c.vocab_size), dtype=torch.float32, device=dev)
+        self.d_rope = torch.zeros((B, c.head_dim), dtype=torch.float32, device=dev)
         # generated ids land here (column = tokens generated so far); persistent so the decode
         # graph survives across generate() calls
         self.token_log = torch.zeros((B, self.cache.max_seq_len), dtype=torch.int64, device=dev)
@@ -196,8 +197,8 @@ class LlamaEngine:
             att = ops.attention(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], causal=True, kv_len=kv_len)
             att = att.view(B * S, H * D)
         else:  # decode: RoPE + KV append happen inside the attention kernel
-            att = ops.attn_decode_rope(qkv, positions, cache.k(i), cache.v(i), cache.block_table, kv_len, H, D,
-                                       cache.page_size, max_kv_len, c.rope_theta)
+            att = ops.attn_decode_rope(qkv, self._rope_tab, cache.k(i), cache.v(i), cache.block_table, kv_len, H, D,
+                                       cache.page_size, max_kv_len)
         ops.gemm(att, L["wo"], residual=h, out=h)
         act = ops.gemm(h, L["wgu"], glu=ops.GLU_SWIGLU, rms_eps=c.rms_norm_eps)
         ops.gemm(act, L["wdown"], residual=h, out=h)
@@ -248,6 +249,7 @@ class LlamaEngine:
         arg-max in d_next, and advances the device-side counters."""
         c = self.cfg
         h = ops.splice_multimodal(self.embed, None, self.d_src[:B])
+        self._rope_tab = ops.rope_table(self.d_pos[:B], c.head_dim, c.rope_theta, out=self.d_rope[:B])
         for i in range(c.num_hidden_layers):
             self._layer(i, h, self.d_pos[:B], self.d_bot[:B], None, kv_len=self.d_len[:B],
                         max_kv_len=self.cache.max_seq_len)

@@ -320,9 +320,22 @@ def attn_decode_paged(q, k_pages, v_pages, block_table, kv_len, n_heads, head_di
     return out
 
 
-def attn_decode_rope(qkv, positions, k_pages, v_pages, block_table, kv_len, n_heads, head_dim, page_size, max_kv_len,
-                     theta, scale=None, out=None):
-    """Decode attention with RoPE + KV append fused in (qkv rows hold the un-rotated q|k|v of the new token)."""
+def rope_table(positions, head_dim, theta, out=None):
+    """fp32 [B, head_dim]: cos | sin of every sequence's current position (once per decode step)."""
+    lib = _lib.load()
+    B = positions.shape[0]
+    if out is None:
+        out = torch.empty((B, head_dim), dtype=torch.float32, device=positions.device)
+    check(lib.vb200_rope_table(positions.data_ptr(), out.data_ptr(), B, head_dim, float(theta), _stream()),
+          "vb200_rope_table")
+    _launches[0] += 1
+    return out
+
+
+def attn_decode_rope(qkv, table, k_pages, v_pages, block_table, kv_len, n_heads, head_dim, page_size, max_kv_len,
+                     scale=None, out=None):
+    """Decode attention with RoPE + KV append fused in (qkv rows hold the un-rotated q|k|v of the new token;
+    table = rope_table(positions))."""
     lib = _lib.load()
     B = qkv.shape[0]
     scale = 1.0 / math.sqrt(head_dim) if scale is None else scale
@@ -330,10 +343,10 @@ def attn_decode_rope(qkv, positions, k_pages, v_pages, block_table, kv_len, n_he
         out = torch.empty((B, n_heads * head_dim), dtype=BF16, device=qkv.device)
     need = lib.vb200_attn_decode_workspace_size(B, n_heads, head_dim, 32)
     ws = workspace(need, qkv.device, "dec")
-    check(lib.vb200_attn_decode_rope(qkv.data_ptr(), qkv.stride(0), positions.data_ptr(), k_pages.data_ptr(),
+    check(lib.vb200_attn_decode_rope(qkv.data_ptr(), qkv.stride(0), table.data_ptr(), k_pages.data_ptr(),
                                      v_pages.data_ptr(), block_table.data_ptr(), block_table.shape[1],
                                      kv_len.data_ptr(), out.data_ptr(), out.stride(0), B, n_heads, head_dim, page_size,
-                                     max_kv_len, float(scale), float(theta), ws.data_ptr(), need, _stream()),
+                                     max_kv_len, float(scale), ws.data_ptr(), need, _stream()),
           "vb200_attn_decode_rope")
     _launches[0] += 1
     return out
