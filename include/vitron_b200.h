@@ -58,6 +58,10 @@ typedef struct vb_epilogue {
 const char* vb200_version(void);
 const char* vb200_last_error(void); /* text of the last CUDA error seen by this library */
 int vb200_device_ok(void);          /* 1 iff the current device is sm_100 (B200) */
+/* Programmatic Dependent Launch for the decode-step kernels (gemv, decode attention, splice, rope table,
+ * arg-max): when on, each of them is launched with programmaticStreamSerialization and overlaps its
+ * prologue / weight prefetch with the tail of its predecessor. Returns the previous setting. */
+int vb200_set_pdl(int enable);
 
 /* ---- GEMM: out[M,N] = epi(A[M,K] @ W[N,K]^T), tcgen05 + TMA (gemm_tcgen05.cu) --------------
  * Replaces every nn.Linear on the path: HF LlamaAttention/LlamaMLP/lm_head (transformers 4.31,

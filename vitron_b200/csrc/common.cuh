@@ -26,6 +26,27 @@
 
 void vb_set_last_error(cudaError_t e);
 int vb_num_sms();
+bool vb_pdl_enabled();
+
+// Launch with Programmatic Dependent Launch when enabled (vb200_set_pdl): the grid may start while its
+// predecessor on the stream drains; kernels call vb::pdl_wait() before touching anything a predecessor
+// wrote (or may still read) and vb::pdl_trigger() to let their own successor start early. Without the
+// attribute both instructions are no-ops.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = vb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 namespace vb {
 
@@ -37,6 +58,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;

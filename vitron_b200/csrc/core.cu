@@ -21,6 +21,14 @@ int vb_num_sms() {
   return sms;
 }
 
+static bool g_pdl = false;
+bool vb_pdl_enabled() { return g_pdl; }
+extern "C" int vb200_set_pdl(int enable) {
+  const int prev = g_pdl ? 1 : 0;
+  g_pdl = enable != 0;
+  return prev;
+}
+
 extern "C" const char* vb200_version(void) { return "vitron_b200 0.1 (sm_100a)"; }
 extern "C" const char* vb200_last_error(void) { return g_last_error; }
 extern "C" int vb200_device_ok(void) {

@@ -58,7 +58,7 @@ __device__ __forceinline__ uint4 ldg_cached(const bf16* p, bool ok) {
 
 // ROWS = 16 or 32 output features per CTA; NT = 1 (M <= 8) or 2 (M <= 16) token tiles of 8.
 template <int ROWS, int NT>
-__global__ void __launch_bounds__(256) gemv_bf16_kernel(const GemvParams p) {
+__global__ void __launch_bounds__(256, 2) gemv_bf16_kernel(const GemvParams p) {
   constexpr int WARPS = 8;
   constexpr int RG = ROWS / 16;        // row groups per CTA
   constexpr int KS = WARPS / RG;       // k-slices per row group
@@ -88,24 +88,36 @@ __global__ void __launch_bounds__(256) gemv_bf16_kernel(const GemvParams p) {
   float sq0 = 0.f, sq1 = 0.f;
 
   // thread t owns k in [8t, 8t+8) and [32+8t, 32+8t+8) of every 64-chunk (same permutation for W and X).
-  // Loads of a whole group of chunks are issued before any MMA so that G*4 16-byte weight loads per
-  // thread are in flight (bytes in flight, not FLOPs, set the speed of this kernel).
-  auto run_group = [&](int cbeg, auto G_) {
-    constexpr int G = decltype(G_)::value;
-    uint4 wl[G][2], wh[G][2], xa[G][2], xb[G][2];
+  // Software pipeline over groups of G chunks with two register buffers: the loads of group i+1 are issued
+  // before the MMAs of group i, so 4G..8G 16-byte weight loads per thread are always in flight (bytes in
+  // flight, not FLOPs, set the speed of this kernel).
+  constexpr int G = 2;
+  struct Buf { uint4 wl[G][2], wh[G][2]; int c; };  // weights only: X comes from L1 at compute time
+  auto load_group = [&](Buf& bf, int cbeg) {
+    bf.c = cbeg;
 #pragma unroll
     for (int u = 0; u < G; ++u) {
       const int k0 = (cbeg + u) * 64 + 8 * t, k1 = k0 + 32;
-      const bool ok0 = k0 < p.K, ok1 = k1 < p.K;
-      wl[u][0] = ldg_stream(wa + k0, ok0); wl[u][1] = ldg_stream(wa + k1, ok1);
-      wh[u][0] = ldg_stream(wb + k0, ok0); wh[u][1] = ldg_stream(wb + k1, ok1);
+      const bool in = (cbeg + u) < c1;
+      const bool ok0 = in && k0 < p.K, ok1 = in && k1 < p.K;
+      bf.wl[u][0] = ldg_stream(wa + k0, ok0); bf.wl[u][1] = ldg_stream(wa + k1, ok1);
+      bf.wh[u][0] = ldg_stream(wb + k0, ok0); bf.wh[u][1] = ldg_stream(wb + k1, ok1);
+    }
+  };
+  auto compute_group = [&](const Buf& bf) {
+    uint4 xa[G][2], xb[G][2];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int k0 = (bf.c + u) * 64 + 8 * t, k1 = k0 + 32;
+      const bool in = (bf.c + u) < c1;
+      const bool ok0 = in && k0 < p.K, ok1 = in && k1 < p.K;
       xa[u][0] = ldg_cached(x0 + k0, ok0 && x0ok); xa[u][1] = ldg_cached(x0 + k1, ok1 && x0ok);
       if (NT == 2) { xb[u][0] = ldg_cached(x1 + k0, ok0 && x1ok); xb[u][1] = ldg_cached(x1 + k1, ok1 && x1ok); }
     }
 #pragma unroll
     for (int u = 0; u < G; ++u) {
-      const uint32_t al[8] = {wl[u][0].x, wl[u][0].y, wl[u][0].z, wl[u][0].w, wl[u][1].x, wl[u][1].y, wl[u][1].z, wl[u][1].w};
-      const uint32_t ah[8] = {wh[u][0].x, wh[u][0].y, wh[u][0].z, wh[u][0].w, wh[u][1].x, wh[u][1].y, wh[u][1].z, wh[u][1].w};
+      const uint32_t al[8] = {bf.wl[u][0].x, bf.wl[u][0].y, bf.wl[u][0].z, bf.wl[u][0].w, bf.wl[u][1].x, bf.wl[u][1].y, bf.wl[u][1].z, bf.wl[u][1].w};
+      const uint32_t ah[8] = {bf.wh[u][0].x, bf.wh[u][0].y, bf.wh[u][0].z, bf.wh[u][0].w, bf.wh[u][1].x, bf.wh[u][1].y, bf.wh[u][1].z, bf.wh[u][1].w};
       const uint32_t b0[8] = {xa[u][0].x, xa[u][0].y, xa[u][0].z, xa[u][0].w, xa[u][1].x, xa[u][1].y, xa[u][1].z, xa[u][1].w};
       uint32_t b1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       if (NT == 2) {
@@ -127,9 +139,16 @@ __global__ void __launch_bounds__(256) gemv_bf16_kernel(const GemvParams p) {
       }
     }
   };
-  int c = c0;
-  for (; c + 3 < c1; c += 4) run_group(c, std::integral_constant<int, 4>{});
-  for (; c < c1; ++c) run_group(c, std::integral_constant<int, 1>{});
+  Buf buf0, buf1;
+  pdl_trigger();
+  load_group(buf0, c0);  // weights do not depend on the previous kernel: prefetch them before the dependency wait
+  pdl_wait();
+  for (int c = c0; c < c1; c += 2 * G) {  // out-of-range chunks load nothing (zero operands)
+    load_group(buf1, c + G);
+    compute_group(buf0);
+    load_group(buf0, c + 2 * G);
+    compute_group(buf1);
+  }
 
   // ---- cross-warp (k-slice) reduction: red[warp][feature 0..15][token]
 #pragma unroll
@@ -215,13 +234,14 @@ int vb_launch_gemv(const void* A, int64_t lda, const void* W, int64_t ldw, void*
   // 32-row CTAs when the packed GLU layout requires it or when 16-row CTAs would exceed ~4 per SM
   const bool rows32 = glu || (N / 16 > 6LL * vb_num_sms());
   const unsigned grid = static_cast<unsigned>((N + (rows32 ? 31 : 15)) / (rows32 ? 32 : 16));
+  cudaError_t err;
   if (M <= 8) {
-    if (rows32) gemv_bf16_kernel<32, 1><<<grid, 256, 0, stream>>>(p);
-    else gemv_bf16_kernel<16, 1><<<grid, 256, 0, stream>>>(p);
+    if (rows32) err = vb_launch(gemv_bf16_kernel<32, 1>, dim3(grid), dim3(256), 0, stream, p);
+    else err = vb_launch(gemv_bf16_kernel<16, 1>, dim3(grid), dim3(256), 0, stream, p);
   } else {
-    if (rows32) gemv_bf16_kernel<32, 2><<<grid, 256, 0, stream>>>(p);
-    else gemv_bf16_kernel<16, 2><<<grid, 256, 0, stream>>>(p);
+    if (rows32) err = vb_launch(gemv_bf16_kernel<32, 2>, dim3(grid), dim3(256), 0, stream, p);
+    else err = vb_launch(gemv_bf16_kernel<16, 2>, dim3(grid), dim3(256), 0, stream, p);
   }
-  VB_LAUNCH_CHECK();
+  if (err != cudaSuccess) { vb_set_last_error(err); return VB_ERR_CUDA; }
   return VB_OK;
 }

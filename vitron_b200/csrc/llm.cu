@@ -74,7 +74,7 @@ __global__ void rope_kv_append_kernel(bf16* __restrict__ qkv, long long ld, cons
 // grid (splits, H, B); 4 warps; 8 lanes per key (16 dims each, head_dim 128), 2 keys in flight
 // per lane group; every lane group runs its own online softmax, merged through smem at the end.
 constexpr int DEC_THREADS = 128;
-constexpr int DEC_CHUNK = 256;  // keys per split
+constexpr int DEC_CHUNK = 512;  // keys per split
 
 // rotate_half RoPE of the 16 dims [16*sub, 16*sub+16) held by lane `sub` of an 8-lane group; the partner
 // dims (+-64) live in lane sub^4. x is rounded to bf16 afterwards, like the unfused rope kernel.
@@ -102,6 +102,8 @@ __device__ __forceinline__ void rope16(float (&x)[16], int sub, const float* __r
 __global__ void rope_table_kernel(const int32_t* __restrict__ positions, float* __restrict__ table, int half,
                                   float log2_theta) {
   const int b = blockIdx.x, i = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (i >= half) return;
   const float inv_freq = exp2f(-(static_cast<float>(i) / half) * log2_theta);
   float sn, cs;
@@ -121,6 +123,8 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 3, sub = lane & 7;
+  pdl_trigger();
+  pdl_wait();
   const int len = kv_len[b];
   const int per = (len + splits - 1) / splits;
   const int c0 = split * per, c1 = min(len, c0 + per);
@@ -173,47 +177,65 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
   const long long head_off = static_cast<long long>(h) * page_size * HD + sub * 16;
   const long long page_stride = static_cast<long long>(H) * page_size * HD;
 
-  // 16 lane groups per CTA, each takes keys c0 + gid, + 16, ... two at a time
+  // 16 lane groups per CTA; a trip covers 64 consecutive keys: lane group gid takes keys tb + gid + 16 u,
+  // u < 4, and issues all 16 K/V loads (256 B per lane) before the first dot product.
   const int gid = warp * 4 + grp;
-  for (int tb = c0; tb < c1; tb += 32) {  // warp-uniform trip count (shuffles below use the full mask)
-    const int t0 = tb + gid, t1 = t0 + 16;
-    const bool has0 = t0 < c1, has1 = t1 < c1;
-    const int u0 = has0 ? t0 : c0, u1 = has1 ? t1 : c0;
-    const long long off0 = static_cast<long long>(bt[u0 / page_size]) * page_stride + static_cast<long long>(u0 % page_size) * HD + head_off;
-    const long long off1 = static_cast<long long>(bt[u1 / page_size]) * page_stride + static_cast<long long>(u1 % page_size) * HD + head_off;
-    uint4 ka0 = *reinterpret_cast<const uint4*>(k_pages + off0), ka1 = *reinterpret_cast<const uint4*>(k_pages + off0 + 8);
-    uint4 kb0 = *reinterpret_cast<const uint4*>(k_pages + off1), kb1 = *reinterpret_cast<const uint4*>(k_pages + off1 + 8);
-    uint4 va0 = *reinterpret_cast<const uint4*>(v_pages + off0), va1 = *reinterpret_cast<const uint4*>(v_pages + off0 + 8);
-    uint4 vb0 = *reinterpret_cast<const uint4*>(v_pages + off1), vb1 = *reinterpret_cast<const uint4*>(v_pages + off1 + 8);
-    const uint32_t ka[8] = {ka0.x, ka0.y, ka0.z, ka0.w, ka1.x, ka1.y, ka1.z, ka1.w};
-    const uint32_t kb[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
-    float s0 = 0.f, s1 = 0.f;
+  for (int tb = c0; tb < c1; tb += 64) {  // warp-uniform trip count (shuffles below use the full mask)
+    uint4 kq[4][2], vq[4][2];
+    bool has[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float2 f0 = unpack_bf16(ka[j]), f1 = unpack_bf16(kb[j]);
-      s0 += qv[2 * j] * f0.x + qv[2 * j + 1] * f0.y;
-      s1 += qv[2 * j] * f1.x + qv[2 * j + 1] * f1.y;
+    for (int u = 0; u < 4; ++u) {
+      const int tk = tb + gid + 16 * u;
+      has[u] = tk < c1;
+      const int tu = has[u] ? tk : c0;
+      const long long off = static_cast<long long>(bt[tu / page_size]) * page_stride + static_cast<long long>(tu % page_size) * HD + head_off;
+      kq[u][0] = *reinterpret_cast<const uint4*>(k_pages + off);
+      kq[u][1] = *reinterpret_cast<const uint4*>(k_pages + off + 8);
+      vq[u][0] = *reinterpret_cast<const uint4*>(v_pages + off);
+      vq[u][1] = *reinterpret_cast<const uint4*>(v_pages + off + 8);
+    }
+    float sc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t kw[8] = {kq[u][0].x, kq[u][0].y, kq[u][0].z, kq[u][0].w, kq[u][1].x, kq[u][1].y, kq[u][1].z, kq[u][1].w};
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float2 f = unpack_bf16(kw[j]);
+        a += qv[2 * j] * f.x + qv[2 * j + 1] * f.y;
+      }
+      sc[u] = a;
     }
 #pragma unroll
     for (int sh = 1; sh < 8; sh <<= 1) {
-      s0 += __shfl_xor_sync(0xffffffffu, s0, sh);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], sh);
     }
-    if (!has0) s0 = -INFINITY;
-    if (!has1) s1 = -INFINITY;
-    const float mn = fmaxf(m, fmaxf(s0, s1));
+    float mn = m;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!has[u]) sc[u] = -INFINITY;
+      mn = fmaxf(mn, sc[u]);
+    }
     const float msafe = (mn == -INFINITY) ? 0.f : mn;
     const float corr = __expf(m - msafe);  // m = -inf on first use -> 0
-    const float p0 = __expf(s0 - msafe), p1 = __expf(s1 - msafe);
-    l = l * corr + p0 + p1;
-    m = mn;
-    const uint32_t va[8] = {va0.x, va0.y, va0.z, va0.w, va1.x, va1.y, va1.z, va1.w};
-    const uint32_t vb_[8] = {vb0.x, vb0.y, vb0.z, vb0.w, vb1.x, vb1.y, vb1.z, vb1.w};
+    float pr[4];
+    float psum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float2 f0 = unpack_bf16(va[j]), f1 = unpack_bf16(vb_[j]);
-      o[2 * j] = o[2 * j] * corr + p0 * f0.x + p1 * f1.x;
-      o[2 * j + 1] = o[2 * j + 1] * corr + p0 * f0.y + p1 * f1.y;
+    for (int u = 0; u < 4; ++u) { pr[u] = __expf(sc[u] - msafe); psum += pr[u]; }
+    l = l * corr + psum;
+    m = mn;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] *= corr;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t vw[8] = {vq[u][0].x, vq[u][0].y, vq[u][0].z, vq[u][0].w, vq[u][1].x, vq[u][1].y, vq[u][1].z, vq[u][1].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float2 f = unpack_bf16(vw[j]);
+        o[2 * j] += pr[u] * f.x;
+        o[2 * j + 1] += pr[u] * f.y;
+      }
     }
   }
 
@@ -270,6 +292,8 @@ __global__ void splice_kernel(const bf16* __restrict__ embed, long long vocab, c
                               long long n_feat, const int32_t* __restrict__ srcmap, bf16* __restrict__ out,
                               int d) {
   const long long row = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   const int src = srcmap[row];
   const bf16* sp = nullptr;
   if (src >= 0 && src < vocab) sp = embed + static_cast<long long>(src) * d;
@@ -326,6 +350,8 @@ argmax_advance_kernel(const float* __restrict__ logits, long long ld, int n, int
   __shared__ float sv[32];
   __shared__ int si[32];
   const int b = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   const float* row = logits + b * ld;
   float best = -INFINITY;
   int bi = INT_MAX;
@@ -373,10 +399,10 @@ extern "C" int vb200_argmax_advance(const float* logits, int64_t ld, int64_t row
                                     int64_t log_stride, const int32_t* prompt_len, cudaStream_t stream) {
   VB_CHECK_ARG(logits && out_idx && rows > 0 && n > 0);
   VB_CHECK_ARG(token_log == nullptr || (kv_len != nullptr && prompt_len != nullptr));
-  argmax_advance_kernel<<<static_cast<unsigned>(rows), 1024, 0, stream>>>(
-      logits, ld, static_cast<int>(n), out_idx, next_src, positions, kv_len, token_log,
-      static_cast<int>(log_stride), prompt_len);
-  VB_LAUNCH_CHECK();
+  cudaError_t e = vb_launch(argmax_advance_kernel, dim3(static_cast<unsigned>(rows)), dim3(1024), 0, stream, logits,
+                            static_cast<long long>(ld), static_cast<int>(n), out_idx, next_src, positions, kv_len,
+                            token_log, static_cast<int>(log_stride), prompt_len);
+  if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
   return VB_OK;
 }
 
@@ -436,17 +462,20 @@ static int launch_attn_decode(const void* q, int64_t ld_q, void* k_pages, void* 
     ws_o = ws_ml + static_cast<size_t>(B) * n_heads * splits * 2;
   }
   dim3 grid(splits, static_cast<unsigned>(n_heads), static_cast<unsigned>(B));
+  cudaError_t e;
   if (rope_table != nullptr)
-    attn_decode_kernel<true><<<grid, DEC_THREADS, 0, stream>>>(
-        reinterpret_cast<const bf16*>(q), ld_q, reinterpret_cast<bf16*>(k_pages), reinterpret_cast<bf16*>(v_pages),
-        block_table, static_cast<int>(max_pages), kv_len, static_cast<int>(n_heads), static_cast<int>(page_size),
-        scale, splits, ws_ml, ws_o, counters, reinterpret_cast<bf16*>(out), ld_o, rope_table);
+    e = vb_launch(attn_decode_kernel<true>, grid, dim3(DEC_THREADS), 0, stream,
+                  reinterpret_cast<const bf16*>(q), static_cast<long long>(ld_q), reinterpret_cast<bf16*>(k_pages),
+                  reinterpret_cast<bf16*>(v_pages), block_table, static_cast<int>(max_pages), kv_len,
+                  static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, ws_ml, ws_o, counters,
+                  reinterpret_cast<bf16*>(out), static_cast<long long>(ld_o), rope_table);
   else
-    attn_decode_kernel<false><<<grid, DEC_THREADS, 0, stream>>>(
-        reinterpret_cast<const bf16*>(q), ld_q, reinterpret_cast<bf16*>(k_pages), reinterpret_cast<bf16*>(v_pages),
-        block_table, static_cast<int>(max_pages), kv_len, static_cast<int>(n_heads), static_cast<int>(page_size),
-        scale, splits, ws_ml, ws_o, counters, reinterpret_cast<bf16*>(out), ld_o, nullptr);
-  VB_LAUNCH_CHECK();
+    e = vb_launch(attn_decode_kernel<false>, grid, dim3(DEC_THREADS), 0, stream,
+                  reinterpret_cast<const bf16*>(q), static_cast<long long>(ld_q), reinterpret_cast<bf16*>(k_pages),
+                  reinterpret_cast<bf16*>(v_pages), block_table, static_cast<int>(max_pages), kv_len,
+                  static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, ws_ml, ws_o, counters,
+                  reinterpret_cast<bf16*>(out), static_cast<long long>(ld_o), static_cast<const float*>(nullptr));
+  if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
   return VB_OK;
 }
 
@@ -464,9 +493,10 @@ extern "C" int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* 
 extern "C" int vb200_rope_table(const int32_t* positions, float* table, int64_t B, int64_t head_dim, float rope_theta,
                                 cudaStream_t stream) {
   VB_CHECK_ARG(positions && table && B > 0 && head_dim > 0 && head_dim % 2 == 0 && head_dim <= 2048);
-  rope_table_kernel<<<static_cast<unsigned>(B), static_cast<unsigned>((head_dim / 2 + 31) / 32 * 32), 0, stream>>>(
-      positions, table, static_cast<int>(head_dim / 2), log2f(rope_theta));
-  VB_LAUNCH_CHECK();
+  cudaError_t e = vb_launch(rope_table_kernel, dim3(static_cast<unsigned>(B)),
+                            dim3(static_cast<unsigned>((head_dim / 2 + 31) / 32 * 32)), 0, stream, positions, table,
+                            static_cast<int>(head_dim / 2), log2f(rope_theta));
+  if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
   return VB_OK;
 }
 
@@ -487,10 +517,11 @@ extern "C" int vb200_splice_multimodal(const void* embed, int64_t vocab, const v
   VB_CHECK_ARG(embed && srcmap && out && d > 0 && d % 8 == 0 && rows >= 0);
   VB_CHECK_ARG(feats != nullptr || n_feat_rows == 0);
   if (rows == 0) return VB_OK;
-  splice_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(
-      reinterpret_cast<const bf16*>(embed), vocab, reinterpret_cast<const bf16*>(feats), n_feat_rows,
-      srcmap, reinterpret_cast<bf16*>(out), static_cast<int>(d));
-  VB_LAUNCH_CHECK();
+  cudaError_t e = vb_launch(splice_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, stream,
+                            reinterpret_cast<const bf16*>(embed), static_cast<long long>(vocab),
+                            reinterpret_cast<const bf16*>(feats), static_cast<long long>(n_feat_rows), srcmap,
+                            reinterpret_cast<bf16*>(out), static_cast<int>(d));
+  if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
   return VB_OK;
 }
 

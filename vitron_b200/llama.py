@@ -126,6 +126,7 @@ class LlamaEngine:
         self.token_log = torch.zeros((B, self.cache.max_seq_len), dtype=torch.int64, device=dev)
         self._graphs = {}
         self.launches_per_step = 0
+        self.use_pdl = True
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, sd, prefix=""):
@@ -256,6 +257,15 @@ class LlamaEngine:
         ops.gemm(h, self.lm_head, out=self.d_logits[:B], out_fp32=True, rms_eps=c.rms_norm_eps)
 
     def _step_kernels(self, B):
+        from . import _lib
+        lib = _lib.load()
+        prev = lib.vb200_set_pdl(1 if self.use_pdl else 0)  # decode-step kernels overlap via PDL
+        try:
+            self._step_kernels_inner(B)
+        finally:
+            lib.vb200_set_pdl(prev)
+
+    def _step_kernels_inner(self, B):
         self._decode_body(B)
         # token_log[b, d_len - d_prompt] = arg-max; d_src = arg-max; d_pos += 1; d_len += 1
         ops.argmax_advance(self.d_logits[:B], self.d_next[:B], next_src=self.d_src[:B], positions=self.d_pos[:B],
