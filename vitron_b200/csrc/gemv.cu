@@ -56,22 +56,24 @@ __device__ __forceinline__ uint4 ldg_cached(const bf16* p, bool ok) {
   return v;
 }
 
-// ROWS = 16 or 32 output features per CTA; NT = 1 (M <= 8) or 2 (M <= 16) token tiles of 8.
+// ROWS = 16 or 32 output features per tile; NT = 1 (M <= 8) or 2 (M <= 16) token tiles of 8.
+// Persistent: grid = 2 CTAs per SM, each CTA walks tiles blockIdx.x, +gridDim.x, ... and keeps its weight
+// load pipeline running ACROSS tiles (the first group of the next tile is requested before the cross-warp
+// reduction / epilogue of the current one), so there is no per-tile ramp-up or drain.
 template <int ROWS, int NT>
 __global__ void __launch_bounds__(256, 2) gemv_bf16_kernel(const GemvParams p) {
   constexpr int WARPS = 8;
-  constexpr int RG = ROWS / 16;        // row groups per CTA
+  constexpr int RG = ROWS / 16;        // row groups per tile
   constexpr int KS = WARPS / RG;       // k-slices per row group
-  __shared__ float red[WARPS][16][NT * 8 + 1];
-  __shared__ float red_sq[WARPS][NT * 8];  // per-warp partial sum of squares of the token rows (fused RMSNorm)
+  constexpr int G = 2;                 // 64-wide k-chunks per load group
+  __shared__ float red[2][WARPS][16][NT * 8 + 1];  // double-buffered by tile parity
+  __shared__ float red_sq[WARPS][NT * 8];
+  __shared__ float rstd_s[NT * 8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int rg = warp % RG, ks = warp / RG;
-  const int row0 = blockIdx.x * ROWS + rg * 16;
-  const int ra = min(row0 + g, p.N - 1), rb = min(row0 + g + 8, p.N - 1);  // clamped (masked in the epilogue)
-  const bf16* wa = p.W + static_cast<long long>(ra) * p.ldw;
-  const bf16* wb = p.W + static_cast<long long>(rb) * p.ldw;
+  const int ntiles = (p.N + ROWS - 1) / ROWS;
   const bf16* x0 = p.X + static_cast<long long>(min(g, p.M - 1)) * p.ldx;
   const bf16* x1 = p.X + static_cast<long long>(min(g + 8, p.M - 1)) * p.ldx;
   const bool x0ok = g < p.M, x1ok = (NT == 2) && (g + 8 < p.M);
@@ -80,36 +82,37 @@ __global__ void __launch_bounds__(256, 2) gemv_bf16_kernel(const GemvParams p) {
   const int base = chunks / KS, rem = chunks % KS;
   const int c0 = ks * base + min(ks, rem);
   const int c1 = c0 + base + (ks < rem ? 1 : 0);
+  const int ngroups = (c1 - c0 + G - 1) / G;
+  const int npairs = (ngroups + 1) / 2;
 
-  float acc[NT][4];
-#pragma unroll
-  for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
   const bool do_rms = p.rms_eps > 0.f && p.rowscale == nullptr;
   float sq0 = 0.f, sq1 = 0.f;
 
-  // thread t owns k in [8t, 8t+8) and [32+8t, 32+8t+8) of every 64-chunk (same permutation for W and X).
-  // Software pipeline over groups of G chunks with two register buffers: the loads of group i+1 are issued
-  // before the MMAs of group i, so 4G..8G 16-byte weight loads per thread are always in flight (bytes in
-  // flight, not FLOPs, set the speed of this kernel).
-  constexpr int G = 2;
-  struct Buf { uint4 wl[G][2], wh[G][2]; int c; };  // weights only: X comes from L1 at compute time
-  auto load_group = [&](Buf& bf, int cbeg) {
-    bf.c = cbeg;
+  struct Buf { uint4 wl[G][2], wh[G][2]; };  // weights only: X comes from L1 at compute time
+  // thread t owns k in [8t, 8t+8) and [32+8t, 32+8t+8) of every 64-chunk (same permutation for W and X)
+  auto load_group = [&](Buf& bf, int tile, int grp) {
+    const int row0 = tile * ROWS + rg * 16;
+    const bf16* wa = p.W + static_cast<long long>(min(row0 + g, p.N - 1)) * p.ldw;      // clamped rows are
+    const bf16* wb = p.W + static_cast<long long>(min(row0 + g + 8, p.N - 1)) * p.ldw;  // masked in the epilogue
+    const bool live = tile < ntiles;
 #pragma unroll
     for (int u = 0; u < G; ++u) {
-      const int k0 = (cbeg + u) * 64 + 8 * t, k1 = k0 + 32;
-      const bool in = (cbeg + u) < c1;
+      const int c = c0 + grp * G + u;
+      const int k0 = c * 64 + 8 * t, k1 = k0 + 32;
+      const bool in = live && c < c1;
       const bool ok0 = in && k0 < p.K, ok1 = in && k1 < p.K;
       bf.wl[u][0] = ldg_stream(wa + k0, ok0); bf.wl[u][1] = ldg_stream(wa + k1, ok1);
       bf.wh[u][0] = ldg_stream(wb + k0, ok0); bf.wh[u][1] = ldg_stream(wb + k1, ok1);
     }
   };
-  auto compute_group = [&](const Buf& bf) {
+  float acc[NT][4];
+  auto compute_group = [&](const Buf& bf, int grp, bool first_tile) {
     uint4 xa[G][2], xb[G][2];
 #pragma unroll
     for (int u = 0; u < G; ++u) {
-      const int k0 = (bf.c + u) * 64 + 8 * t, k1 = k0 + 32;
-      const bool in = (bf.c + u) < c1;
+      const int c = c0 + grp * G + u;
+      const int k0 = c * 64 + 8 * t, k1 = k0 + 32;
+      const bool in = c < c1;
       const bool ok0 = in && k0 < p.K, ok1 = in && k1 < p.K;
       xa[u][0] = ldg_cached(x0 + k0, ok0 && x0ok); xa[u][1] = ldg_cached(x0 + k1, ok1 && x0ok);
       if (NT == 2) { xb[u][0] = ldg_cached(x1 + k0, ok0 && x1ok); xb[u][1] = ldg_cached(x1 + k1, ok1 && x1ok); }
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(256, 2) gemv_bf16_kernel(const GemvParams p) {
         b1[0] = xb[u][0].x; b1[1] = xb[u][0].y; b1[2] = xb[u][0].z; b1[3] = xb[u][0].w;
         b1[4] = xb[u][1].x; b1[5] = xb[u][1].y; b1[6] = xb[u][1].z; b1[7] = xb[u][1].w;
       }
-      if (do_rms && rg == 0) {
+      if (do_rms && first_tile && rg == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float2 f = unpack_bf16(b0[j]);
@@ -139,76 +142,85 @@ __global__ void __launch_bounds__(256, 2) gemv_bf16_kernel(const GemvParams p) {
       }
     }
   };
+
   Buf buf0, buf1;
   pdl_trigger();
-  load_group(buf0, c0);  // weights do not depend on the previous kernel: prefetch them before the dependency wait
+  load_group(buf0, blockIdx.x, 0);  // weights never depend on the previous kernel: request them before the wait
   pdl_wait();
-  for (int c = c0; c < c1; c += 2 * G) {  // out-of-range chunks load nothing (zero operands)
-    load_group(buf1, c + G);
-    compute_group(buf0);
-    load_group(buf0, c + 2 * G);
-    compute_group(buf1);
-  }
 
-  // ---- cross-warp (k-slice) reduction: red[warp][feature 0..15][token]
-#pragma unroll
-  for (int i = 0; i < NT; ++i) {
-    red[warp][g][i * 8 + 2 * t] = acc[i][0];
-    red[warp][g][i * 8 + 2 * t + 1] = acc[i][1];
-    red[warp][g + 8][i * 8 + 2 * t] = acc[i][2];
-    red[warp][g + 8][i * 8 + 2 * t + 1] = acc[i][3];
-  }
-  if (do_rms) {
-    sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
-    if (NT == 2) { sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2); }
-    if (t == 0) { red_sq[warp][g] = sq0; if (NT == 2) red_sq[warp][8 + g] = sq1; }
-  }
-  __syncthreads();
-
-  // ---- epilogue: one thread per (token, output column of this CTA)
   const bool glu = p.glu != VB_GLU_NONE;
   const int out_cols = glu ? ROWS / 2 : ROWS;            // ROWS == 32 when glu
   const int n_out_total = glu ? p.N / 2 : p.N;
-  for (int item = threadIdx.x; item < p.M * out_cols; item += 256) {
-    const int tok = item / out_cols, j = item % out_cols;
-    int fa = j, fb = -1;                                  // feature rows inside the CTA tile
-    if (glu) fb = j + 16;                                 // packed layout: [16 x a | 16 x b]
-    const int na = blockIdx.x * ROWS + fa;                // accumulator column (weight row)
-    const int oc = glu ? blockIdx.x * (ROWS / 2) + j : na;
-    if (oc >= n_out_total) continue;
-    float va = 0.f, vb_ = 0.f;
+  int par = 0;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 #pragma unroll
-    for (int s = 0; s < KS; ++s) {
-      va += red[s * RG + fa / 16][fa % 16][tok];
-      if (glu) vb_ += red[s * RG + fb / 16][fb % 16][tok];
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int pr = 0; pr < npairs; ++pr) {
+      load_group(buf1, tile, 2 * pr + 1);                 // past the slice: loads nothing (zero operands)
+      compute_group(buf0, 2 * pr, first);
+      if (pr + 1 < npairs) load_group(buf0, tile, 2 * pr + 2);
+      else load_group(buf0, tile + gridDim.x, 0);         // first group of the NEXT tile
+      compute_group(buf1, 2 * pr + 1, first);
     }
-    if (do_rms) {
-      float ss = 0.f;
+    // ---- cross-warp (k-slice) reduction: red[par][warp][feature 0..15][token]
 #pragma unroll
-      for (int s = 0; s < KS; ++s) ss += red_sq[s * RG][tok];  // row-group-0 warps cover every k once
-      const float rs = rsqrtf(ss / p.K + p.rms_eps);
-      va *= rs; vb_ *= rs;
-    } else if (p.rowscale) {
-      const float rs = p.rowscale[tok];
-      va *= rs; vb_ *= rs;
+    for (int i = 0; i < NT; ++i) {
+      red[par][warp][g][i * 8 + 2 * t] = acc[i][0];
+      red[par][warp][g][i * 8 + 2 * t + 1] = acc[i][1];
+      red[par][warp][g + 8][i * 8 + 2 * t] = acc[i][2];
+      red[par][warp][g + 8][i * 8 + 2 * t + 1] = acc[i][3];
     }
-    if (p.bias) {
-      va += __bfloat162float(p.bias[na]);
-      if (glu) vb_ += __bfloat162float(p.bias[na + 16]);
+    if (do_rms && first) {
+      sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
+      if (NT == 2) { sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2); }
+      if (t == 0) { red_sq[warp][g] = sq0; if (NT == 2) red_sq[warp][8 + g] = sq1; }
     }
-    if (p.rowbias) {
-      const bf16* rbp = p.rowbias + (tok / p.rowbias_rows) * static_cast<long long>(p.N);
-      va += __bfloat162float(rbp[na]);
-      if (glu) vb_ += __bfloat162float(rbp[na + 16]);
+    __syncthreads();
+    if (do_rms && first) {
+      if (threadIdx.x < NT * 8) {
+        float ss = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < KS; ++s2) ss += red_sq[s2 * RG][threadIdx.x];  // row-group-0 warps cover every k once
+        rstd_s[threadIdx.x] = rsqrtf(ss / p.K + p.rms_eps);
+      }
+      __syncthreads();
     }
-    float r;
-    if (p.glu == VB_GLU_SWIGLU) r = silu(va) * vb_;
-    else if (p.glu == VB_GLU_GEGLU) r = va * gelu_erf(vb_);
-    else r = gemv_act(va, p.act);
-    if (p.residual) r = __bfloat162float(p.residual[tok * p.ldr + oc]) + p.alpha * r;
-    else r *= p.alpha;
-    if (p.out_fp32) reinterpret_cast<float*>(p.out)[tok * p.ldo + oc] = r;
-    else reinterpret_cast<bf16*>(p.out)[tok * p.ldo + oc] = __float2bfloat16(r);
+    // ---- epilogue: one thread per (token, output column of this tile)
+    for (int item = threadIdx.x; item < p.M * out_cols; item += 256) {
+      const int tok = item / out_cols, j = item % out_cols;
+      const int fa = j, fb = j + 16;                       // packed GLU layout: [16 x a | 16 x b]
+      const int na = tile * ROWS + fa;                      // accumulator column (weight row)
+      const int oc = glu ? tile * (ROWS / 2) + j : na;
+      if (oc >= n_out_total) continue;
+      float va = 0.f, vb_ = 0.f;
+#pragma unroll
+      for (int s2 = 0; s2 < KS; ++s2) {
+        va += red[par][s2 * RG + fa / 16][fa % 16][tok];
+        if (glu) vb_ += red[par][s2 * RG + (fb / 16) % RG][fb % 16][tok];
+      }
+      if (do_rms) { const float rs = rstd_s[tok]; va *= rs; vb_ *= rs; }
+      else if (p.rowscale) { const float rs = p.rowscale[tok]; va *= rs; vb_ *= rs; }
+      if (p.bias) {
+        va += __bfloat162float(p.bias[na]);
+        if (glu) vb_ += __bfloat162float(p.bias[na + 16]);
+      }
+      if (p.rowbias) {
+        const bf16* rbp = p.rowbias + (tok / p.rowbias_rows) * static_cast<long long>(p.N);
+        va += __bfloat162float(rbp[na]);
+        if (glu) vb_ += __bfloat162float(rbp[na + 16]);
+      }
+      float r;
+      if (p.glu == VB_GLU_SWIGLU) r = silu(va) * vb_;
+      else if (p.glu == VB_GLU_GEGLU) r = va * gelu_erf(vb_);
+      else r = gemv_act(va, p.act);
+      if (p.residual) r = __bfloat162float(p.residual[tok * p.ldr + oc]) + p.alpha * r;
+      else r *= p.alpha;
+      if (p.out_fp32) reinterpret_cast<float*>(p.out)[tok * p.ldo + oc] = r;
+      else reinterpret_cast<bf16*>(p.out)[tok * p.ldo + oc] = __float2bfloat16(r);
+    }
+    par ^= 1;
+    first = false;
   }
 }
 
@@ -233,7 +245,9 @@ int vb_launch_gemv(const void* A, int64_t lda, const void* W, int64_t ldw, void*
   const bool glu = e->glu != VB_GLU_NONE;
   // 32-row CTAs when the packed GLU layout requires it or when 16-row CTAs would exceed ~4 per SM
   const bool rows32 = glu || (N / 16 > 6LL * vb_num_sms());
-  const unsigned grid = static_cast<unsigned>((N + (rows32 ? 31 : 15)) / (rows32 ? 32 : 16));
+  const unsigned tiles = static_cast<unsigned>((N + (rows32 ? 31 : 15)) / (rows32 ? 32 : 16));
+  const unsigned cap = 2u * static_cast<unsigned>(vb_num_sms());  // persistent: 2 CTAs per SM
+  const unsigned grid = tiles < cap ? tiles : cap;
   cudaError_t err;
   if (M <= 8) {
     if (rows32) err = vb_launch(gemv_bf16_kernel<32, 1>, dim3(grid), dim3(256), 0, stream, p);
