@@ -266,6 +266,53 @@ def run_profile():
     print(json.dumps({"profile": "ok", "tokens": eng.token_log[:BATCH, :5].tolist()}))
 
 
+UNET_CFG = dict(in_dim=4, concat_dim=4, dim=320, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
+                head_dim=64, num_res_blocks=2, attn_scales=[1.0, 0.5, 0.25], num_tokens=4)
+UNET_TFLOP_PER_FORWARD = 12.67  # algorithmic FLOPs of the reference class at f=16, 40x64 latent
+
+
+def bench_unet(device, tf_peak, steps=3):
+    """Second half of BASELINE.json's metric: i2vgen-xl UNet3D denoise steps/s (config 5: 16 x (40x64) latent
+    = 320x512 px, DDIM step = 2 UNet forwards with classifier-free guidance 9.0), bf16, random-init 1.42 B
+    parameter UNetSD_I2VGen, one request on one GPU, CUDA-graphed step."""
+    from vitron_b200 import ops
+    from vitron_b200 import param_shapes as PS
+    from vitron_b200.unet_i2vgen import DiffusionDDIM, GraphedCFGDenoiser, UNetSD_I2VGen
+    unet = UNetSD_I2VGen(**UNET_CFG, device=device)
+    sd = PS.random_state_dict(PS.unet_shapes(UNET_CFG), device, seed=4)
+    unet.load_state_dict(sd)
+    del sd
+    g = torch.Generator(device=device).manual_seed(4)
+    rn = lambda *s: torch.randn(s, generator=g, device=device)
+    noise, local = rn(1, 4, 16, 40, 64), rn(1, 4, 16, 40, 64)
+    cond = dict(y=rn(1, 77, 1024), image=rn(1, 1, 1024), local_image=local, fps=torch.tensor([16], device=device))
+    unc = dict(y=rn(1, 77, 1024), image=torch.zeros((1, 1, 1024), device=device), local_image=local,
+               fps=torch.tensor([16], device=device))
+    den = GraphedCFGDenoiser(unet, cond, unc, 9.0, noise, torch.zeros((1,), dtype=torch.long, device=device))
+    diff = DiffusionDDIM()
+    xt = noise
+    ts = [981, 961, 941, 921, 901, 881, 861, 841]
+    for tv in ts[:2]:  # warm-up + capture
+        xt, _ = diff.ddim_sample(xt, torch.tensor([tv], device=device), den, None, 9.0, 50)
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for tv in ts[2:2 + steps]:
+        xt, _ = diff.ddim_sample(xt, torch.tensor([tv], device=device), den, None, 9.0, 50)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    tfs = 2 * UNET_TFLOP_PER_FORWARD / (ms * 1e-3)
+    finite = bool(torch.isfinite(xt).all())
+    del unet, den
+    torch.cuda.empty_cache()
+    return {"metric": "i2vgen-xl UNet3D DDIM steps/s (2 UNet forwards + CFG per step)", "value": 1000.0 / ms, "unit": "steps/s",
+            "ms_per_step": ms, "latent": [1, 4, 16, 40, 64], "guide_scale": 9.0, "launches_per_step": (ops.launch_count() - l0) // steps,
+            "achieved_tflops": tfs, "frac_of_bf16_peak": tfs / tf_peak, "finite": finite,
+            "algorithmic_tflop_per_step": 2 * UNET_TFLOP_PER_FORWARD}
+
+
 def run_ours(args, rank, world):
     from vitron_b200 import _lib, ops
     lib = _lib.load()
@@ -353,6 +400,10 @@ def run_ours(args, rank, world):
                 "phases": {"vit_projector_ms": t_vit, "prefill_ms": t_pre, "decode_ms_per_token": t_dec,
                            "prefill_tokens_per_s": BATCH * S / (t_pre * 1e-3),
                            "decode_tokens_per_s": BATCH / (t_dec * 1e-3)}}
+        if world == 1 and not args.no_unet:
+            del model
+            torch.cuda.empty_cache()
+            line["unet"] = bench_unet(device, tf_peak)
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "oracle port, fp32, ViT 2/23 + LLaMA 2/32 layers (prefill B=1 S=768, 4 decode "
@@ -370,6 +421,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-unet", action="store_true", help="skip the secondary i2vgen-xl UNet3D steps/s measurement")
     ap.add_argument("--profile", action="store_true",
                     help="ncu launch-list mode: one un-graphed step with 4 decode tokens, no timing loops")
     args = ap.parse_args()

@@ -80,14 +80,82 @@ def vitron_shapes(cfg):
     return s
 
 
+def unet_shapes(cfg):
+    """Reference parameter names / shapes of UNetSD_I2VGen for a config (block plan = the drop-in's own,
+    which mirrors unet_i2vgen.py:133-233)."""
+    from .unet_i2vgen import UNetSD_I2VGen
+    dim, ed, ctx = cfg["dim"], cfg["dim"] * 4, cfg["context_dim"]
+    cd = cfg["in_dim"]
+    s = {}
+
+    def lin(p, o, i, bias=True):
+        s[p + ".weight"] = [o, i]
+        if bias:
+            s[p + ".bias"] = [o]
+
+    def norm(p, c):
+        s[p + ".weight"] = [c]
+        s[p + ".bias"] = [c]
+
+    def tblock(p, inner, cdim):
+        for a, kd in (("attn1", inner), ("attn2", cdim)):
+            lin(f"{p}.{a}.to_q", inner, inner, False); lin(f"{p}.{a}.to_k", inner, kd, False); lin(f"{p}.{a}.to_v", inner, kd, False)
+            lin(f"{p}.{a}.to_out.0", inner, inner)
+        for n in ("norm1", "norm2", "norm3"):
+            norm(f"{p}.{n}", inner)
+        lin(f"{p}.ff.net.0.proj", inner * 8, inner); lin(f"{p}.ff.net.2", inner, inner * 4)
+
+    for n, i in (("time_embed", dim), ("fps_embedding", dim), ("context_embedding", cfg["y_dim"])):
+        lin(n + ".0", ed, i); lin(n + ".2", ctx * cfg["num_tokens"] if n == "context_embedding" else ed, ed)
+    for k, (o, i) in zip((0, 2, 4), ((cd * 4, 4), (cd * 4, cd * 4), (cd, cd * 4))):
+        s[f"local_image_concat.{k}.weight"] = [o, i, 3, 3]; s[f"local_image_concat.{k}.bias"] = [o]
+    p = "local_temporal_encoder.layers.0."
+    norm(p + "0.norm", cd); lin(p + "0.fn.to_qkv", cd * 2 * 3, cd, False); lin(p + "0.fn.to_out.0", cd, cd * 2)
+    lin(p + "1.net.0.0", cd * 4, cd); lin(p + "1.net.2", cd, cd * 4)
+    for k, (o, i) in zip((0, 3, 5), ((cd * 8, 4), (cd * 16, cd * 8), (1024, cd * 16))):
+        s[f"local_image_embedding.{k}.weight"] = [o, i, 3, 3]; s[f"local_image_embedding.{k}.bias"] = [o]
+    m = UNetSD_I2VGen(**cfg, device="cpu")
+    blocks = list(m._all_blocks())
+    for kind, p, ci, co in blocks:
+        if kind == "conv_in":
+            s[p + ".weight"] = [dim, cfg["in_dim"] + cd, 3, 3]; s[p + ".bias"] = [dim]
+        elif kind == "res":
+            norm(p + ".in_layers.0", ci); s[p + ".in_layers.2.weight"] = [co, ci, 3, 3]; s[p + ".in_layers.2.bias"] = [co]
+            lin(p + ".emb_layers.1", co, ed); norm(p + ".out_layers.0", co)
+            s[p + ".out_layers.3.weight"] = [co, co, 3, 3]; s[p + ".out_layers.3.bias"] = [co]
+            if ci != co:
+                s[p + ".skip_connection.weight"] = [co, ci, 1, 1]; s[p + ".skip_connection.bias"] = [co]
+            for c_, l_ in ((1, 2), (2, 3), (3, 3), (4, 3)):
+                norm(f"{p}.temopral_conv.conv{c_}.0", co)
+                s[f"{p}.temopral_conv.conv{c_}.{l_}.weight"] = [co, co, 3, 1, 1]; s[f"{p}.temopral_conv.conv{c_}.{l_}.bias"] = [co]
+        elif kind == "st":
+            norm(p + ".norm", ci); lin(p + ".proj_in", ci, ci); lin(p + ".proj_out", ci, ci)
+            tblock(p + ".transformer_blocks.0", ci, ctx)
+        elif kind == "tt":
+            inner = co * cfg["head_dim"]
+            norm(p + ".norm", ci)
+            s[p + ".proj_in.weight"] = [inner, ci, 1]; s[p + ".proj_in.bias"] = [inner]
+            s[p + ".proj_out.weight"] = [ci, inner, 1]; s[p + ".proj_out.bias"] = [ci]
+            tblock(p + ".transformer_blocks.0", inner, inner)
+        elif kind == "down":
+            s[p + ".op.weight"] = [co, ci, 3, 3]; s[p + ".op.bias"] = [co]
+        elif kind == "up":
+            s[p + ".conv.weight"] = [co, ci, 3, 3]; s[p + ".conv.bias"] = [co]
+    fd = dim
+    norm("out.0", fd); s["out.2.weight"] = [cfg["out_dim"], fd, 3, 3]; s["out.2.bias"] = [cfg["out_dim"]]
+    return s
+
+
 def random_state_dict(shapes, device, seed=0, std=0.02):
     """N(0, std) weights, unit norm gains, zero biases, generated on `device`."""
     g = torch.Generator(device=device).manual_seed(seed)
     out = {}
     for name, shape in shapes.items():
         low = name.lower()
-        if len(shape) == 1 and low.endswith("weight") and ("norm" in low):
+        if len(shape) == 1 and low.endswith("weight"):  # every 1-D ".weight" on the path is a norm gain
             out[name] = torch.ones(shape, dtype=BF16, device=device)
+        elif len(shape) == 0:
+            out[name] = torch.zeros(shape, dtype=BF16, device=device)
         elif low.endswith("bias"):
             out[name] = torch.zeros(shape, dtype=BF16, device=device)
         else:

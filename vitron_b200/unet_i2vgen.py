@@ -28,7 +28,7 @@ BF16 = torch.bfloat16
 def sinusoidal_embedding(timesteps, dim):
     half = dim // 2
     timesteps = timesteps.float()
-    sinusoid = torch.outer(timesteps, torch.pow(10000, -torch.arange(half).to(timesteps).div(half)))
+    sinusoid = torch.outer(timesteps, torch.pow(10000, -torch.arange(half, device=timesteps.device).to(timesteps).div(half)))
     x = torch.cat([torch.cos(sinusoid), torch.sin(sinusoid)], dim=1)
     if dim % 2 != 0:
         x = torch.cat([x, torch.zeros_like(x[:, :1])], dim=1)
@@ -366,6 +366,45 @@ class UNetSD_I2VGen:
     __call__ = forward
 
 
+class GraphedCFGDenoiser:
+    """One classifier-free-guidance evaluation  u + s (y - u)  = 2 UNet forwards + combine, captured in a
+    CUDA graph (≈1500 kernel launches per DDIM step would otherwise be bound by the host launch rate).
+    The conditioning (y / image / local_image / fps) is fixed per video; xt and t are static buffers."""
+
+    def __init__(self, unet, cond, uncond, guide_scale, xt_like, t_like):
+        self.unet, self.cond, self.uncond, self.scale = unet, cond, uncond, float(guide_scale)
+        self.xt = xt_like.detach().clone().float().contiguous()
+        self.t = t_like.detach().clone()
+        self.graph = None
+        self.out = None
+
+    def _eval(self):
+        y = self.unet(self.xt, self.t, **self.cond).float().contiguous()
+        u = self.unet(self.xt, self.t, **self.uncond).float().contiguous()
+        return ops.cfg_combine(y, u, self.scale)
+
+    def __call__(self, xt, t):
+        self.xt.copy_(xt)
+        self.t.copy_(t)
+        if self.graph is None:
+            s = torch.cuda.Stream(device=self.xt.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):  # warm-up: workspaces, adapter cache, lazy attributes
+                    self._eval()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                self.out = self._eval()
+            self.launches = ops.launch_count() - l0
+            self.graph = g
+        self.graph.replay()
+        ops.count_launches(self.launches)
+        return self.out
+
+
 # ====================================================================================== DDIM sampler
 def _cosine_betas(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True):
     """schedules.py:50-57 (+ rescale_zero_terminal_snr :121-143), float64."""
@@ -410,7 +449,9 @@ class DiffusionDDIM:
     @torch.no_grad()
     def ddim_sample(self, xt, t, model, model_kwargs, guide_scale=None, ddim_timesteps=20, eta=0.0, clamp=None):
         stride = self.num_timesteps // ddim_timesteps
-        if guide_scale is None:
+        if isinstance(model, GraphedCFGDenoiser):
+            out = model(xt, t)
+        elif guide_scale is None:
             out = model(xt, t, **model_kwargs).float()
         else:
             y_out = model(xt, t, **model_kwargs[0]).float().contiguous()
@@ -435,11 +476,16 @@ class DiffusionDDIM:
 
     @torch.no_grad()
     def ddim_sample_loop(self, noise, model, model_kwargs={}, clamp=None, percentile=None, condition_fn=None,
-                         guide_scale=None, ddim_timesteps=20, eta=0.0):
+                         guide_scale=None, ddim_timesteps=20, eta=0.0, use_graph=False):
+        """Reference signature (+ use_graph: capture the per-step CFG evaluation of a UNetSD_I2VGen in a
+        CUDA graph)."""
         if percentile is not None or condition_fn is not None:
             raise NotImplementedError("percentile / condition_fn are not used by the i2vgen-xl inference entrance")
         b = noise.size(0)
         xt = noise.float()
+        if use_graph and guide_scale is not None and isinstance(model, UNetSD_I2VGen):
+            model = GraphedCFGDenoiser(model, model_kwargs[0], model_kwargs[1], guide_scale, xt,
+                                       torch.zeros((b,), dtype=torch.long, device=xt.device))
         steps = (1 + torch.arange(0, self.num_timesteps, self.num_timesteps // ddim_timesteps)).clamp(
             0, self.num_timesteps - 1).flip(0)
         for step in steps:
