@@ -59,6 +59,7 @@ struct GemmParams {
   float* ws;          // split-K / swap workspace [splits, rows_c, cols_c] fp32
   long long ws_split_stride;
   long long ws_ld;
+  int c_box;          // > 0: bf16 output leaves through smem + TMA store in boxes of c_box (64 | 32) columns
   int* counters;      // one arrival counter per output tile (zero on entry, zero again on exit)
   int rows_c, cols_c; // extent of the output in C orientation (rows = tokens, cols = features)
 };
@@ -185,11 +186,13 @@ __device__ __forceinline__ void split_range(const GemmParams& p, int split, int&
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                         const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int ACC_STAGES = 2;
+  constexpr int C_STAGE_BYTES = (BLOCK_N >= 32) ? 2 * BLOCK_M * 128 : 0;
   constexpr uint32_t TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32)    ? 32
                                  : (ACC_STAGES * BLOCK_N <= 64)  ? 64
                                  : (ACC_STAGES * BLOCK_N <= 128) ? 128
@@ -198,7 +201,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* cstage = smem + STAGES * STAGE_BYTES;  // 2 x 16 KB output staging for the TMA-store epilogue
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(cstage + C_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
@@ -211,6 +215,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (p.c_box > 0) prefetch_tmap(&tmap_c);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -311,6 +316,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     int acc = 0;
     uint32_t acc_phase = 0;
+    int cbuf = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       TileCoord t = decode_work(p, unit);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -371,6 +377,118 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       } else {
+        if constexpr (BLOCK_N >= 32) {
+          if (p.c_box > 0) {
+            // -------- fused epilogue -> 128B/64B-swizzled smem tile -> TMA store (coalesced, clipped by the
+            // tensor map at the ragged edges; conv: one 4-D box per pixel tile, mirroring the A load)
+            const bool g = p.glu != VB_GLU_NONE;
+            const int bw = p.c_box;                       // output columns per box
+            const int outs_per_acc = g ? 16 : 32;         // outputs produced by one 32-column accumulator chunk
+            const int acc_per_box = bw / outs_per_acc;
+            const int nboxes = (g ? BLOCK_N / 2 : BLOCK_N) / bw;
+            const int row_bytes = bw * 2;
+            const int swz_shift = bw == 64 ? 0 : 1, swz_mask = bw == 64 ? 7 : 3;
+            const int et = threadIdx.x - 64;
+            const bf16* rb = nullptr;
+            if (p.rowbias != nullptr && orow >= 0) rb = p.rowbias + (orow / p.rowbias_rows) * static_cast<long long>(p.N);
+            const float rs = (p.rowscale != nullptr && orow >= 0) ? p.rowscale[orow] : 1.f;
+            const int n_out_total = g ? (p.N >> 1) : p.N;
+            const int ocol0 = g ? col0 / 2 : col0;
+#pragma unroll 1
+            for (int bx = 0; bx < nboxes; ++bx) {
+              uint8_t* cb = cstage + (cbuf & 1) * (BLOCK_M * 128);
+              ++cbuf;
+              if (et == 0) bulk_wait_read<1>();           // the store that last used this buffer has read it
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+              for (int a = 0; a < acc_per_box; ++a) {
+                const int c = (bx * acc_per_box + a) * 32;
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c, v);
+                tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * rs;
+                const int gc = col0 + c;
+                if (p.bias != nullptr) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (gc + j < p.N) f[j] += __bfloat162float(p.bias[gc + j]);
+                }
+                if (rb != nullptr) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (gc + j < p.N) f[j] += __bfloat162float(rb[gc + j]);
+                }
+                int nout = 32;
+                if (g) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float x = f[j], y = f[j + 16];
+                    f[j] = (p.glu == VB_GLU_SWIGLU) ? silu(x) * y : x * gelu_erf(y);
+                  }
+                  nout = 16;
+                } else if (p.act != VB_ACT_NONE) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+                }
+                const int oc = ocol0 + bx * bw + a * outs_per_acc;  // first output column of these values
+                if (p.residual != nullptr && orow >= 0) {
+                  const bf16* rp = p.residual + orow * p.ldr + oc;
+                  if (oc + nout <= n_out_total && (p.ldr & 7) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                      if (j < nout) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
+                        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                          const float2 r2 = unpack_bf16(uu[q]);
+                          f[j + 2 * q] = r2.x + p.alpha * f[j + 2 * q];
+                          f[j + 2 * q + 1] = r2.y + p.alpha * f[j + 2 * q + 1];
+                        }
+                      }
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                      if (j < nout && oc + j < n_out_total) f[j] = __bfloat162float(rp[j]) + p.alpha * f[j];
+                  }
+                } else if (p.alpha != 1.0f) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+                }
+                // 16-byte pieces into the swizzled staging row of this thread
+                uint8_t* rowp = cb + r * row_bytes;
+                const int piece0 = (a * outs_per_acc) >> 3;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  if (j < nout) {
+                    const int piece = (piece0 + (j >> 3)) ^ ((r >> swz_shift) & swz_mask);
+                    *reinterpret_cast<uint4*>(rowp + piece * 16) =
+                        make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                   pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+                  }
+                }
+              }
+              fence_proxy_async_smem();
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (et == 0) {
+                const int cc = ocol0 + bx * bw;
+                if (cc < n_out_total) {
+                  if (p.a_mode == 0) {
+                    tma_store_2d(&tmap_c, cb, cc, t.m_blk * BLOCK_M);
+                  } else {
+                    const int tiw = t.m_blk % p.tiles_w, rest = t.m_blk / p.tiles_w;
+                    tma_store_4d(&tmap_c, cb, cc, tiw * p.tw, (rest % p.tiles_h) * p.th, (rest / p.tiles_h) * p.tn);
+                  }
+                }
+                bulk_commit();
+              }
+            }
+          }
+        }
+        if (BLOCK_N < 32 || p.c_box == 0) {
         // -------- fused epilogue straight to the output tensor
         const bf16* rb = nullptr;
         if (p.rowbias != nullptr && orow >= 0)
@@ -465,6 +583,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       }
+        }
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -504,6 +623,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   }
 
+  if (threadIdx.x == 64 && p.c_box > 0) bulk_wait<0>();  // staged tiles must be read out before smem goes away
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -548,20 +668,19 @@ static PFN_encodeTiled get_encode_fn() {
 
 static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
-                     const uint32_t* estr) {
+                     const uint32_t* estr, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return VB_ERR_DRIVER;
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims,
-                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? VB_OK : VB_ERR_DRIVER;
 }
 
 template <int BN, int STAGES>
-static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                       cudaStream_t stream) {
-  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + (BN >= 32 ? 2 * BLOCK_M * 128 : 0) + 1024 + 256;
   static_assert(smem <= SMEM_LIMIT, "smem budget");
   static bool attr_set = false;
   auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES>;
@@ -572,34 +691,36 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   }
   int units = p.m_blocks * p.n_blocks * p.splits;
   int grid = units < vb_num_sms() ? units : vb_num_sms();
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, tc, p);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
 
-static int launch_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                       cudaStream_t stream) {
+static int launch_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                       const GemmParams& p, cudaStream_t stream) {
   switch (bn) {
-    case 256: return launch_cfg<256, 4>(ta, tb, p, stream);
-    case 128: return launch_cfg<128, 6>(ta, tb, p, stream);
-    case 64: return launch_cfg<64, 8>(ta, tb, p, stream);
-    case 32: return launch_cfg<32, 10>(ta, tb, p, stream);
-    case 16: return launch_cfg<16, 10>(ta, tb, p, stream);
+    case 256: return launch_cfg<256, 4>(ta, tb, tc, p, stream);
+    case 160: return launch_cfg<160, 5>(ta, tb, tc, p, stream);
+    case 128: return launch_cfg<128, 6>(ta, tb, tc, p, stream);
+    case 64: return launch_cfg<64, 7>(ta, tb, tc, p, stream);
+    case 32: return launch_cfg<32, 8>(ta, tb, tc, p, stream);
+    case 16: return launch_cfg<16, 10>(ta, tb, tc, p, stream);
     default: return VB_ERR_ARG;
   }
 }
 
 static int pick_block_n(long long M, long long N, int glu) {
-  // widest tile wins unless it leaves most SMs idle: score = tile efficiency x wave utilisation
+  // widest tile wins unless it leaves SMs idle or pads many columns:
+  // score = tile efficiency x wave utilisation x column fill. 160 divides the UNet widths 320/640/1280.
   (void)glu;
   const int sms = vb_num_sms();
   const long long mb = (M + BLOCK_M - 1) / BLOCK_M;
-  const int cands[4] = {256, 128, 64, 32};
+  const int cands[5] = {256, 160, 128, 64, 32};
   // relative per-tile efficiency measured on B200 (narrow tiles are L2->SMEM bandwidth bound)
-  const float eff[4] = {1.0f, 0.66f, 0.40f, 0.22f};
+  const float eff[5] = {1.0f, 0.80f, 0.66f, 0.40f, 0.22f};
   int best = 32;
   float best_score = -1.f;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
     const long long nbk = (N + bn - 1) / bn;
     const long long tiles = mb * nbk;
@@ -635,19 +756,13 @@ static int swap_splits(long long M, long long N, long long K) {
   return best;
 }
 
-static int run_reduce(const GemmParams& p, int rows, int ncols, void* out, long long ldo,
-                      const vb_epilogue* e, cudaStream_t stream) {
-  int n_out = e->glu != VB_GLU_NONE ? ncols / 2 : ncols;
-  long long work = static_cast<long long>(rows) * ((n_out + 7) / 8);
-  int threads = 256;
-  long long blocks = (work + threads - 1) / threads;
-  splitk_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-      p.ws, p.splits, p.ws_split_stride, p.ws_ld, rows, ncols, out, ldo,
-      reinterpret_cast<const bf16*>(e->bias), reinterpret_cast<const bf16*>(e->rowbias),
-      e->rowbias_rows > 0 ? e->rowbias_rows : 1, reinterpret_cast<const bf16*>(e->residual),
-      e->ldr, e->alpha, e->act, e->glu, e->out_fp32);
-  VB_LAUNCH_CHECK();
-  return VB_OK;
+// output box width of the TMA-store epilogue: 64 (128B swizzle) or 32 (64B swizzle) columns, 0 = direct stores
+static int c_box_for(int bn, int glu, int out_fp32, long long ldo, const void* out) {
+  if (out_fp32 || bn < 32 || (ldo & 7) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return 0;
+  const int out_w = glu != VB_GLU_NONE ? bn / 2 : bn;
+  if (out_w % 64 == 0) return 64;
+  if (out_w % 32 == 0) return 32;
+  return 0;
 }
 
 static int validate_epi(const vb_epilogue* e, long long N) {
@@ -732,7 +847,7 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
     uint64_t sB[1] = {static_cast<uint64_t>(lda) * 2};
     uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
     if (int r = make_tmap(&tb, A, 2, dB, sB, bB, estr2)) return r;
-    return launch_gemm(bn, ta, tb, p, stream);  // the last CTA of every tile finalises it
+    return launch_gemm(bn, ta, tb, ta, p, stream);  // the last CTA of every tile finalises it (no TMA store)
   }
 
   int bn = pick_block_n(M, N, epi->glu);
@@ -749,7 +864,18 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   uint64_t sB[1] = {static_cast<uint64_t>(ldw) * 2};
   uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
   if (int r = make_tmap(&tb, W, 2, dB, sB, bB, estr2)) return r;
-  return launch_gemm(bn, ta, tb, p, stream);
+  CUtensorMap tc = ta;
+  p.c_box = c_box_for(bn, epi->glu, epi->out_fp32, ldo, out);
+  if (p.c_box > 0) {
+    const long long n_out = epi->glu != VB_GLU_NONE ? N / 2 : N;
+    uint64_t dC[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
+    uint64_t sC[1] = {static_cast<uint64_t>(ldo) * 2};
+    uint32_t bC[2] = {static_cast<uint32_t>(p.c_box), BLOCK_M};
+    if (int r = make_tmap(&tc, out, 2, dC, sC, bC, estr2,
+                          p.c_box == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
+      return r;
+  }
+  return launch_gemm(bn, ta, tb, tc, p, stream);
 }
 
 extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int64_t nb,
@@ -826,5 +952,19 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
   uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
   const uint32_t estr2[2] = {1, 1};
   if (int r = make_tmap(&tb, Wt, 2, dB, sB, bB, estr2)) return r;
-  return launch_gemm(bn, ta, tb, p, stream);
+  CUtensorMap tc = tb;
+  p.c_box = c_box_for(bn, epi->glu, epi->out_fp32, p.ldo, out);
+  if (p.c_box > 0) {
+    uint64_t dC[4] = {static_cast<uint64_t>(p.ldo), static_cast<uint64_t>(wo), static_cast<uint64_t>(ho),
+                      static_cast<uint64_t>(nb)};
+    uint64_t sC[3] = {static_cast<uint64_t>(p.ldo) * 2, static_cast<uint64_t>(p.ldo) * wo * 2,
+                      static_cast<uint64_t>(p.ldo) * wo * ho * 2};
+    uint32_t bC[4] = {static_cast<uint32_t>(p.c_box), static_cast<uint32_t>(tw), static_cast<uint32_t>(th),
+                      static_cast<uint32_t>(tn)};
+    const uint32_t e4[4] = {1, 1, 1, 1};
+    if (int r = make_tmap(&tc, out, 4, dC, sC, bC, e4,
+                          p.c_box == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
+      return r;
+  }
+  return launch_gemm(bn, ta, tb, tc, p, stream);
 }

@@ -115,6 +115,68 @@ __global__ void row_rstd_kernel(const bf16* __restrict__ x, long long ldx, float
   if (lane == 0) out[row] = rsqrtf(s / d + eps);
 }
 
+// d <= 1024: one WARP per row (8 rows per CTA); each lane keeps up to 4 x 8 elements in registers.
+template <bool LAYER>
+__global__ void __launch_bounds__(256)
+rownorm_warp_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                    bf16* __restrict__ out, long long ldo, long long rows, int d, float eps) {
+  const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const bf16* xr = x + row * ldx;
+  float v[4][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float2 f = unpack_bf16(uu[j]); v[i][2 * j] = f.x; v[i][2 * j + 1] = f.y; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += LAYER ? v[i][j] : v[i][j] * v[i][j];
+    }
+  }
+  s = warp_sum(s);
+  float mean = 0.f, rstd;
+  if (LAYER) {
+    mean = s / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < d) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float t = v[i][j] - mean; q += t * t; }
+      }
+    }
+    rstd = rsqrtf(warp_sum(q) / d + eps);
+  } else {
+    rstd = rsqrtf(s / d + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < d) {
+      const uint4 uw = *reinterpret_cast<const uint4*>(w + c);
+      const uint32_t ww[4] = {uw.x, uw.y, uw.z, uw.w};
+      uint32_t bb[4] = {0, 0, 0, 0};
+      if (LAYER && b != nullptr) {
+        const uint4 ub = *reinterpret_cast<const uint4*>(b + c);
+        bb[0] = ub.x; bb[1] = ub.y; bb[2] = ub.z; bb[3] = ub.w;
+      }
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 wf = unpack_bf16(ww[j]), bf = unpack_bf16(bb[j]);
+        o[j] = pack_bf16((v[i][2 * j] - mean) * rstd * wf.x + bf.x, (v[i][2 * j + 1] - mean) * rstd * wf.y + bf.y);
+      }
+      *reinterpret_cast<uint4*>(out + row * ldo + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 template <bool LAYER>
 static int launch_rownorm(const void* x, long long ldx, const void* w, const void* b, void* out,
                           long long ldo, long long rows, long long d, float eps, cudaStream_t st) {
@@ -125,7 +187,9 @@ static int launch_rownorm(const void* x, long long ldx, const void* w, const voi
   const bf16* bp = reinterpret_cast<const bf16*>(b);
   bf16* op = reinterpret_cast<bf16*>(out);
   unsigned grid = static_cast<unsigned>(rows);
-  if (d <= 128 * 8) rownorm_kernel<128, 1, LAYER><<<grid, 128, 0, st>>>(xp, ldx, wp, bp, op, ldo, (int)d, eps);
+  if (d <= 1024 && rows >= 64)
+    rownorm_warp_kernel<LAYER><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(xp, ldx, wp, bp, op, ldo, rows, (int)d, eps);
+  else if (d <= 128 * 8) rownorm_kernel<128, 1, LAYER><<<grid, 128, 0, st>>>(xp, ldx, wp, bp, op, ldo, (int)d, eps);
   else if (d <= 256 * 8 * 1) rownorm_kernel<256, 1, LAYER><<<grid, 256, 0, st>>>(xp, ldx, wp, bp, op, ldo, (int)d, eps);
   else if (d <= 256 * 8 * 2) rownorm_kernel<256, 2, LAYER><<<grid, 256, 0, st>>>(xp, ldx, wp, bp, op, ldo, (int)d, eps);
   else if (d <= 256 * 8 * 4) rownorm_kernel<256, 4, LAYER><<<grid, 256, 0, st>>>(xp, ldx, wp, bp, op, ldo, (int)d, eps);
@@ -187,39 +251,46 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ 
     atomicAdd(&stats[static_cast<long long>(n) * groups * 2 + i], sacc[i]);
 }
 
-__global__ void gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
-                                const bf16* __restrict__ w, const bf16* __restrict__ b,
-                                bf16* __restrict__ out, long long spatial, int c, int groups, float eps,
-                                int act, long long total_vec) {
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= total_vec) return;
-  const int vec_per_row = c / 8;
-  const int cv = static_cast<int>(i % vec_per_row) * 8;
-  const long long n = i / (vec_per_row * spatial);
+// y = x * scale[n][c] + shift[n][c] (+ activation): the per-channel affine of this image is computed once
+// per CTA into smem, then a slab of rows is streamed with 16-byte loads / stores.
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats, const bf16* __restrict__ w,
+                const bf16* __restrict__ b, bf16* __restrict__ out, long long spatial, int c, int groups, float eps,
+                int act, int rows_per_cta) {
+  extern __shared__ float ss[];  // [c] scale, [c] shift
+  const int n = blockIdx.y;
   const int cpg = c / groups;
   const float cnt = static_cast<float>(cpg) * static_cast<float>(spatial);
-  uint4 u = *reinterpret_cast<const uint4*>(x + i * 8);
-  const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-  uint32_t oo[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float2 f = unpack_bf16(uu[j]);
-    float r[2] = {f.x, f.y};
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int ch = cv + 2 * j + e;
-      const int g = ch / cpg;
-      const float sum = stats[(n * groups + g) * 2], sq = stats[(n * groups + g) * 2 + 1];
-      const float mean = sum / cnt;
-      const float var = fmaxf(sq / cnt - mean * mean, 0.f);
-      float y = (r[e] - mean) * rsqrtf(var + eps) * __bfloat162float(w[ch]) + __bfloat162float(b[ch]);
-      if (act == VB_ACT_SILU) y = silu(y);
-      else if (act == VB_ACT_RELU) y = fmaxf(y, 0.f);
-      r[e] = y;
-    }
-    oo[j] = pack_bf16(r[0], r[1]);
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const int g = ch / cpg;
+    const float sum = stats[(static_cast<long long>(n) * groups + g) * 2], sq = stats[(static_cast<long long>(n) * groups + g) * 2 + 1];
+    const float mean = sum / cnt;
+    const float rstd = rsqrtf(fmaxf(sq / cnt - mean * mean, 0.f) + eps);
+    const float sc = rstd * __bfloat162float(w[ch]);
+    ss[ch] = sc;
+    ss[c + ch] = __bfloat162float(b[ch]) - mean * sc;
   }
-  *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+  __syncthreads();
+  const int vec_per_row = c / 8;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long nvec = min(static_cast<long long>(rows_per_cta), spatial - r0) * vec_per_row;
+  const long long base = (static_cast<long long>(n) * spatial + r0) * c;
+  for (long long i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const int cv = static_cast<int>(i % vec_per_row) * 8;
+    const uint4 u = *reinterpret_cast<const uint4*>(x + base + i * 8);
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    uint32_t oo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16(uu[j]);
+      float y0 = f.x * ss[cv + 2 * j] + ss[c + cv + 2 * j];
+      float y1 = f.y * ss[cv + 2 * j + 1] + ss[c + cv + 2 * j + 1];
+      if (act == VB_ACT_SILU) { y0 = silu(y0); y1 = silu(y1); }
+      else if (act == VB_ACT_RELU) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+      oo[j] = pack_bf16(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(out + base + i * 8) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+  }
 }
 
 }  // namespace vb
@@ -278,13 +349,16 @@ extern "C" int vb200_groupnorm_nhwc(const void* x, const void* weight, const voi
       reinterpret_cast<const bf16*>(x), reinterpret_cast<float*>(workspace), spatial,
       static_cast<int>(c), static_cast<int>(groups), static_cast<int>(rows_per_cta));
   VB_LAUNCH_CHECK();
-  long long total_vec = n * spatial * (c / 8);
-  long long blocks = (total_vec + 255) / 256;
-  gn_apply_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+  // apply: ~8 CTAs per SM, each with its own smem copy of the per-channel affine
+  long long want2 = (8LL * vb_num_sms() + n - 1) / n;
+  long long rpc = (spatial + want2 - 1) / want2;
+  if (rpc < 4) rpc = 4;
+  dim3 grid2(static_cast<unsigned>((spatial + rpc - 1) / rpc), static_cast<unsigned>(n));
+  gn_apply_kernel<<<grid2, 256, 2 * c * sizeof(float), stream>>>(
       reinterpret_cast<const bf16*>(x), reinterpret_cast<const float*>(workspace),
       reinterpret_cast<const bf16*>(weight), reinterpret_cast<const bf16*>(bias),
       reinterpret_cast<bf16*>(out), spatial, static_cast<int>(c), static_cast<int>(groups), eps, act,
-      total_vec);
+      static_cast<int>(rpc));
   VB_LAUNCH_CHECK();
   return VB_OK;
 }

@@ -173,8 +173,7 @@ class UNetSD_I2VGen:
         for name in ("time_embed", "fps_embedding", "context_embedding"):
             w[name] = (lin(name + ".0"), lin(name + ".2"))
         w["out_gn"] = lin("out.0")
-        ow = g("out.2.weight")
-        w["out_conv"] = (ow.permute(0, 2, 3, 1).reshape(ow.shape[0], 9, ow.shape[1]).contiguous(), g("out.2.bias"))
+        w["out_conv"] = (ops.pack_conv_weight(g("out.2.weight")), g("out.2.bias"))
         # tiny local-image adapter: fp32 torch weights (see module docstring)
         w["adapter"] = {k: g32(k) for k in sd if k.startswith(("local_image_concat.", "local_temporal_encoder.",
                                                                "local_image_embedding."))}
@@ -360,7 +359,7 @@ class UNetSD_I2VGen:
             cur = torch.cat([cur, xs.pop()], dim=-1)
             cur = self._run(blk, cur, emb_all, context, batch, f)
         a = ops.groupnorm_nhwc(cur, *self.w["out_gn"], 32, 1e-5, act=ops.ACT_SILU)
-        out = ops.conv_nhwc_direct(a, self.w["out_conv"][0], self.w["out_conv"][1], 3, 3)
+        out = ops.conv_nhwc(a, self.w["out_conv"][0], 3, 3, bias=self.w["out_conv"][1])
         return out.view(batch, f, h, w, self.out_dim).permute(0, 4, 1, 2, 3).float()
 
     __call__ = forward
