@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(256, 2) gemv_bf16_kernel(const GemvParams p) {
 
   Buf buf0, buf1;
   pdl_trigger();
-  load_group(buf0, blockIdx.x, 0);  // weights never depend on the previous kernel: request them before the wait
+  // weights never depend on the previous kernel: two groups are requested before the dependency wait, and
+  // the pipeline stays two groups ahead of the MMAs from then on
+  load_group(buf0, blockIdx.x, 0);
+  load_group(buf1, blockIdx.x, 1);
   pdl_wait();
 
   const bool glu = p.glu != VB_GLU_NONE;
@@ -157,11 +160,11 @@ __global__ void __launch_bounds__(256, 2) gemv_bf16_kernel(const GemvParams p) {
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     for (int pr = 0; pr < npairs; ++pr) {
-      load_group(buf1, tile, 2 * pr + 1);                 // past the slice: loads nothing (zero operands)
+      const bool last = pr + 1 == npairs;                 // then prefetch the first two groups of the NEXT tile
       compute_group(buf0, 2 * pr, first);
-      if (pr + 1 < npairs) load_group(buf0, tile, 2 * pr + 2);
-      else load_group(buf0, tile + gridDim.x, 0);         // first group of the NEXT tile
-      compute_group(buf1, 2 * pr + 1, first);
+      if (!last) load_group(buf0, tile, 2 * pr + 2); else load_group(buf0, tile + gridDim.x, 0);
+      compute_group(buf1, 2 * pr + 1, first);             // groups past the slice carry zero operands
+      if (!last) load_group(buf1, tile, 2 * pr + 3); else load_group(buf1, tile + gridDim.x, 1);
     }
     // ---- cross-warp (k-slice) reduction: red[par][warp][feature 0..15][token]
 #pragma unroll

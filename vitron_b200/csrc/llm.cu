@@ -116,19 +116,29 @@ template <bool ROPE>
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict__ k_pages,
                    bf16* __restrict__ v_pages, const int32_t* __restrict__ block_table, int max_pages,
-                   const int32_t* __restrict__ kv_len, int H, int page_size, float scale, int splits,
+                   const int32_t* __restrict__ kv_len, int H, int page_size, float scale, int splits, int per,
                    float* __restrict__ ws_ml, float* __restrict__ ws_o, int* __restrict__ counters,
                    bf16* __restrict__ out, long long ld_o, const float* __restrict__ rope_table) {
+  // page_size == 64 and per % 64 == 0 (host-checked): a 64-key trip is exactly one page, and the page ids of
+  // this split depend only on (split, per), so they are fetched before anything else (the block table is
+  // constant during decoding -> safe ahead of the PDL dependency wait).
   constexpr int HD = 128;
+  constexpr int MAX_TRIPS = DEC_CHUNK / 64;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 3, sub = lane & 7;
+  const int32_t* bt = block_table + static_cast<long long>(b) * max_pages;
+  const int c0 = split * per;
+  int pg[MAX_TRIPS];
+#pragma unroll
+  for (int i = 0; i < MAX_TRIPS; ++i) {
+    const int pi = c0 / 64 + i;
+    pg[i] = (pi < max_pages && i * 64 < per) ? bt[pi] : 0;
+  }
   pdl_trigger();
   pdl_wait();
   const int len = kv_len[b];
-  const int per = (len + splits - 1) / splits;
-  const int c0 = split * per, c1 = min(len, c0 + per);
-  const int32_t* bt = block_table + static_cast<long long>(b) * max_pages;
+  const int c1 = min(len, c0 + per);
 
   float qv[16];
   {
@@ -177,18 +187,21 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
   const long long head_off = static_cast<long long>(h) * page_size * HD + sub * 16;
   const long long page_stride = static_cast<long long>(H) * page_size * HD;
 
-  // 16 lane groups per CTA; a trip covers 64 consecutive keys: lane group gid takes keys tb + gid + 16 u,
-  // u < 4, and issues all 16 K/V loads (256 B per lane) before the first dot product.
+  // 16 lane groups per CTA; trip i covers page pg[i] = keys c0 + 64 i .. + 63: lane group gid takes the keys
+  // gid + 16 u (u < 4) of the page and issues all 16 K/V loads (256 B per lane) before the first dot product.
   const int gid = warp * 4 + grp;
-  for (int tb = c0; tb < c1; tb += 64) {  // warp-uniform trip count (shuffles below use the full mask)
+#pragma unroll
+  for (int i = 0; i < MAX_TRIPS; ++i) {
+    const int tb = c0 + 64 * i;
+    if (tb >= c1) break;  // warp-uniform (shuffles below use the full mask)
+    const long long pbase = static_cast<long long>(pg[i]) * page_stride + head_off;
     uint4 kq[4][2], vq[4][2];
     bool has[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int tk = tb + gid + 16 * u;
-      has[u] = tk < c1;
-      const int tu = has[u] ? tk : c0;
-      const long long off = static_cast<long long>(bt[tu / page_size]) * page_stride + static_cast<long long>(tu % page_size) * HD + head_off;
+      const int kk = gid + 16 * u;  // key inside the page
+      has[u] = tb + kk < c1;
+      const long long off = pbase + static_cast<long long>(has[u] ? kk : 0) * HD;
       kq[u][0] = *reinterpret_cast<const uint4*>(k_pages + off);
       kq[u][1] = *reinterpret_cast<const uint4*>(k_pages + off + 8);
       vq[u][0] = *reinterpret_cast<const uint4*>(v_pages + off);
@@ -450,7 +463,11 @@ static int launch_attn_decode(const void* q, int64_t ld_q, void* k_pages, void* 
   VB_CHECK_ARG(B > 0 && n_heads > 0 && page_size > 0 && max_pages > 0);
   if (head_dim != 128) return VB_ERR_UNSUPPORTED;
   VB_CHECK_ARG(ld_q % 8 == 0);
+  if (page_size != 64) return VB_ERR_UNSUPPORTED;  // one 64-key trip == one page
   const int splits = decode_splits(max_kv_len);
+  int per = static_cast<int>((max_kv_len + splits - 1) / splits);
+  per = (per + 63) / 64 * 64;
+  if (per > DEC_CHUNK) return VB_ERR_ARG;
   float* ws_ml = nullptr;
   float* ws_o = nullptr;
   int* counters = nullptr;
@@ -467,13 +484,13 @@ static int launch_attn_decode(const void* q, int64_t ld_q, void* k_pages, void* 
     e = vb_launch(attn_decode_kernel<true>, grid, dim3(DEC_THREADS), 0, stream,
                   reinterpret_cast<const bf16*>(q), static_cast<long long>(ld_q), reinterpret_cast<bf16*>(k_pages),
                   reinterpret_cast<bf16*>(v_pages), block_table, static_cast<int>(max_pages), kv_len,
-                  static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, ws_ml, ws_o, counters,
+                  static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, per, ws_ml, ws_o, counters,
                   reinterpret_cast<bf16*>(out), static_cast<long long>(ld_o), rope_table);
   else
     e = vb_launch(attn_decode_kernel<false>, grid, dim3(DEC_THREADS), 0, stream,
                   reinterpret_cast<const bf16*>(q), static_cast<long long>(ld_q), reinterpret_cast<bf16*>(k_pages),
                   reinterpret_cast<bf16*>(v_pages), block_table, static_cast<int>(max_pages), kv_len,
-                  static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, ws_ml, ws_o, counters,
+                  static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, per, ws_ml, ws_o, counters,
                   reinterpret_cast<bf16*>(out), static_cast<long long>(ld_o), static_cast<const float*>(nullptr));
   if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
   return VB_OK;
