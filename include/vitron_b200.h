@@ -62,6 +62,16 @@ int vb200_device_ok(void);          /* 1 iff the current device is sm_100 (B200)
  * arg-max): when on, each of them is launched with programmaticStreamSerialization and overlaps its
  * prologue / weight prefetch with the tail of its predecessor. Returns the previous setting. */
 int vb200_set_pdl(int enable);
+/* Attention kernel selection for vb200_attention: 0 = automatic (tcgen05/TMEM kernel for unmasked head_dim
+ * 64/128 with >= 96 query rows, mma.sync otherwise), 1 = mma.sync only, 2 = tcgen05 whenever supported.
+ * Both kernels compute the same function; the switch exists so the parity tests can pin each of them. */
+int vb200_set_attention_impl(int impl);
+/* Diagnostics for the tcgen05 attention kernel: every mbarrier wait in it is bounded (~0.5 s); if one expires
+ * the CTA drains instead of hanging the GPU and records where. out3 = {site id (0 = never fired), packed block
+ * index, thread}; reading clears the record. Synchronises the device. */
+int vb200_attention_watchdog(uint32_t* out3);
+/* Resident CTAs per SM (registers / shared memory) of the tcgen05 attention kernel for head_dim 64 or 128. */
+int vb200_attention_tc_occupancy(int head_dim);
 
 /* ---- GEMM: out[M,N] = epi(A[M,K] @ W[N,K]^T), tcgen05 + TMA (gemm_tcgen05.cu) --------------
  * Replaces every nn.Linear on the path: HF LlamaAttention/LlamaMLP/lm_head (transformers 4.31,

@@ -195,6 +195,62 @@ def test_attention(cuda, B, H, Sq, Skv, D, causal):
     close(out, sdpa_ref(q, k, v, 1 / math.sqrt(D), causal), 2e-2, 2e-2, "attention")
 
 
+ATT_TC = [
+    # B, H, Sq, Skv, D, causal — shapes of the prefill (hd 128, causal), ViT (257, hd 64), UNet spatial (hd 64)
+    (2, 4, 768, 768, 128, True), (8, 16, 257, 257, 64, False), (2, 5, 2560, 2560, 64, False),
+    (2, 5, 640, 145, 64, False), (1, 8, 101, 1024, 64, False), (3, 2, 70, 200, 128, True),
+    (1, 2, 1, 130, 128, True), (1, 3, 130, 1, 64, False), (2, 2, 129, 63, 128, False), (1, 32, 1728, 1728, 128, True),
+]
+
+
+@pytest.mark.parametrize("B,H,Sq,Skv,D,causal", ATT_TC)
+@pytest.mark.parametrize("amp", [1.0, 6.0])
+def test_attention_tcgen05(cuda, B, H, Sq, Skv, D, causal, amp):
+    """tcgen05/TMEM kernel pinned (impl 2) against the fp32 reference and against the mma.sync kernel; amp 6
+    makes row maxima jump by far more than 2^8 between key blocks so the lazy O rescale path runs."""
+    from vitron_b200 import ops
+    q, k, v = rnd((B, Sq, H, D), cuda, 1) * amp, rnd((B, Skv, H, D), cuda, 2) * amp, rnd((B, Skv, H, D), cuda, 3)
+    ref = sdpa_ref(q, k, v, 1 / math.sqrt(D), causal)
+    try:
+        ops.set_attention_impl(2)
+        out = ops.attention(q, k, v, causal=causal)
+        ops.set_attention_impl(1)
+        out_mma = ops.attention(q, k, v, causal=causal)
+    finally:
+        ops.set_attention_impl(0)
+    close(out, ref, 2e-2, 2e-2, "tcgen05 attention")
+    close(out, out_mma, 2e-2, 2e-2, "tcgen05 vs mma.sync")
+
+
+def test_attention_tcgen05_layouts(cuda):
+    from vitron_b200 import ops
+    B, S, H, D = 3, 300, 4, 128
+    qkv = rnd((B, S, 3 * H * D), cuda, 1)
+    q, k, v = (qkv[..., i * H * D:(i + 1) * H * D].view(B, S, H, D) for i in range(3))
+    lens = torch.tensor([300, 17, 129], dtype=torch.int32, device=cuda)
+    try:
+        ops.set_attention_impl(2)
+        out = ops.attention(q, k, v, causal=False, kv_len=lens)
+        close(out, sdpa_ref(q, k, v, 1 / math.sqrt(D), False, lens), 2e-2, 2e-2, "kv_len")
+        out = ops.attention(q, k, v, causal=True, kv_len=lens)
+        ref = sdpa_ref(q, k, v, 1 / math.sqrt(D), True, lens)
+        for b, l in enumerate(lens.tolist()):
+            close(out[b, :l], ref[b, :l], 2e-2, 2e-2, "causal + kv_len")
+        # output written through a strided view ([B, S, H*D] slice of a wider buffer)
+        wide = torch.zeros((B, S, 2 * H * D), dtype=torch.bfloat16, device=cuda)
+        o = wide[..., H * D:].view(B, S, H, D)
+        ops.attention(q, k, v, out=o)
+        close(o, sdpa_ref(q, k, v, 1 / math.sqrt(D)), 2e-2, 2e-2, "strided out")
+        assert float(wide[..., :H * D].abs().max()) == 0.0
+        # head-major [B, H, S, D] storage viewed as [B, S, H, D]
+        qh = rnd((B, H, S, D), cuda, 7).permute(0, 2, 1, 3)
+        kh = rnd((B, H, S, D), cuda, 8).permute(0, 2, 1, 3)
+        vh = rnd((B, H, S, D), cuda, 9).permute(0, 2, 1, 3)
+        close(ops.attention(qh, kh, vh), sdpa_ref(qh, kh, vh, 1 / math.sqrt(D)), 2e-2, 2e-2, "head-major")
+    finally:
+        ops.set_attention_impl(0)
+
+
 def test_attention_fused_qkv_layout_kvlen_mask(cuda):
     from vitron_b200 import ops
     B, S, H, D = 3, 300, 4, 128

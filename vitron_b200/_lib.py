@@ -32,6 +32,9 @@ SIGNATURES = {
     "vb200_last_error": (C.c_char_p, []),
     "vb200_device_ok": (_i32, []),
     "vb200_set_pdl": (_i32, [_i32]),
+    "vb200_set_attention_impl": (_i32, [_i32]),
+    "vb200_attention_watchdog": (_i32, [_p]),
+    "vb200_attention_tc_occupancy": (_i32, [_i32]),
     "vb200_gemm_bf16_workspace_size": (_sz, [_i64, _i64, _i64]),
     "vb200_gemm_bf16": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, C.POINTER(Epilogue), _p, _sz, _p]),
     "vb200_conv_nhwc_bf16": (_i32, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,

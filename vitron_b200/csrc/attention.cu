@@ -340,6 +340,18 @@ __global__ void __launch_bounds__(WARPS * 32) attn_short_kernel(const ShortParam
 
 using namespace vb;
 
+int vb_attention_tc(const void* q, const void* k, const void* v, void* out, int64_t B, int64_t H, int64_t Sq,
+                    int64_t Skv, int64_t head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb,
+                    int64_t k_ss, int64_t k_sh, int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss,
+                    int64_t o_sh, float scale, int causal, const int32_t* kv_len, cudaStream_t stream);
+
+static int g_attention_impl = 0;  // 0 auto, 1 mma.sync only, 2 tcgen05 whenever the shape is supported
+extern "C" int vb200_set_attention_impl(int impl) {
+  VB_CHECK_ARG(impl >= 0 && impl <= 2);
+  g_attention_impl = impl;
+  return VB_OK;
+}
+
 extern "C" int vb200_attention(const void* q, const void* k, const void* v, void* out, int64_t B,
                                int64_t H, int64_t Sq, int64_t Skv, int64_t head_dim, int64_t q_sb,
                                int64_t q_ss, int64_t q_sh, int64_t k_sb, int64_t k_ss, int64_t k_sh,
@@ -352,6 +364,14 @@ extern "C" int vb200_attention(const void* q, const void* k, const void* v, void
   VB_CHECK_ARG(H <= 65535 && B <= 65535);
   const int64_t strides[12] = {q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh};
   for (int i = 0; i < 12; ++i) VB_CHECK_ARG(strides[i] % 8 == 0);
+  // tcgen05 / TMEM kernel (attention_tc.cu) for unmasked head_dim 64 / 128 with enough query rows to fill
+  // its 128-row tiles; everything else (boolean masks, head_dim 40/80/160, short queries) stays on mma.sync.
+  if (!mask && g_attention_impl != 1 && (head_dim == 64 || head_dim == 128) && Skv >= 1 &&
+      (Sq >= 96 || g_attention_impl == 2)) {
+    int r = vb_attention_tc(q, k, v, out, B, H, Sq, Skv, head_dim, q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss,
+                            v_sh, o_sb, o_ss, o_sh, scale, causal, kv_len, stream);
+    if (r != VB_ERR_UNSUPPORTED) return r;
+  }
   AttnParams p;
   p.q = reinterpret_cast<const bf16*>(q); p.k = reinterpret_cast<const bf16*>(k);
   p.v = reinterpret_cast<const bf16*>(v); p.o = reinterpret_cast<bf16*>(out);

@@ -251,6 +251,21 @@ def attention(q, k, v, scale=None, causal=False, kv_len=None, mask=None, out=Non
     return out
 
 
+def set_attention_impl(impl):
+    """0 = automatic, 1 = mma.sync kernel only, 2 = tcgen05 kernel whenever the shape is supported."""
+    check(_lib.load().vb200_set_attention_impl(int(impl)), "vb200_set_attention_impl")
+
+
+def attention_watchdog():
+    """(site, block, thread) of the first expired wait in the tcgen05 attention kernel since the last call;
+    site 0 = none. Synchronises."""
+    import ctypes
+    buf = (ctypes.c_uint32 * 3)()
+    torch.cuda.synchronize()
+    check(_lib.load().vb200_attention_watchdog(ctypes.addressof(buf)), "vb200_attention_watchdog")
+    return tuple(buf)
+
+
 def attention_short(q, k, v, scale=None, out=None):
     """q/k/v [nseq, S, H, 64] or [outer, inner, S, H, 64] strided views (sequence = leading dims),
     S <= 32. out defaults to a fresh tensor of q's shape."""
