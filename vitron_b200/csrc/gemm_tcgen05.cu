@@ -24,8 +24,13 @@ namespace vb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quadrant
+constexpr int EPI_THREADS = 32 * NUM_EPI_WARPS;
 constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
+
+__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+}
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct GemmParams {
@@ -208,6 +213,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
   volatile int* fin_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // BLOCK_N floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -313,10 +319,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else {
     // ===================================================== epilogue warps
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int ehalf = (warp - 2) >> 2;  // two warps per quadrant: they split the accumulator columns
+    const int et = threadIdx.x - 64;    // 0 .. EPI_THREADS-1
     int acc = 0;
     uint32_t acc_phase = 0;
-    int cbuf = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       TileCoord t = decode_work(p, unit);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -348,7 +355,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // -------- raw fp32 partials to the workspace (split-K and/or swap-AB)
         float* wsp = p.ws + static_cast<long long>(t.split) * p.ws_split_stride;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 16) {
+        for (int c = ehalf * 16; c < BLOCK_N; c += 32) {
           uint32_t v[16];
           tmem_ld_32x16(taddr + c, v);
           tmem_ld_wait();
@@ -380,76 +387,115 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if constexpr (BLOCK_N >= 32) {
           if (p.c_box > 0) {
             // -------- fused epilogue -> 128B/64B-swizzled smem tile -> TMA store (coalesced, clipped by the
-            // tensor map at the ragged edges; conv: one 4-D box per pixel tile, mirroring the A load)
+            // tensor map at the ragged edges; conv: one 4-D box per pixel tile, mirroring the A load).
+            // The two warps of a TMEM lane quadrant take alternate 32-column accumulator chunks; each keeps
+            // the tcgen05.ld and the residual loads of its next chunk in flight while it works on the current one.
             const bool g = p.glu != VB_GLU_NONE;
             const int bw = p.c_box;                       // output columns per box
             const int outs_per_acc = g ? 16 : 32;         // outputs produced by one 32-column accumulator chunk
             const int acc_per_box = bw / outs_per_acc;
             const int nboxes = (g ? BLOCK_N / 2 : BLOCK_N) / bw;
+            constexpr int NCHUNKS = BLOCK_N / 32;
             const int row_bytes = bw * 2;
             const int swz_shift = bw == 64 ? 0 : 1, swz_mask = bw == 64 ? 7 : 3;
-            const int et = threadIdx.x - 64;
             const bf16* rb = nullptr;
             if (p.rowbias != nullptr && orow >= 0) rb = p.rowbias + (orow / p.rowbias_rows) * static_cast<long long>(p.N);
             const float rs = (p.rowscale != nullptr && orow >= 0) ? p.rowscale[orow] : 1.f;
             const int n_out_total = g ? (p.N >> 1) : p.N;
             const int ocol0 = g ? col0 / 2 : col0;
+            // bias of this tile's accumulator columns -> smem (read back as broadcasts); visible after the
+            // bar.sync that opens the first box, and not rewritten before every reader passed the last one
+            for (int i = et; i < BLOCK_N; i += EPI_THREADS)
+              sbias[i] = (p.bias != nullptr && col0 + i < p.N) ? __bfloat162float(p.bias[col0 + i]) : 0.f;
+            const bf16* rrow = (p.residual != nullptr && orow >= 0) ? p.residual + orow * p.ldr + ocol0 : nullptr;
+            const bool res_vec = rrow != nullptr && (p.ldr & 7) == 0;
+            uint32_t v[32];
+            uint4 rnext[4];
+            auto issue = [&](int c) {
+              tmem_ld_32x32(taddr + c * 32, v);
+              if (res_vec && ocol0 + (c + 1) * outs_per_acc <= n_out_total) {
+                const uint4* rp = reinterpret_cast<const uint4*>(rrow + c * outs_per_acc);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (q * 8 < outs_per_acc) rnext[q] = __ldg(rp + q);
+              }
+            };
+            if (ehalf < NCHUNKS) issue(ehalf);
+            // rounds of two boxes (one per staging buffer): one barrier pair per round
 #pragma unroll 1
-            for (int bx = 0; bx < nboxes; ++bx) {
-              uint8_t* cb = cstage + (cbuf & 1) * (BLOCK_M * 128);
-              ++cbuf;
-              if (et == 0) bulk_wait_read<1>();           // the store that last used this buffer has read it
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int bx0 = 0; bx0 < nboxes; bx0 += 2) {
+              const int bx1 = min(bx0 + 2, nboxes);
+              if (et == 0) bulk_wait_read<0>();           // the stores of the previous round have read the buffers
+              epi_bar_sync();
 #pragma unroll 1
-              for (int a = 0; a < acc_per_box; ++a) {
-                const int c = (bx * acc_per_box + a) * 32;
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c, v);
+              for (int ci = bx0 * acc_per_box + ehalf; ci < bx1 * acc_per_box; ci += 2) {
+                const int bx = ci / acc_per_box, a = ci - bx * acc_per_box;
+                uint8_t* cb = cstage + (bx & 1) * (BLOCK_M * 128);
                 tmem_ld_wait();
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * rs;
-                const int gc = col0 + c;
-                if (p.bias != nullptr) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (gc + j < p.N) f[j] += __bfloat162float(p.bias[gc + j]);
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 bv = *reinterpret_cast<const float4*>(sbias + ci * 32 + j);
+                  f[j] = fmaf(__uint_as_float(v[j]), rs, bv.x);
+                  f[j + 1] = fmaf(__uint_as_float(v[j + 1]), rs, bv.y);
+                  f[j + 2] = fmaf(__uint_as_float(v[j + 2]), rs, bv.z);
+                  f[j + 3] = fmaf(__uint_as_float(v[j + 3]), rs, bv.w);
                 }
-                if (rb != nullptr) {
+                uint4 rcur[4];
 #pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (gc + j < p.N) f[j] += __bfloat162float(rb[gc + j]);
+                for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+                if (ci + 2 < NCHUNKS) issue(ci + 2);
+                const int gc = col0 + ci * 32;
+                if (rb != nullptr) {
+                  if (gc + 32 <= p.N && (p.N & 7) == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const uint4 u = __ldg(reinterpret_cast<const uint4*>(rb + gc) + q);
+                      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                      for (int w = 0; w < 4; ++w) {
+                        const float2 r2 = unpack_bf16(uu[w]);
+                        f[q * 8 + 2 * w] += r2.x;
+                        f[q * 8 + 2 * w + 1] += r2.y;
+                      }
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                      if (gc + j < p.N) f[j] += __bfloat162float(rb[gc + j]);
+                  }
                 }
                 int nout = 32;
                 if (g) {
+                  if (p.glu == VB_GLU_SWIGLU) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const float x = f[j], y = f[j + 16];
-                    f[j] = (p.glu == VB_GLU_SWIGLU) ? silu(x) * y : x * gelu_erf(y);
+                    for (int j = 0; j < 16; ++j) f[j] = silu(f[j]) * f[j + 16];
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = f[j] * gelu_erf_fast(f[j + 16]);
                   }
                   nout = 16;
                 } else if (p.act != VB_ACT_NONE) {
 #pragma unroll
                   for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
                 }
-                const int oc = ocol0 + bx * bw + a * outs_per_acc;  // first output column of these values
-                if (p.residual != nullptr && orow >= 0) {
-                  const bf16* rp = p.residual + orow * p.ldr + oc;
-                  if (oc + nout <= n_out_total && (p.ldr & 7) == 0) {
+                const int oc = ocol0 + ci * outs_per_acc;  // first output column of these values
+                if (rrow != nullptr) {
+                  if (res_vec && oc + nout <= n_out_total) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                      if (j < nout) {
-                        const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
-                        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+                    for (int q = 0; q < 4; ++q) {
+                      if (q * 8 < nout) {
+                        const uint32_t uu[4] = {rcur[q].x, rcur[q].y, rcur[q].z, rcur[q].w};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                          const float2 r2 = unpack_bf16(uu[q]);
-                          f[j + 2 * q] = r2.x + p.alpha * f[j + 2 * q];
-                          f[j + 2 * q + 1] = r2.y + p.alpha * f[j + 2 * q + 1];
+                        for (int w = 0; w < 4; ++w) {
+                          const float2 r2 = unpack_bf16(uu[w]);
+                          f[q * 8 + 2 * w] = fmaf(p.alpha, f[q * 8 + 2 * w], r2.x);
+                          f[q * 8 + 2 * w + 1] = fmaf(p.alpha, f[q * 8 + 2 * w + 1], r2.y);
                         }
                       }
                     }
                   } else {
+                    const bf16* rp = rrow + ci * outs_per_acc;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                       if (j < nout && oc + j < n_out_total) f[j] = __bfloat162float(rp[j]) + p.alpha * f[j];
@@ -472,15 +518,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
               }
               fence_proxy_async_smem();
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              epi_bar_sync();
               if (et == 0) {
-                const int cc = ocol0 + bx * bw;
-                if (cc < n_out_total) {
-                  if (p.a_mode == 0) {
-                    tma_store_2d(&tmap_c, cb, cc, t.m_blk * BLOCK_M);
-                  } else {
-                    const int tiw = t.m_blk % p.tiles_w, rest = t.m_blk / p.tiles_w;
-                    tma_store_4d(&tmap_c, cb, cc, tiw * p.tw, (rest % p.tiles_h) * p.th, (rest / p.tiles_h) * p.tn);
+                for (int bx = bx0; bx < bx1; ++bx) {
+                  const int cc = ocol0 + bx * bw;
+                  const uint8_t* cb = cstage + (bx & 1) * (BLOCK_M * 128);
+                  if (cc < n_out_total) {
+                    if (p.a_mode == 0) {
+                      tma_store_2d(&tmap_c, cb, cc, t.m_blk * BLOCK_M);
+                    } else {
+                      const int tiw = t.m_blk % p.tiles_w, rest = t.m_blk / p.tiles_w;
+                      tma_store_4d(&tmap_c, cb, cc, tiw * p.tw, (rest % p.tiles_h) * p.th, (rest / p.tiles_h) * p.tn);
+                    }
                   }
                 }
                 bulk_commit();
@@ -495,7 +544,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           rb = p.rowbias + (orow / p.rowbias_rows) * static_cast<long long>(p.N);
         constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += CH) {
+        for (int c = ehalf * CH; c < BLOCK_N; c += 2 * CH) {
           float f[CH];
           if constexpr (CH == 32) {
             uint32_t v[32];
@@ -594,14 +643,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // -------- split-K finalisation without a second kernel: the CTA that completes a tile last
         // sums the partials in split order (deterministic) and applies the fused epilogue.
         const int tile = unit / p.splits;
-        const int et = threadIdx.x - 64;  // 0..127 among the epilogue warps
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        epi_bar_sync();
         if (et == 0) {
           const int prev = atomicAdd(&p.counters[tile], 1);
           *fin_flag = (prev == p.splits - 1) ? 1 : 0;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        epi_bar_sync();
         if (*fin_flag) {
           __threadfence();
           int r0, r1, c0, c1;  // tile extent in C orientation
@@ -611,14 +659,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int oc0 = g ? c0 / 2 : c0, oc1 = g ? c1 / 2 : c1;
           const int chunks = (oc1 - oc0 + 7) / 8;
           const int items = (r1 - r0) * chunks;
-          for (int it = et; it < items; it += 128) {
+          for (int it = et; it < items; it += EPI_THREADS) {
             const int row = r0 + it / chunks, oc = oc0 + (it % chunks) * 8;
             reduce_item(p.ws, p.splits, p.ws_split_stride, p.ws_ld, row, oc, p.cols_c, p.out, p.ldo, p.bias,
                         p.rowbias, p.rowbias_rows, p.residual, p.ldr, p.alpha, p.act, p.glu, p.out_fp32, p.rowscale);
           }
           if (et == 0) p.counters[tile] = 0;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // fin_flag is reused by the next unit
+        epi_bar_sync();  // fin_flag is reused by the next unit
       }
     }
   }
@@ -680,7 +728,7 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* 
 template <int BN, int STAGES>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                       cudaStream_t stream) {
-  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + (BN >= 32 ? 2 * BLOCK_M * 128 : 0) + 1024 + 256;
+  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + (BN >= 32 ? 2 * BLOCK_M * 128 : 0) + 1024 + 256 + 1024;
   static_assert(smem <= SMEM_LIMIT, "smem budget");
   static bool attr_set = false;
   auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES>;
@@ -897,14 +945,21 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  int tw = wo < 128 ? wo : 128;
-  // keep boxes rectangular: tw must not exceed 128/stride-independent limit of 256 elements
-  int th = 128 / tw;
-  if (th > ho) th = ho;
-  if (th < 1) th = 1;
-  int tn = 128 / (tw * th);
-  if (tn > nb) tn = static_cast<int>(nb);
-  if (tn < 1) tn = 1;
+  // pixel tile tw x th x tn (<= 128 accumulator rows): the shape that covers the output with the fewest tiles;
+  // ties go to the widest tile (longest contiguous runs for the TMA boxes)
+  int tw = 1, th = 1, tn = 1;
+  {
+    long long best = -1;
+    for (int cw = wo < 128 ? wo : 128; cw >= 1; --cw) {
+      const int hmax = 128 / cw < ho ? 128 / cw : ho;
+      for (int ch = hmax; ch >= 1; --ch) {
+        int cn = 128 / (cw * ch);
+        if (cn > nb) cn = static_cast<int>(nb);
+        const long long blocks = static_cast<long long>((wo + cw - 1) / cw) * ((ho + ch - 1) / ch) * ((nb + cn - 1) / cn);
+        if (best < 0 || blocks < best) { best = blocks; tw = cw; th = ch; tn = cn; }
+      }
+    }
+  }
   p.a_mode = 1;
   p.cin_chunks = cin_chunks;
   p.kw = kw;
