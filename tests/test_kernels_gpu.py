@@ -140,7 +140,8 @@ def test_conv_epilogue(cuda):
     close(d, ref2, 5e-2, 2e-2, "direct conv")
 
 
-@pytest.mark.parametrize("rows,d", [(7, 4096), (300, 1024), (33, 320), (5, 1280), (3, 11008), (9, 512)])
+@pytest.mark.parametrize("rows,d", [(7, 4096), (300, 1024), (33, 320), (5, 1280), (3, 11008), (9, 512),
+                                    (2001, 320), (1025, 512), (4099, 64), (40960, 320)])
 def test_norms(cuda, rows, d):
     from vitron_b200 import ops
     x, w, b = rnd((rows, d), cuda, 1, 2.0), rnd((d,), cuda, 2), rnd((d,), cuda, 3)
@@ -151,7 +152,11 @@ def test_norms(cuda, rows, d):
 
 
 @pytest.mark.parametrize("n,sp,c,act", [(16, 40 * 64, 320, 4), (2, 16 * 100, 640, 0), (3, 77, 1280, 4), (1, 64 * 64, 512, 3),
-                                        (2, 50, 2560, 4), (2, 33, 960, 4)])
+                                        (2, 50, 2560, 4), (2, 33, 960, 4),
+                                        # slabs too large for the single-pass kernel -> stats + apply
+                                        (1, 16 * 2560, 320, 4), (1, 16 * 640, 640, 4), (2, 5000, 1920, 0),
+                                        # UNet temporal layouts on the single-pass kernel
+                                        (1, 16 * 160, 1280, 4), (1, 16 * 40, 1280, 0), (16, 20 * 32, 640, 4)])
 def test_groupnorm(cuda, n, sp, c, act):
     from vitron_b200 import ops
     x, w, b = rnd((n, sp, c), cuda, 1, 1.5), rnd((c,), cuda, 2), rnd((c,), cuda, 3)
@@ -281,6 +286,15 @@ def test_attention_short(cuda, nseq, S, H):
     q, k, v = (base[:, :, i].permute(1, 0, 2, 3) for i in range(3))
     out = ops.attention_short(q, k, v)
     close(out, sdpa_ref(q, k, v, 1 / 8.0), 2e-2, 2e-2, "short attention")
+
+
+def test_attention_short_unaligned_rows(cuda):
+    """Row pieces that are only 4-byte aligned take the scalar kernel instead of the 16-byte / mma.sync one."""
+    from vitron_b200 import ops
+    base = rnd((16, 50, 3, 4, 66), cuda, 3)
+    q, k, v = (base[:, :, i, :, 2:].permute(1, 0, 2, 3) for i in range(3))
+    out = ops.attention_short(q, k, v)
+    close(out, sdpa_ref(q, k, v, 1 / 8.0), 2e-2, 2e-2, "short attention (unaligned)")
 
 
 def rope_ref(x, pos, theta):

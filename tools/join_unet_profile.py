@@ -25,7 +25,7 @@ for k, v in sorted(byk.items(), key=lambda kv: -kv[1][1])[:25]:
     print(f"{v[1] / 1000:8.3f} ms {100 * v[1] / tot:5.1f}%  n={v[0]:4d}  {k[:110]}")
 # ---- attach shapes: walk ops in order, consuming the expected kernels
 EXPECT = {"gemm": ["gemm_bf16_tcgen05_kernel", "gemv_bf16_kernel"], "conv_nhwc": ["gemm_bf16_tcgen05_kernel"],
-          "conv_nhwc_direct": ["conv_direct"], "layernorm": ["rownorm"], "groupnorm_nhwc": ["gn_stats", "gn_apply"],
+          "conv_nhwc_direct": ["conv_direct"], "layernorm": ["rownorm"], "groupnorm_nhwc": ["gn_stats", "gn_apply", "gn_fused"],
           "attention": ["flash_attn"], "attention_short": ["attn_short"], "add_rowgroup": ["add_rowgroup"],
           "upsample2x_nhwc": ["upsample"], "add": ["add_"], "cfg_combine": ["cfg_"], "rmsnorm": ["rownorm"]}
 i = 0
@@ -42,6 +42,8 @@ for op in seq:
         if any(p in n for p in pats):
             got += 1
             t += us
+            if "gn_fused" in n:
+                break
         else:
             other += us
     key = f'{op["op"]} {op["shapes"][:2]} {op["pos"]} {op["kw"]}'

@@ -336,6 +336,117 @@ __global__ void __launch_bounds__(WARPS * 32) attn_short_kernel(const ShortParam
   }
 }
 
+// S <= 16, head_dim 64, 16-byte aligned rows: one warp per (sequence, head) on mma.sync tensor cores.
+// The three 16 x 64 operand tiles arrive with twelve independent 16-byte loads per lane (rows >= S are
+// zero-filled), go through warp-private shared memory for ldmatrix, and the whole attention is
+// 8 (QK^T) + 8 (PV) m16n8k16 MMAs; the result leaves through the Q tile with 16-byte stores.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) attn_short_mma_kernel(const ShortParams p) {
+  constexpr int HD = 64, LD = HD + 8;
+  __shared__ __align__(16) bf16 sm[WARPS][3][16][LD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = static_cast<long long>(blockIdx.x) * WARPS + warp;
+  if (item >= p.nseq * p.H) return;  // no CTA-wide barriers below
+  const long long seq = item / p.H;
+  const int h = static_cast<int>(item % p.H);
+  const long long so = seq / p.inner, si = seq % p.inner;
+  const bf16* qg = p.q + so * p.q_so + si * p.q_sb + h * p.q_sh;
+  const bf16* kg = p.k + so * p.k_so + si * p.k_sb + h * p.k_sh;
+  const bf16* vg = p.v + so * p.v_so + si * p.v_sb + h * p.v_sh;
+  const int S = p.S;
+  const int piece = (lane & 7) * 8, r0 = lane >> 3;
+  uint4 rq[4], rk[4], rv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = r0 + 4 * i;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    rq[i] = rk[i] = rv[i] = z;
+    if (row < S) {
+      rq[i] = __ldg(reinterpret_cast<const uint4*>(qg + row * p.q_ss + piece));
+      rk[i] = __ldg(reinterpret_cast<const uint4*>(kg + row * p.k_ss + piece));
+      rv[i] = __ldg(reinterpret_cast<const uint4*>(vg + row * p.v_ss + piece));
+    }
+  }
+  bf16 (*sq)[LD] = sm[warp][0];
+  bf16 (*sk)[LD] = sm[warp][1];
+  bf16 (*sv)[LD] = sm[warp][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = r0 + 4 * i;
+    *reinterpret_cast<uint4*>(&sq[row][piece]) = rq[i];
+    *reinterpret_cast<uint4*>(&sk[row][piece]) = rk[i];
+    *reinterpret_cast<uint4*>(&sv[row][piece]) = rv[i];
+  }
+  __syncwarp();
+  const int g = lane >> 2, t = lane & 3;
+  float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+    ldsm_x4(smem_u32(&sq[lane & 15][ks * 16 + (lane >> 4) * 8]), a0, a1, a2, a3);
+    ldsm_x4(smem_u32(&sk[(lane & 7) + (lane >> 4) * 8][ks * 16 + ((lane >> 3) & 1) * 8]), b0, b1, b2, b3);
+    mma_16816(sc[0], a0, a1, a2, a3, b0, b1);
+    mma_16816(sc[1], a0, a1, a2, a3, b2, b3);
+  }
+  // softmax over the S valid keys; thread holds rows g (e = 0, 1) and g + 8 (e = 2, 3), keys nt * 8 + 2t + (e & 1)
+  const float sl2 = p.scale * 1.4426950408889634f;
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (nt * 8 + 2 * t + (e & 1) >= S) sc[nt][e] = -INFINITY;
+      mx[e >> 1] = fmaxf(mx[e >> 1], sc[nt][e]);
+    }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      sc[nt][e] = exp2f((sc[nt][e] - mx[e >> 1]) * sl2);
+      sum[e >> 1] += sc[nt][e];
+    }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+    sum[r] = 1.f / sum[r];
+  }
+  const uint32_t pa0 = pack_bf16(sc[0][0] * sum[0], sc[0][1] * sum[0]);
+  const uint32_t pa1 = pack_bf16(sc[0][2] * sum[1], sc[0][3] * sum[1]);
+  const uint32_t pa2 = pack_bf16(sc[1][0] * sum[0], sc[1][1] * sum[0]);
+  const uint32_t pa3 = pack_bf16(sc[1][2] * sum[1], sc[1][3] * sum[1]);
+  float oa[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) oa[i][0] = oa[i][1] = oa[i][2] = oa[i][3] = 0.f;
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    uint32_t b0, b1, b2, b3;
+    ldsm_x4_t(smem_u32(&sv[(lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]), b0, b1, b2, b3);
+    mma_16816(oa[2 * np], pa0, pa1, pa2, pa3, b0, b1);
+    mma_16816(oa[2 * np + 1], pa0, pa1, pa2, pa3, b2, b3);
+  }
+  // O through the (already consumed) Q tile, then 16-byte row pieces
+  __syncwarp();
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<uint32_t*>(&sq[g][nt * 8 + 2 * t]) = pack_bf16(oa[nt][0], oa[nt][1]);
+    *reinterpret_cast<uint32_t*>(&sq[g + 8][nt * 8 + 2 * t]) = pack_bf16(oa[nt][2], oa[nt][3]);
+  }
+  __syncwarp();
+  bf16* og = p.o + so * p.o_so + si * p.o_sb + h * p.o_sh;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = r0 + 4 * i;
+    if (row < S) *reinterpret_cast<uint4*>(og + row * p.o_ss + piece) = *reinterpret_cast<const uint4*>(&sq[row][piece]);
+  }
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -409,6 +520,16 @@ extern "C" int vb200_attention_short(const void* q, const void* k, const void* v
   p.nseq = nseq; p.H = (int)H; p.S = (int)S; p.scale = scale;
   p.inner = inner; p.q_so = q_so; p.k_so = k_so; p.v_so = v_so; p.o_so = o_so;
   const long long items = nseq * H;
+  // tensor-core kernel when every row piece can move as 16 bytes
+  bool vec16 = S <= 16 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                            reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const int64_t all[16] = {q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh, q_so, k_so, v_so, o_so};
+  for (int i = 0; i < 16; ++i) vec16 = vec16 && (all[i] % 8 == 0);
+  if (vec16) {
+    attn_short_mma_kernel<4><<<static_cast<unsigned>((items + 3) / 4), 128, 0, stream>>>(p);
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+  }
   if (S <= 8) attn_short_kernel<8, 4><<<static_cast<unsigned>((items + 3) / 4), 128, 0, stream>>>(p);
   else if (S <= 16) attn_short_kernel<16, 4><<<static_cast<unsigned>((items + 3) / 4), 128, 0, stream>>>(p);
   else attn_short_kernel<32, 2><<<static_cast<unsigned>((items + 1) / 2), 64, 0, stream>>>(p);

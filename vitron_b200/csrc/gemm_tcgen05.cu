@@ -28,6 +28,12 @@ constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quadrant
 constexpr int EPI_THREADS = 32 * NUM_EPI_WARPS;
 constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the epilogue warps only
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 }
@@ -324,6 +330,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int et = threadIdx.x - 64;    // 0 .. EPI_THREADS-1
     int acc = 0;
     uint32_t acc_phase = 0;
+    int cbuf = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       TileCoord t = decode_work(p, unit);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -421,16 +428,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
               }
             };
             if (ehalf < NCHUNKS) issue(ehalf);
-            // rounds of two boxes (one per staging buffer): one barrier pair per round
+            // staging buffers alternate box by box; the store of box b overlaps the epilogue math of box b+1
 #pragma unroll 1
-            for (int bx0 = 0; bx0 < nboxes; bx0 += 2) {
-              const int bx1 = min(bx0 + 2, nboxes);
-              if (et == 0) bulk_wait_read<0>();           // the stores of the previous round have read the buffers
+            for (int bx = 0; bx < nboxes; ++bx) {
+              uint8_t* cb = cstage + (cbuf & 1) * (BLOCK_M * 128);
+              ++cbuf;
+              if (et == 0) bulk_wait_read<1>();           // the store that last used this buffer has read it
               epi_bar_sync();
 #pragma unroll 1
-              for (int ci = bx0 * acc_per_box + ehalf; ci < bx1 * acc_per_box; ci += 2) {
-                const int bx = ci / acc_per_box, a = ci - bx * acc_per_box;
-                uint8_t* cb = cstage + (bx & 1) * (BLOCK_M * 128);
+              for (int a = (ehalf + bx * acc_per_box) & 1; a < acc_per_box; a += 2) {
+                const int ci = bx * acc_per_box + a;      // accumulator chunk (32 columns); ci % 2 == ehalf
                 tmem_ld_wait();
                 float f[32];
 #pragma unroll
@@ -520,16 +527,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
               fence_proxy_async_smem();
               epi_bar_sync();
               if (et == 0) {
-                for (int bx = bx0; bx < bx1; ++bx) {
-                  const int cc = ocol0 + bx * bw;
-                  const uint8_t* cb = cstage + (bx & 1) * (BLOCK_M * 128);
-                  if (cc < n_out_total) {
-                    if (p.a_mode == 0) {
-                      tma_store_2d(&tmap_c, cb, cc, t.m_blk * BLOCK_M);
-                    } else {
-                      const int tiw = t.m_blk % p.tiles_w, rest = t.m_blk / p.tiles_w;
-                      tma_store_4d(&tmap_c, cb, cc, tiw * p.tw, (rest % p.tiles_h) * p.th, (rest / p.tiles_h) * p.tn);
-                    }
+                const int cc = ocol0 + bx * bw;
+                if (cc < n_out_total) {
+                  if (p.a_mode == 0) {
+                    tma_store_2d(&tmap_c, cb, cc, t.m_blk * BLOCK_M);
+                  } else {
+                    const int tiw = t.m_blk % p.tiles_w, rest = t.m_blk / p.tiles_w;
+                    tma_store_4d(&tmap_c, cb, cc, tiw * p.tw, (rest % p.tiles_h) * p.th, (rest / p.tiles_h) * p.tn);
                   }
                 }
                 bulk_commit();
