@@ -92,7 +92,7 @@ def cpu_sample(threads=None):
     layers — prefill S=768 at B=1, 4 cached decode steps at B=8 — fp32, all host threads; the
     per-layer times are scaled to the full depth and batch. Returns (tokens_per_s, info)."""
     from oracle import restate_llm as R
-    threads = threads or os.cpu_count() or 1
+    threads = _pick_threads()
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(0)
     rn = lambda *s: torch.randn(s, generator=g) * 0.02
@@ -131,6 +131,34 @@ def cpu_sample(threads=None):
 _CPU_CACHE = {}
 
 
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _pick_threads():
+    """torch's intra-op pool does not always scale to every hardware thread of a large host (SMT siblings,
+    cgroup quotas): probe a prefill-shaped fp32 GEMM at a few thread counts once and keep the fastest."""
+    if "threads" in _CPU_CACHE:
+        return _CPU_CACHE["threads"]
+    avail = _host_cores()
+    x, w = torch.randn(768, 4096), torch.randn(4096, 4096)
+    best, best_t = avail, None
+    for th in sorted({avail, max(1, avail // 2), min(avail, 64), min(avail, 32), min(avail, 16)}, reverse=True):
+        torch.set_num_threads(th)
+        torch.nn.functional.linear(x, w)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.linear(x, w)
+        t = time.perf_counter() - t0
+        if best_t is None or t < best_t * 0.95:
+            best, best_t = th, t
+    _CPU_CACHE["threads"] = best
+    return best
+
+
 def _cpu_time(R, sd, cfg, vsd, vcfg, vp, rn, g, LL, d):
     with torch.no_grad():
         t0 = time.perf_counter()
@@ -142,34 +170,55 @@ def _cpu_time(R, sd, cfg, vsd, vcfg, vp, rn, g, LL, d):
         t_pre = time.perf_counter() - t0
         m8 = R.LlamaCPU(sd, cfg)
         m8.prefill(rn(BATCH, 64, d))  # short context is enough for the weight-bound decode step
-        tok = torch.zeros(BATCH, dtype=torch.long)
-        t0 = time.perf_counter()
-        for _ in range(4):
-            m8.step(tok)
-        t_dec = (time.perf_counter() - t0) / 4
-    full = BATCH * (23 / LL) * t_vit + BATCH * (32 / LL) * t_pre + NEW * (32 / LL) * t_dec
+        # decoder layers and the (single) norm + lm_head are timed separately, so that only the layers are
+        # scaled to the full depth; small-M GEMVs do not always profit from every host thread, so the
+        # decode part is timed at two thread counts and the faster one is reported
+        import torch.nn.functional as F
+        best = None
+        base_threads = torch.get_num_threads()
+        for th in sorted({base_threads, max(1, base_threads // 2), min(base_threads, 16)}, reverse=True):
+            torch.set_num_threads(th)
+            h = rn(BATCH, 1, d)
+            m8._layers(h, m8.pos)  # warm
+            m8.pos += 1
+            t0 = time.perf_counter()
+            for _ in range(3):
+                m8._layers(h, m8.pos)
+                m8.pos += 1
+            t_lay = (time.perf_counter() - t0) / 3
+            t0 = time.perf_counter()
+            for _ in range(3):
+                F.linear(R.rms_norm(h, sd["model.norm.weight"], 1e-5), sd["lm_head.weight"])
+            t_head = (time.perf_counter() - t0) / 3
+            if best is None or t_lay + t_head < best[0] + best[1]:
+                best = (t_lay, t_head, th)
+        t_lay, t_head, dec_threads = best
+        torch.set_num_threads(base_threads)
+    t_dec_full = (32 / LL) * t_lay + t_head
+    full = BATCH * (23 / LL) * t_vit + BATCH * (32 / LL) * t_pre + NEW * t_dec_full
     info = {"t_vit_2layers_1img_s": round(t_vit, 3), "t_prefill_2layers_b1_s": round(t_pre, 3),
-            "t_decode_step_2layers_b8_s": round(t_dec, 4), "extrapolated_step_s": round(full, 2)}
+            "t_decode_2layers_b8_s": round(t_lay, 4), "t_lm_head_b8_s": round(t_head, 4), "threads": base_threads, "decode_threads": dec_threads,
+            "extrapolated_decode_step_s": round(t_dec_full, 3), "extrapolated_step_s": round(full, 2)}
     return BATCH * NEW / full, info
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
     vals, info = [], {}
     for i in range(args.warmup + args.steps):
-        v, info = cpu_sample(cores)
+        v, info = cpu_sample()
         if i >= args.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
     sample = ("oracle port (fp32 torch CPU restatement of the reference path): ViT-L/14 2/23 layers on 1 image, "
-              "LLaMA-7B 2/32 layers prefill S=768 B=1 + 4 cached decode steps B=8; scaled to full depth and batch 8")
+              "LLaMA-7B 2/32 layers prefill S=768 B=1 + 3 cached decode steps B=8 (layers scaled to full depth, lm_head timed once); batch 8")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * BATCH * NEW / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample, **info},
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": info.get("threads"), "host_cores": _host_cores(), "kind": "port",
+                             "sample": sample, **info},
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -405,9 +454,11 @@ def run_ours(args, rank, world):
             torch.cuda.empty_cache()
             line["unet"] = bench_unet(device, tf_peak)
         if cpu_v is not None:
-            line["cpu_baseline"] = {"value": cpu_v, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "oracle port, fp32, ViT 2/23 + LLaMA 2/32 layers (prefill B=1 S=768, 4 decode "
-                                              "steps B=8), scaled to full depth and batch 8", **cpu_info}
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "tokens/s", "cores": cpu_info.get("threads"),
+                                    "host_cores": _host_cores(), "kind": "port",
+                                    "sample": "oracle port, fp32, ViT 2/23 + LLaMA 2/32 layers (prefill B=1 S=768, 3 decode "
+                                              "steps B=8; layers scaled to full depth, lm_head timed once), batch 8",
+                                    **cpu_info}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

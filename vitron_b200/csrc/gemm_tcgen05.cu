@@ -16,6 +16,7 @@
 // Covers (reference file:line in DESIGN.md): LLaMA q/k/v/o/gate/up/down/lm_head, CLIP ViT
 // q/k/v/out/fc1/fc2, mm_projector, region MLP, every Linear / Conv2d(3x3,1x1) / Conv3d(3,1,1) of
 // UNetSD_I2VGen, SEEM FPN convs + mask einsum, GLIGEN fuser linears.
+#include <cstdlib>
 #include "common.cuh"
 #include "vitron_b200.h"
 
@@ -765,6 +766,10 @@ static int pick_block_n(long long M, long long N, int glu) {
   // widest tile wins unless it leaves SMs idle or pads many columns:
   // score = tile efficiency x wave utilisation x column fill. 160 divides the UNet widths 320/640/1280.
   (void)glu;
+  if (const char* force = getenv("VB200_FORCE_BN")) {  // tuning knob for tools/bn_sweep.py
+    const int v = atoi(force);
+    if (v == 256 || v == 160 || v == 128 || v == 64 || v == 32) return v;
+  }
   const int sms = vb_num_sms();
   const long long mb = (M + BLOCK_M - 1) / BLOCK_M;
   const int cands[5] = {256, 160, 128, 64, 32};

@@ -112,7 +112,7 @@ __global__ void rope_table_kernel(const int32_t* __restrict__ positions, float* 
   table[b * 2 * half + half + i] = sn;
 }
 
-template <bool ROPE>
+template <bool ROPE, int MAX_TRIPS>
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict__ k_pages,
                    bf16* __restrict__ v_pages, const int32_t* __restrict__ block_table, int max_pages,
@@ -123,7 +123,6 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
   // this split depend only on (split, per), so they are fetched before anything else (the block table is
   // constant during decoding -> safe ahead of the PDL dependency wait).
   constexpr int HD = 128;
-  constexpr int MAX_TRIPS = DEC_CHUNK / 64;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 3, sub = lane & 7;
@@ -440,7 +439,9 @@ extern "C" int vb200_rope_kv_append(void* qkv, int64_t ld_qkv, const int32_t* po
 }
 
 static int decode_splits(int64_t max_kv_len) {
-  int s = static_cast<int>((max_kv_len + DEC_CHUNK - 1) / DEC_CHUNK);
+  // 256-key splits: the per-CTA chain of dependent 64-key trips (the kernel's critical path at decode-time
+  // context lengths) stays at 4; contexts beyond 32 x 256 keys fall back to 512-key splits
+  int s = static_cast<int>((max_kv_len + DEC_CHUNK / 2 - 1) / (DEC_CHUNK / 2));
   if (s < 1) s = 1;
   if (s > 32) s = 32;
   return s;
@@ -480,18 +481,21 @@ static int launch_attn_decode(const void* q, int64_t ld_q, void* k_pages, void* 
   }
   dim3 grid(splits, static_cast<unsigned>(n_heads), static_cast<unsigned>(B));
   cudaError_t e;
-  if (rope_table != nullptr)
-    e = vb_launch(attn_decode_kernel<true>, grid, dim3(DEC_THREADS), 0, stream,
-                  reinterpret_cast<const bf16*>(q), static_cast<long long>(ld_q), reinterpret_cast<bf16*>(k_pages),
-                  reinterpret_cast<bf16*>(v_pages), block_table, static_cast<int>(max_pages), kv_len,
-                  static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, per, ws_ml, ws_o, counters,
-                  reinterpret_cast<bf16*>(out), static_cast<long long>(ld_o), rope_table);
-  else
-    e = vb_launch(attn_decode_kernel<false>, grid, dim3(DEC_THREADS), 0, stream,
-                  reinterpret_cast<const bf16*>(q), static_cast<long long>(ld_q), reinterpret_cast<bf16*>(k_pages),
-                  reinterpret_cast<bf16*>(v_pages), block_table, static_cast<int>(max_pages), kv_len,
-                  static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, per, ws_ml, ws_o, counters,
-                  reinterpret_cast<bf16*>(out), static_cast<long long>(ld_o), static_cast<const float*>(nullptr));
+#define VB_LAUNCH_DECODE(ROPE_, TRIPS_, TABLE_)                                                                    \
+  e = vb_launch(attn_decode_kernel<ROPE_, TRIPS_>, grid, dim3(DEC_THREADS), 0, stream,                            \
+                reinterpret_cast<const bf16*>(q), static_cast<long long>(ld_q), reinterpret_cast<bf16*>(k_pages), \
+                reinterpret_cast<bf16*>(v_pages), block_table, static_cast<int>(max_pages), kv_len,                \
+                static_cast<int>(n_heads), static_cast<int>(page_size), scale, splits, per, ws_ml, ws_o, counters, \
+                reinterpret_cast<bf16*>(out), static_cast<long long>(ld_o), TABLE_)
+  const float* no_table = nullptr;
+  if (rope_table != nullptr) {
+    if (per <= DEC_CHUNK / 2) VB_LAUNCH_DECODE(true, DEC_CHUNK / 128, rope_table);
+    else VB_LAUNCH_DECODE(true, DEC_CHUNK / 64, rope_table);
+  } else {
+    if (per <= DEC_CHUNK / 2) VB_LAUNCH_DECODE(false, DEC_CHUNK / 128, no_table);
+    else VB_LAUNCH_DECODE(false, DEC_CHUNK / 64, no_table);
+  }
+#undef VB_LAUNCH_DECODE
   if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
   return VB_OK;
 }

@@ -146,6 +146,49 @@ def unet_shapes(cfg):
     return s
 
 
+def seem_shapes(in_channels=(192, 384, 768, 1536), conv_dim=512, ffn=2048, queries=101, enc_layers=6, dec_layers=9,
+                dim_proj=512):
+    """Parameter names / shapes of SEEM's sem_seg_head.{pixel_decoder,predictor} that the seg path reads
+    (transformer_encoder_fpn.py:23-308, seem.py:193-392)."""
+    C, s = conv_dim, {}
+
+    def lin(p, o, i):
+        s[p + ".weight"], s[p + ".bias"] = [o, i], [o]
+
+    def norm(p):
+        s[p + ".weight"], s[p + ".bias"] = [C], [C]
+
+    def mha(p):
+        s[p + ".in_proj_weight"], s[p + ".in_proj_bias"] = [3 * C, C], [3 * C]
+        lin(p + ".out_proj", C, C)
+
+    pd = "pixel_decoder."
+    s[pd + "input_proj.weight"], s[pd + "input_proj.bias"] = [C, in_channels[-1], 1, 1], [C]
+    for i in range(enc_layers):
+        q = pd + f"transformer.encoder.layers.{i}"
+        mha(q + ".self_attn"); lin(q + ".linear1", ffn, C); lin(q + ".linear2", C, ffn); norm(q + ".norm1"); norm(q + ".norm2")
+    for idx, cin in enumerate(in_channels):
+        s[pd + f"layer_{idx + 1}.weight"] = [C, C, 3, 3]
+        norm(pd + f"layer_{idx + 1}.norm")
+        if idx != len(in_channels) - 1:
+            s[pd + f"adapter_{idx + 1}.weight"] = [C, cin, 1, 1]
+            norm(pd + f"adapter_{idx + 1}.norm")
+    s[pd + "mask_features.weight"], s[pd + "mask_features.bias"] = [C, C, 3, 3], [C]
+    pr = "predictor."
+    for i in range(dec_layers):
+        mha(pr + f"transformer_cross_attention_layers.{i}.multihead_attn"); norm(pr + f"transformer_cross_attention_layers.{i}.norm")
+        mha(pr + f"transformer_self_attention_layers.{i}.self_attn"); norm(pr + f"transformer_self_attention_layers.{i}.norm")
+        lin(pr + f"transformer_ffn_layers.{i}.linear1", ffn, C); lin(pr + f"transformer_ffn_layers.{i}.linear2", C, ffn)
+        norm(pr + f"transformer_ffn_layers.{i}.norm")
+    norm(pr + "decoder_norm")
+    for n, shape in (("query_feat.weight", [queries, C]), ("query_embed.weight", [queries, C]), ("level_embed.weight", [3, C])):
+        s[pr + n] = shape
+    for i in range(3):
+        lin(pr + f"mask_embed.layers.{i}", C, C)
+    s[pr + "class_embed"] = [C, dim_proj]
+    return s
+
+
 def random_state_dict(shapes, device, seed=0, std=0.02):
     """N(0, std) weights, unit norm gains, zero biases, generated on `device`."""
     g = torch.Generator(device=device).manual_seed(seed)
