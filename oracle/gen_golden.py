@@ -125,7 +125,89 @@ def gen_gligen(seed=31):
     print("gligen_tiny.pt", [tuple(c["block_out"].shape) for c in out["cases"]])
 
 
-GENERATORS = {"vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen}
+SEEM_TINY = dict(in_channels=(32, 48, 64, 96), C=128, ffn=256, Q=16, enc_layers=2, dec_layers=3, dim_proj=64, heads=2,
+                 n_text=8, logit_scale=1.3)
+
+
+def _seem_attn_arch():
+    """ATTENTION_ARCH of configs/seem/seem_focall_lang.yaml:114-139."""
+    return {
+        "VARIABLE": {"queries": ["object"], "tokens": ["grounding", "spatial", "visual", "audio"]},
+        "SELF_ATTENTION": {
+            "queries": {"object": ["queries_object", "tokens_grounding", "tokens_spatial", "tokens_visual", "tokens_audio"]},
+            "tokens": {"grounding": ["queries_object", "tokens_grounding"], "spatial": ["tokens_spatial"],
+                       "visual": ["tokens_visual"], "audio": ["queries_object", "tokens_audio"]}},
+        "CROSS_ATTENTION": {"queries": {"object": True},
+                            "tokens": {"grounding": False, "spatial": False, "visual": False, "audio": False}},
+        "MASKING": ["tokens_spatial", "tokens_grounding", "tokens_visual", "tokens_audio"],
+        "DUPLICATION": {"queries": {"grounding": "queries_object", "spatial": "queries_object"}},
+        "SPATIAL_MEMORIES": 32,
+    }
+
+
+def build_reference_seem(t=SEEM_TINY, seed=41):
+    """The UNMODIFIED TransformerEncoderPixelDecoder + MultiScaleMaskedTransformerDecoder (through the
+    detectron2-layer stubs of refshim.setup_seem), seeded weights; returns (pixel_decoder, predictor, sd)."""
+    import torch.nn as nn
+    PD, MD, ShapeSpec = refshim.seem_classes()
+    shape = {f"res{i + 2}": ShapeSpec(channels=c, stride=4 << i) for i, c in enumerate(t["in_channels"])}
+    pd = PD(input_shape=shape, transformer_dropout=0.0, transformer_nheads=t["heads"], transformer_dim_feedforward=t["ffn"],
+            transformer_enc_layers=t["enc_layers"], transformer_pre_norm=False, conv_dim=t["C"], mask_dim=t["C"],
+            mask_on=True, norm="GN").eval()
+
+    class Lang(nn.Module):
+        """Only `compute_similarity` of language/vlpencoder.py:293-299 is on the seg path; the text
+        embeddings are an input (the text tower is out of scope)."""
+
+        def __init__(self):
+            super().__init__()
+            self.logit_scale = nn.Parameter(torch.tensor(float(t["logit_scale"])))
+            self.register_buffer("default_text_embeddings", torch.zeros(t["n_text"], t["dim_proj"]))
+
+        def compute_similarity(self, v_emb, name="default", fake=False):
+            v_emb = v_emb / (v_emb.norm(dim=-1, keepdim=True) + 1e-7)
+            t_emb = getattr(self, "{}_text_embeddings".format(name))
+            return self.logit_scale.exp() * v_emb @ t_emb.unsqueeze(0).transpose(1, 2)
+
+    # task switch of configs/seem/seem_focall_lang.yaml:60-86 (MASK, SPATIAL enabled; the rest disabled)
+    task_switch = {"bbox": False, "mask": True, "spatial": True, "grounding": False, "openimage": {"grounding": False, "mask": False},
+                   "visual": False, "audio": False}
+    md = MD(Lang(), t["C"], True, hidden_dim=t["C"], dim_proj=t["dim_proj"], num_queries=t["Q"], contxt_len=77,
+            nheads=t["heads"], dim_feedforward=t["ffn"], dec_layers=t["dec_layers"], pre_norm=False, mask_dim=t["C"],
+            task_switch=task_switch, enforce_input_project=False, max_spatial_len=[512, 512, 512, 512],
+            attn_arch=_seem_attn_arch()).eval()
+    shapes = {}
+    shapes.update({"pixel_decoder." + k: v for k, v in shapes_of(pd).items()})
+    shapes.update({"predictor." + k: v for k, v in shapes_of(md).items() if not k.startswith("lang_encoder.")})
+    sd = seeded_state_dict(shapes, seed)
+    pd.load_state_dict({k[len("pixel_decoder."):]: v for k, v in sd.items() if k.startswith("pixel_decoder.")})
+    miss, unexp = md.load_state_dict({k[len("predictor."):]: v for k, v in sd.items() if k.startswith("predictor.")}, strict=False)
+    assert not unexp and all(m.startswith("lang_encoder.") for m in miss), (miss, unexp)
+    return pd, md, sd, shapes
+
+
+def gen_seem(seed=41):
+    """SEEM pixel decoder + mask decoder, task='seg', extra={} from the unmodified reference classes."""
+    t = SEEM_TINY
+    pd, md, sd, shapes = build_reference_seem(t, seed)
+    g = torch.Generator().manual_seed(seed)
+    feats = {f"res{i + 2}": torch.randn((1, c, 32 >> i, 40 >> i), generator=g) for i, c in enumerate(t["in_channels"])}
+    t_emb = torch.randn((t["n_text"], t["dim_proj"]), generator=g)
+    t_emb = t_emb / t_emb.norm(dim=-1, keepdim=True)
+    md.lang_encoder.default_text_embeddings.copy_(t_emb)
+    with torch.no_grad():
+        mf, enc, multi = pd.forward_features(feats)
+        out = md(multi, mf, task="seg", extra={})
+    keep = {k: out[k] for k in ("pred_logits", "pred_masks", "pred_maskembs")}
+    keep["aux_outputs"] = [{k: a[k] for k in ("pred_logits", "pred_masks", "pred_maskembs")} for a in out["aux_outputs"]]
+    fx = dict(seed=seed, cfg=dict(t), shapes=shapes, features=feats, t_emb=t_emb, mask_features=mf, enc_features=enc,
+              multi_scale=multi, out=keep, out_keys=sorted(out.keys()))
+    torch.save(fx, os.path.join(OUT, "seem_tiny.pt"))
+    print("seem_tiny.pt", tuple(mf.shape), tuple(out["pred_masks"].shape), float(out["pred_masks"].abs().max()),
+          len(out["aux_outputs"]), sorted(out.keys()))
+
+
+GENERATORS = {"vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen, "seem": gen_seem}
 
 
 def main(argv):

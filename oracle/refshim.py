@@ -250,3 +250,121 @@ def seem_pieces():
     base = "modules/SEEM/demo_code/xdecoder"
     ns.attn = load_file("ref_seem_attn", base + "/utils/attn.py")
     return ns
+
+
+_seem_ready = False
+
+
+def setup_seem():
+    """Make the *unmodified* SEEM classes importable: `xdecoder.body.decoder.seem`
+    (MultiScaleMaskedTransformerDecoder), `xdecoder.body.encoder.transformer_encoder_fpn`
+    (TransformerEncoderPixelDecoder) and `xdecoder.backbone.focal` (FocalNet).
+
+    Absent third-party packages are replaced by the minimal layer definitions the reference uses
+    from them (stated here because they are OUR statement of third-party code, pinned versions in
+    modules/SEEM/requirements: detectron2@afe9eb9, timm 0.9.16, fvcore):
+      * detectron2.layers.Conv2d  = nn.Conv2d + optional `norm` module + optional `activation`
+        callable applied in that order (detectron2/layers/wrappers.py `Conv2d.forward`);
+      * detectron2.layers.get_norm("GN", c) = nn.GroupNorm(32, c); "" -> None;
+      * detectron2.layers.ShapeSpec = namedtuple(channels, height, width, stride);
+      * fvcore.nn.weight_init.c2_xavier_fill / c2_msra_fill: init only (weights are overwritten);
+      * timm.models.layers: trunc_normal_ (init only), to_2tuple, DropPath (identity in eval);
+      * omegaconf.DictConfig: only used in an isinstance() check of `configurable`.
+    The xdecoder package `__init__` chains (which pull the language encoder, registry side effects
+    and detectron2 structures) are skipped by pre-registering empty package modules.
+    """
+    global _seem_ready
+    if _seem_ready:
+        return
+    import collections
+
+    import torch
+    from torch import nn
+
+    class Conv2d(nn.Conv2d):
+        def __init__(self, *args, **kwargs):
+            norm = kwargs.pop("norm", None)
+            activation = kwargs.pop("activation", None)
+            super().__init__(*args, **kwargs)
+            self.norm = norm
+            self.activation = activation
+
+        def forward(self, x):
+            x = nn.functional.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+            if self.norm is not None:
+                x = self.norm(x)
+            if self.activation is not None:
+                x = self.activation(x)
+            return x
+
+    def get_norm(norm, out_channels):
+        if norm is None or norm == "":
+            return None
+        assert norm == "GN", norm
+        return nn.GroupNorm(32, out_channels)
+
+    class ShapeSpec(collections.namedtuple("_ShapeSpec", ["channels", "height", "width", "stride"])):
+        def __new__(cls, channels=None, height=None, width=None, stride=None):
+            return super().__new__(cls, channels, height, width, stride)
+
+    class DropPath(nn.Module):
+        def __init__(self, drop_prob=0.0):
+            super().__init__()
+            self.drop_prob = drop_prob
+
+        def forward(self, x):
+            assert not self.training, "oracle shim: DropPath is identity (eval only)"
+            return x
+
+    def to_2tuple(x):
+        return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+
+    def trunc_normal_(t, mean=0.0, std=1.0, a=-2.0, b=2.0):
+        return nn.init.trunc_normal_(t, mean, std, a, b)
+
+    noop = lambda *a, **k: None
+    _stub("detectron2")
+    _stub("detectron2.layers", Conv2d=Conv2d, DeformConv=None, ShapeSpec=ShapeSpec, get_norm=get_norm,
+          cat=torch.cat, shapes_to_tensor=None)
+    _stub("detectron2.utils")
+    _stub("detectron2.utils.file_io", PathManager=None)
+    _stub("detectron2.modeling", BACKBONE_REGISTRY=None, Backbone=nn.Module, ShapeSpec=ShapeSpec)
+    _stub("detectron2.structures", BitMasks=None, Boxes=None)
+    _stub("fvcore")
+    _stub("fvcore.nn")
+    _stub("fvcore.nn.weight_init", c2_xavier_fill=noop, c2_msra_fill=noop)
+    sys.modules["fvcore.nn"].weight_init = sys.modules["fvcore.nn.weight_init"]
+    _stub("timm")
+    _stub("timm.models")
+    _stub("timm.models.layers", trunc_normal_=trunc_normal_, to_2tuple=to_2tuple, DropPath=DropPath)
+    _stub("omegaconf", DictConfig=type("DictConfig", (), {}))
+
+    base = os.path.join(REF, "modules/SEEM/demo_code/xdecoder")
+    rel = "modules/SEEM/demo_code/xdecoder"
+    _pkg("xdecoder", base)
+    cfgmod = load_file("xdecoder.utils.config", rel + "/utils/config.py")
+    u = _pkg("xdecoder.utils", os.path.join(base, "utils"))
+    u.configurable = cfgmod.configurable
+    pe = load_file("xdecoder.modules.position_encoding", rel + "/modules/position_encoding.py")
+    pf = load_file("xdecoder.modules.point_features", rel + "/modules/point_features.py")
+    m = _pkg("xdecoder.modules", os.path.join(base, "modules"))
+    m.PositionEmbeddingSine = pe.PositionEmbeddingSine
+    m.point_features = pf
+    _pkg("xdecoder.body", os.path.join(base, "body"))
+    _pkg("xdecoder.body.decoder", os.path.join(base, "body/decoder"))
+    _pkg("xdecoder.body.encoder", os.path.join(base, "body/encoder"))
+    _pkg("xdecoder.backbone", os.path.join(base, "backbone"))
+    _seem_ready = True
+
+
+def seem_classes():
+    """(TransformerEncoderPixelDecoder, MultiScaleMaskedTransformerDecoder, ShapeSpec) — unmodified."""
+    setup_seem()
+    enc = importlib.import_module("xdecoder.body.encoder.transformer_encoder_fpn")
+    dec = importlib.import_module("xdecoder.body.decoder.seem")
+    return enc.TransformerEncoderPixelDecoder, dec.MultiScaleMaskedTransformerDecoder, sys.modules["detectron2.layers"].ShapeSpec
+
+
+def seem_focalnet_class():
+    setup_seem()
+    return importlib.import_module("xdecoder.backbone.focal").FocalNet

@@ -9,11 +9,13 @@ body/decoder/utils/attention_data_struct.py:173-187,250-264, body/decoder/utils/
 (bool mask -> -inf, softmax(...).nan_to_num()), modules/position_encoding.py:18-52,
 language/vlpencoder.py:293-299.
 
-Parity status: the full SEEM classes cannot be imported here (detectron2 / fvcore / timm are absent),
-so this restatement is pinned PIECEWISE against the importable reference files —
-multi_head_attention_forward, PositionEmbeddingSine, prepare_features, AttentionDataStruct's
-mask rule (tests/test_oracle_cpu.py::test_seem_*) — and is otherwise "parity unpinned" at the
-whole-module level (stated in DESIGN.md).
+Parity status: PINNED at module level. The unmodified reference classes TransformerEncoderPixelDecoder and
+MultiScaleMaskedTransformerDecoder are imported through oracle/refshim.setup_seem (which states the few
+detectron2 / fvcore / timm layer definitions they use, absent from this image) and this restatement
+reproduces their outputs to 3e-4: tests/golden/seem_tiny.pt (oracle/gen_golden.py::gen_seem) and a live
+comparison on a second configuration (tests/test_oracle_cpu.py::test_seem_restatement_matches_*), in
+addition to the piecewise pins of multi_head_attention_forward, PositionEmbeddingSine, prepare_features
+and AttentionDataStruct's mask rule.
 """
 import math
 

@@ -215,3 +215,55 @@ def test_seem_restatement_runs_and_is_self_consistent():
     out = S.mask_decoder_forward(sd, multi, mf, "predictor.", heads=2, num_layers=3, t_emb=torch.randn(5, 32), logit_scale=1.0)
     assert out["pred_logits"].shape == (1, 7, 5) and out["pred_masks"].shape == (1, 7, 32, 48)
     assert len(out["aux_outputs"]) == 3 and out["pred_maskembs"].shape == (1, 7, 64)
+
+
+def _seem_restated(fx, sd, feats, t_emb):
+    from oracle import restate_seem as S
+    t = fx["cfg"]
+    mf, enc, multi = S.pixel_decoder_forward(sd, feats, "pixel_decoder.", nheads=t["heads"], enc_layers=t["enc_layers"])
+    out = S.mask_decoder_forward(sd, multi, mf, "predictor.", heads=t["heads"], num_layers=t["dec_layers"], t_emb=t_emb,
+                                 logit_scale=t["logit_scale"])
+    return mf, enc, multi, out
+
+
+def _seem_compare(mf, enc, multi, out, ref_mf, ref_enc, ref_multi, ref_out, atol=3e-4):
+    assert torch.allclose(mf, ref_mf, atol=atol, rtol=1e-4)
+    assert torch.allclose(enc, ref_enc, atol=atol, rtol=1e-4)
+    for a, b in zip(multi, ref_multi):
+        assert torch.allclose(a, b, atol=atol, rtol=1e-4)
+    for k in ("pred_logits", "pred_masks", "pred_maskembs"):
+        assert torch.allclose(out[k], ref_out[k], atol=atol, rtol=1e-4), k
+        for a, b in zip(out["aux_outputs"], ref_out["aux_outputs"]):
+            assert torch.allclose(a[k], b[k], atol=atol, rtol=1e-4), ("aux", k)
+
+
+def test_seem_restatement_matches_reference_golden():
+    """Module-level pin of rows a10 + a11: the restatement reproduces what the UNMODIFIED reference classes
+    TransformerEncoderPixelDecoder.forward_features + MultiScaleMaskedTransformerDecoder.forward(task='seg')
+    computed (oracle/gen_golden.py::gen_seem, detectron2-layer stubs stated in refshim.setup_seem)."""
+    fx = load("seem_tiny.pt")
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    mf, enc, multi, out = _seem_restated(fx, sd, fx["features"], fx["t_emb"])
+    assert fx["out_keys"] == ["aux_outputs", "pred_logits", "pred_maskembs", "pred_masks"]
+    assert len(out["aux_outputs"]) == len(fx["out"]["aux_outputs"]) == fx["cfg"]["dec_layers"]
+    _seem_compare(mf, enc, multi, out, fx["mask_features"], fx["enc_features"], fx["multi_scale"], fx["out"])
+
+
+def test_seem_restatement_matches_live_reference():
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    from oracle import gen_golden as G
+    t = dict(G.SEEM_TINY, C=96, ffn=160, Q=11, enc_layers=1, dec_layers=4, heads=3, in_channels=(16, 24, 40, 56))
+    pd, md, sd, shapes = G.build_reference_seem(t, seed=77)
+    g = torch.Generator().manual_seed(3)
+    sizes = [(36, 28), (18, 14), (9, 7), (5, 4)]  # odd FPN chain: nearest-upsample to the lateral's size
+    feats = {f"res{i + 2}": torch.randn((2, c, *sizes[i]), generator=g) for i, c in enumerate(t["in_channels"])}
+    t_emb = torch.randn((t["n_text"], t["dim_proj"]), generator=g)
+    md.lang_encoder.default_text_embeddings.copy_(t_emb)
+    with torch.no_grad():
+        r_mf, r_enc, r_multi = pd.forward_features(feats)
+        r_out = md(r_multi, r_mf, task="seg", extra={})
+    fx = {"cfg": t}
+    mf, enc, multi, out = _seem_restated(fx, sd, feats, t_emb)
+    _seem_compare(mf, enc, multi, out, r_mf, r_enc, r_multi, r_out)

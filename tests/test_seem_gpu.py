@@ -1,6 +1,7 @@
 """GPU parity for SURVEY.md §8 rows a10 (SEEM pixel decoder) and a11 (SEEM mask decoder), task 'seg':
-CUDA path vs the CPU oracle restatement (the full reference classes need detectron2, absent here —
-the restatement is pinned piecewise, tests/test_oracle_cpu.py). Float outputs: <= 5% inf / 4% L2;
+CUDA path vs the CPU oracle restatement (pinned at module level against the unmodified reference classes,
+tests/test_oracle_cpu.py::test_seem_restatement_matches_*) and vs the reference's own golden outputs
+(tests/golden/seem_tiny.pt). Float outputs: <= 5% inf / 4% L2;
 bool attention masks: identical except where the oracle's mask logit is within the float tolerance
 of the 0 threshold (mask-pixel decisions are bit-exact away from that band)."""
 import pytest
@@ -106,3 +107,28 @@ def test_seem_end_to_end_head(cuda):
     assert_close(out["pred_masks"], ref["pred_masks"], "e2e pred_masks", 0.12, 0.1)
     with pytest.raises(NotImplementedError):
         head({k: v.to(cuda) for k, v in feats.items()}, extra={"grounding_tokens": None})
+
+
+def test_seem_vs_reference_golden(cuda):
+    """Product path against outputs of the UNMODIFIED reference classes (tests/golden/seem_tiny.pt)."""
+    import os
+    from oracle.weights import seeded_state_dict
+    from vitron_b200.seem import MultiScaleMaskedTransformerDecoder, TransformerEncoderPixelDecoder, XDecoderHead
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "seem_tiny.pt"), weights_only=False)
+    t = fx["cfg"]
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    pd = TransformerEncoderPixelDecoder(t["in_channels"], t["C"], t["C"], t["heads"], t["ffn"], t["enc_layers"], device=cuda)
+    pr = MultiScaleMaskedTransformerDecoder(t["C"], t["dim_proj"], t["Q"], t["heads"], t["ffn"], t["dec_layers"], t["C"], device=cuda)
+    head = XDecoderHead(pd, pr).load_state_dict(sd)
+    head.predictor.set_text_embeddings(fx["t_emb"], t["logit_scale"])
+    mf, enc, multi = head.pixel_decoder.forward_features({k: v.to(cuda) for k, v in fx["features"].items()})
+    assert_close(enc, fx["enc_features"], "golden transformer encoder features")
+    for a, b in zip(multi, fx["multi_scale"]):
+        assert_close(a, b, "golden multi-scale feature")
+    assert_close(mf, fx["mask_features"], "golden mask_features")
+    out = head.predictor([m.to(cuda) for m in fx["multi_scale"]], fx["mask_features"].to(cuda))
+    ref = fx["out"]
+    assert_close(out["aux_outputs"][0]["pred_masks"], ref["aux_outputs"][0]["pred_masks"], "golden layer-0 mask logits", 0.03, 0.03)
+    assert_close(out["aux_outputs"][0]["pred_logits"], ref["aux_outputs"][0]["pred_logits"], "golden layer-0 class logits", 0.03, 0.03)
+    assert_close(out["pred_masks"], ref["pred_masks"], "golden pred_masks", 0.3, 0.08)
+    assert_close(out["pred_maskembs"], ref["pred_maskembs"], "golden pred_maskembs", 0.3, 0.08)
