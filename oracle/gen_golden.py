@@ -207,7 +207,40 @@ def gen_seem(seed=41):
           len(out["aux_outputs"]), sorted(out.keys()))
 
 
-GENERATORS = {"vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen, "seem": gen_seem}
+FOCAL_TINY = dict(embed_dim=64, depths=(1, 1, 2, 1), focal_levels=(4, 4, 4, 4), focal_windows=(3, 3, 3, 3), mlp_ratio=4.0,
+                  patch_size=4, use_conv_embed=True, use_postln=True, use_postln_in_modulation=False,
+                  scaling_modulator=True, use_layerscale=True, patch_norm=True, out_indices=(0, 1, 2, 3))
+
+
+def build_reference_focalnet(cfg, seed):
+    """The UNMODIFIED FocalNet (backbone/focal.py:340-590) in eval mode with seeded weights (layerscale gammas are
+    seeded at O(0.5) instead of the 1e-4 init, otherwise the blocks would not contribute)."""
+    FocalNet = refshim.seem_focalnet_class()
+    net = FocalNet(pretrain_img_size=224, patch_size=cfg["patch_size"], in_chans=3, embed_dim=cfg["embed_dim"],
+                   depths=list(cfg["depths"]), mlp_ratio=cfg["mlp_ratio"], drop_rate=0.0, drop_path_rate=0.3,
+                   patch_norm=cfg["patch_norm"], out_indices=list(cfg["out_indices"]), focal_levels=list(cfg["focal_levels"]),
+                   focal_windows=list(cfg["focal_windows"]), use_conv_embed=cfg["use_conv_embed"], use_postln=cfg["use_postln"],
+                   use_postln_in_modulation=cfg["use_postln_in_modulation"], scaling_modulator=cfg["scaling_modulator"],
+                   use_layerscale=cfg["use_layerscale"])
+    net.eval()  # FocalNet.train() returns None (focal.py:592-595), so no chaining
+    shapes = shapes_of(net)
+    sd = seeded_state_dict(shapes, seed)
+    net.load_state_dict(sd)
+    return net, sd, shapes
+
+
+def gen_focal(seed=51):
+    """FocalNet backbone (SEEM's FocalNet-L block structure at tiny widths) from the unmodified reference class."""
+    net, sd, shapes = build_reference_focalnet(FOCAL_TINY, seed)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((1, 3, 64, 96), generator=g)
+    with torch.no_grad():
+        outs = net(x)
+    torch.save(dict(seed=seed, cfg=dict(FOCAL_TINY), shapes=shapes, x=x, outs=outs), os.path.join(OUT, "focal_tiny.pt"))
+    print("focal_tiny.pt", {k: (tuple(v.shape), round(float(v.abs().max()), 3)) for k, v in outs.items()})
+
+
+GENERATORS = {"vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen, "seem": gen_seem, "focal": gen_focal}
 
 
 def main(argv):

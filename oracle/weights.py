@@ -29,7 +29,7 @@ def seeded_tensor(name, shape, seed, gain=0.8):
         return 0.05 * torch.randn(shape, generator=g)
     n = name.lower()
     if any(k in n for k in ("embed_tokens", "position_embedding", "class_embedding", "temporal_embedding",
-                            "query_feat", "query_embed", "level_embed")):
+                            "query_feat", "query_embed", "level_embed", "gamma_")):
         return 0.5 * torch.randn(shape, generator=g)  # lookup tables / learned tokens, not projections
     fan_in = 1
     for s in shape[1:]:

@@ -267,3 +267,31 @@ def test_seem_restatement_matches_live_reference():
     fx = {"cfg": t}
     mf, enc, multi, out = _seem_restated(fx, sd, feats, t_emb)
     _seem_compare(mf, enc, multi, out, r_mf, r_enc, r_multi, r_out)
+
+
+def test_focal_restatement_matches_reference_golden():
+    """§8(f1) FocalNet backbone: restatement == outputs of the unmodified reference class (golden)."""
+    from oracle import restate_focal as FR
+    fx = load("focal_tiny.pt")
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    outs = FR.focalnet_forward(sd, fx["x"], fx["cfg"])
+    assert sorted(outs) == sorted(fx["outs"]) == ["res2", "res3", "res4", "res5"]
+    for k, v in fx["outs"].items():
+        assert outs[k].shape == v.shape
+        assert torch.allclose(outs[k], v, atol=2e-4, rtol=1e-4), k
+
+
+def test_focal_restatement_matches_live_reference():
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    from oracle import gen_golden as G, restate_focal as FR
+    cfg = dict(G.FOCAL_TINY, embed_dim=48, depths=(1, 2, 1, 1), focal_levels=(3, 2, 4, 1), focal_windows=(5, 3, 3, 7),
+               scaling_modulator=False, use_postln=False, use_postln_in_modulation=True)
+    net, sd, _ = G.build_reference_focalnet(cfg, seed=88)
+    x = torch.randn((2, 3, 62, 90), generator=torch.Generator().manual_seed(4))  # exercises the pad-to-patch path
+    with torch.no_grad():
+        ref = net(x)
+    outs = FR.focalnet_forward(sd, x, cfg)
+    for k, v in ref.items():
+        assert torch.allclose(outs[k], v, atol=2e-4, rtol=1e-4), k
