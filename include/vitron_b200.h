@@ -213,6 +213,39 @@ int vb200_region_mask_pool(const void* feats, const float* boxes, void* out, int
 int vb200_seem_attn_mask(const float* mask_logits, uint8_t* out_mask, int64_t Q, int64_t H,
                          int64_t W, int64_t h2, int64_t w2, cudaStream_t stream);
 
+/* ---- FocalNet backbone glue (focal.cu) — SEEM backbone, SURVEY.md §8(f1) -------------------------
+ * reference: modules/SEEM/demo_code/xdecoder/backbone/focal.py */
+#define VB_FOCAL_MAX_LEVELS 6
+/* stem PatchEmbed Conv2d(c, C, k, stride, pad) as im2col rows for vb200_gemm_bf16 (focal.py:311-338): NCHW
+ * pixels (fp32 or bf16) -> [nb*ho*wo, kpad] bf16, columns ordered (c, ky, kx) like weight.reshape(C, -1), zero
+ * beyond c*k*k and outside the image (this also realises the pad-to-multiple-of-patch of :325-328). */
+int vb200_im2col_nchw(const void* pixels, int in_is_fp32, void* out, int64_t nb, int64_t c, int64_t h,
+                      int64_t w, int64_t k, int64_t stride, int64_t pad, int64_t ho, int64_t wo,
+                      int64_t kpad, cudaStream_t stream);
+/* depthwise Conv2d(c, c, k, padding=k/2, groups=c, bias=False) [+ GELU] on NHWC bf16 (focal.py:80-89,105).
+ * x: [nb, h, w, ld_in] view (first c channels of every pixel row), wt: [k*k, c] tap-major, out: [nb, h, w, c].
+ * k in {3, 5, 7, 9, 11}; act = VB_ACT_NONE | VB_ACT_GELU. */
+int vb200_dwconv_nhwc(const void* x, int64_t ld_in, const void* wt, void* out, int64_t nb, int64_t h,
+                      int64_t w, int64_t c, int64_t k, int act, cudaStream_t stream);
+/* out[b, ch] = act(mean over the t rows of x[b]) in fp32, x [nb, t, c] bf16 (ctx.mean(2).mean(3) + GELU,
+ * focal.py:107); deterministic two-stage reduction through the workspace. */
+size_t vb200_colmean_workspace_size(int64_t nb, int64_t t, int64_t c);
+int vb200_colmean(const void* x, float* out, int64_t nb, int64_t t, int64_t c, int act, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream);
+/* ctx_all = scale * (sum_l ctx_l * gates[:, l] + glob * gates[:, nlev]) (focal.py:103-111): ctx_levels = nlev
+ * device pointers to [nb*t, c] bf16, gates = bf16 view with row stride ld_g, glob fp32 [nb, c]. */
+int vb200_focal_modulate(const void* const* ctx_levels, int64_t nlev, const void* gates, int64_t ld_g,
+                         const float* glob, void* out, int64_t nb, int64_t t, int64_t c, float scale,
+                         cudaStream_t stream);
+/* out[rows, c] = a (row stride ld_a) * b (row stride ld_b): x_out = q * h(ctx_all) (focal.py:113) */
+int vb200_mul_rows(const void* a, int64_t ld_a, const void* b, int64_t ld_b, void* out, int64_t rows,
+                   int64_t c, cudaStream_t stream);
+/* out = residual + LayerNorm(x) * weight + bias (residual / bias may be NULL), d <= 2048: the post-LN +
+ * layerscale residual of FocalModulationBlock (focal.py:190-199; gamma folded into weight / bias by the host) */
+int vb200_layernorm_add(const void* x, int64_t ldx, const void* weight, const void* bias, const void* residual,
+                        int64_t ldr, void* out, int64_t ldo, int64_t rows, int64_t d, float eps,
+                        cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

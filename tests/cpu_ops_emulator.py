@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE ONLY — torch (CPU) statements of the vitron_b200.ops entry points used by the host-side
+modules, so that their HOST LOGIC (weight folding / packing, view slicing, call order, shapes) can be checked
+without a GPU (`-m "not gpu"`). Never imported by the product: tests install it with monkeypatch over
+`vitron_b200.ops`; the kernels themselves are checked on the GPU against the oracle (tests/*_gpu.py).
+Each function mirrors the contract in vitron_b200/ops.py: bf16 storage, fp32 arithmetic."""
+import torch
+import torch.nn.functional as F
+
+BF16 = torch.bfloat16
+ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_RELU, ACT_SILU = 0, 1, 2, 3, 4
+
+
+def _act(x, act):
+    return {ACT_NONE: lambda t: t, ACT_GELU: F.gelu, ACT_QUICK_GELU: lambda t: t * torch.sigmoid(1.702 * t),
+            ACT_RELU: F.relu, ACT_SILU: F.silu}[int(act)](x)
+
+
+def gemm(a, w, bias=None, act=ACT_NONE, glu=0, residual=None, alpha=1.0, out=None, out_fp32=False, **kw):
+    assert glu == 0 and not kw.get("rowbias") and not kw.get("rowscale") and not kw.get("rms_eps")
+    assert a.dtype == BF16 and w.dtype == BF16 and a.shape[-1] == w.shape[1]
+    v = a.float().reshape(-1, a.shape[-1]) @ w.float().t()
+    if bias is not None:
+        v = v + bias.float()
+    v = _act(v, act) * alpha
+    if residual is not None:
+        v = residual.float().reshape(v.shape) + v
+    v = v.reshape(*a.shape[:-1], w.shape[0]).to(torch.float32 if out_fp32 else BF16)
+    if out is not None:
+        out.copy_(v.reshape(out.shape))
+        return out
+    return v
+
+
+def layernorm(x, weight, bias, eps, out=None):
+    v = F.layer_norm(x.float(), (x.shape[-1],), weight.float(), None if bias is None else bias.float(), eps).to(BF16)
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v
+
+
+def layernorm_add(x, weight, bias, residual, eps, out=None):
+    v = F.layer_norm(x.float(), (x.shape[-1],), weight.float(), None if bias is None else bias.float(), eps)
+    if residual is not None:
+        v = v + residual.float()
+    v = v.to(BF16)
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v
+
+
+def pack_dwconv_weight(w):
+    c, one, kh, kw = w.shape
+    return w.reshape(c, kh * kw).t().to(BF16).contiguous()
+
+
+def dwconv_nhwc(x, wt, k, act=ACT_NONE):
+    nb, h, w, c = x.shape
+    assert x.stride(3) == 1 and x.stride(1) == w * x.stride(2) and x.stride(0) == h * w * x.stride(2)
+    assert wt.shape == (k * k, c)
+    wc = wt.float().t().reshape(c, 1, k, k)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wc, None, padding=k // 2, groups=c)
+    return _act(y, act).permute(0, 2, 3, 1).to(BF16).contiguous()
+
+
+def colmean(x, nb, act=ACT_NONE):
+    c = x.shape[-1]
+    return _act(x.float().reshape(nb, -1, c).mean(1), act)
+
+
+def focal_modulate(levels, gates, glob, nb, scale):
+    c = levels[0].shape[-1]
+    t = levels[0].numel() // (nb * c)
+    g = gates.float().reshape(nb * t, -1)
+    v = glob.repeat_interleave(t, 0) * g[:, len(levels):len(levels) + 1]
+    for l, lv in enumerate(levels):
+        v = v + lv.float().reshape(nb * t, c) * g[:, l:l + 1]
+    return (v * scale).to(BF16)
+
+
+def mul_rows(a, b):
+    return (a.float() * b.float()).to(BF16)
+
+
+def im2col_nchw(pixels, k, stride, pad, ho, wo, kpad):
+    nb, c, h, w = pixels.shape
+    hp, wp = (ho - 1) * stride + k - 2 * pad, (wo - 1) * stride + k - 2 * pad  # extent the output grid reads
+    xp = F.pad(pixels.float(), (0, max(0, wp - w), 0, max(0, hp - h)))
+    cols = F.unfold(xp, k, padding=pad, stride=stride).transpose(1, 2)[:, :ho * wo].reshape(nb * ho * wo, c * k * k)
+    out = torch.zeros((nb * ho * wo, kpad), dtype=BF16)
+    out[:, :c * k * k] = cols.to(BF16)
+    return out
+
+
+def pack_conv_weight(w):
+    if w.dim() == 5:
+        w = w[:, :, :, 0, 0].unsqueeze(-1)
+    cout, cin, kh, kw = w.shape
+    cpad = (cin + 63) // 64 * 64
+    out = torch.zeros((cout, kh * kw, cpad), dtype=BF16)
+    out[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).to(BF16)
+    return out
+
+
+def conv_nhwc(x, wt, kh, kw, stride=1, pad_h=None, pad_w=None, bias=None, act=ACT_NONE, residual=None, alpha=1.0, **kw_):
+    nb, h, w, cin = x.shape
+    cout = wt.shape[0]
+    pad_h = kh // 2 if pad_h is None else pad_h
+    pad_w = kw // 2 if pad_w is None else pad_w
+    wc = wt.float()[:, :, :cin].reshape(cout, kh, kw, cin).permute(0, 3, 1, 2)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wc, None if bias is None else bias.float(), stride=stride,
+                 padding=(pad_h, pad_w))
+    y = _act(y, act).permute(0, 2, 3, 1) * alpha
+    if residual is not None:
+        y = residual.float() + y
+    return y.to(BF16).contiguous()
+
+
+def install(monkeypatch):
+    """Replace the kernel-launching entry points of vitron_b200.ops with the statements above."""
+    from vitron_b200 import ops
+    for name in ("gemm", "layernorm", "layernorm_add", "pack_dwconv_weight", "dwconv_nhwc", "colmean", "focal_modulate",
+                 "mul_rows", "im2col_nchw", "pack_conv_weight", "conv_nhwc"):
+        monkeypatch.setattr(ops, name, globals()[name])

@@ -107,3 +107,65 @@ def test_host_splice_layout_matches_oracle():
     assert lens == [9, 10, 10] and src.shape[1] == 10
     with pytest.raises(ValueError):
         layout_multimodal(torch.tensor([[1, -300, 2]]), torch.ones((1, 3), dtype=torch.bool), torch.zeros((1, 3), dtype=torch.long), [4], None, None, False)
+
+
+def test_focalnet_shape_table_matches_reference_names():
+    """vitron_b200.param_shapes.focalnet_shapes == state-dict names / shapes of the unmodified reference class
+    (recorded in tests/golden/focal_tiny.pt by oracle/gen_golden.py)."""
+    import os
+    import torch
+    from vitron_b200 import param_shapes
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "focal_tiny.pt"), weights_only=False)
+    assert param_shapes.focalnet_shapes(fx["cfg"]) == fx["shapes"]
+
+
+def _rel(got, ref):
+    got, ref = got.float(), ref.float()
+    return ((got - ref).abs().max() / (ref.abs().max() + 1e-6)).item(), ((got - ref).norm() / (ref.norm() + 1e-6)).item()
+
+
+def test_focalnet_host_logic_against_reference_golden(monkeypatch):
+    """Host side of vitron_b200.focal.FocalNet (weight folding / padding, in-place column slices, call order) with
+    the kernels replaced by their torch statements (tests/cpu_ops_emulator.py): must reproduce the unmodified
+    reference's golden outputs to bf16 accuracy. The kernels proper are checked on the GPU (test_zfocal_gpu.py)."""
+    import os
+    import torch
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200.focal import FocalNet
+    cpu_ops_emulator.install(monkeypatch)
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "focal_tiny.pt"), weights_only=False)
+    c = fx["cfg"]
+    net = FocalNet(patch_size=c["patch_size"], embed_dim=c["embed_dim"], depths=c["depths"], mlp_ratio=c["mlp_ratio"],
+                   patch_norm=c["patch_norm"], out_indices=c["out_indices"], focal_levels=c["focal_levels"],
+                   focal_windows=c["focal_windows"], use_conv_embed=True, use_postln=c["use_postln"],
+                   use_postln_in_modulation=c["use_postln_in_modulation"], scaling_modulator=c["scaling_modulator"],
+                   use_layerscale=c["use_layerscale"], device="cpu")
+    net.load_state_dict(seeded_state_dict(fx["shapes"], fx["seed"]))
+    outs = net(fx["x"])
+    for k, ref in fx["outs"].items():
+        assert tuple(outs[k].shape) == tuple(ref.shape)
+        e_inf, e_l2 = _rel(outs[k], ref)
+        assert e_inf < 0.04 and e_l2 < 0.03, (k, e_inf, e_l2)
+
+
+def test_focalnet_host_logic_preln_and_ragged(monkeypatch):
+    import torch
+    from oracle import restate_focal as FR
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200 import param_shapes
+    from vitron_b200.focal import FocalNet
+    cpu_ops_emulator.install(monkeypatch)
+    cfg = dict(FR.FOCAL_L, embed_dim=64, depths=(1, 1, 1, 1), use_postln=False, use_postln_in_modulation=True,
+               scaling_modulator=False, focal_levels=(3, 2, 2, 1), focal_windows=(5, 3, 7, 3))
+    sd = seeded_state_dict(param_shapes.focalnet_shapes(cfg), 7)
+    x = torch.randn((2, 3, 62, 90), generator=torch.Generator().manual_seed(2))
+    ref = FR.focalnet_forward(sd, x, cfg)
+    net = FocalNet(embed_dim=64, depths=cfg["depths"], focal_levels=cfg["focal_levels"], focal_windows=cfg["focal_windows"],
+                   use_conv_embed=True, use_postln=False, use_postln_in_modulation=True, scaling_modulator=False,
+                   use_layerscale=True, device="cpu").load_state_dict(sd)
+    outs = net(x)
+    for k, r in ref.items():
+        e_inf, e_l2 = _rel(outs[k], r)
+        assert e_inf < 0.04 and e_l2 < 0.03, (k, e_inf, e_l2)

@@ -488,3 +488,99 @@ def seem_attn_mask(mask_logits, h2, w2):
           "vb200_seem_attn_mask")
     _launches[0] += 1
     return out
+
+
+# ---- FocalNet backbone glue (focal.cu) ---------------------------------------------------------
+
+def im2col_nchw(pixels, k, stride, pad, ho, wo, kpad):
+    """NCHW fp32/bf16 pixels -> [nb*ho*wo, kpad] bf16 rows ordered (c, ky, kx); zero outside the image."""
+    lib = _lib.load()
+    _req(pixels.is_contiguous() and pixels.dim() == 4 and pixels.dtype in (torch.float32, BF16), "pixels: contiguous NCHW fp32/bf16")
+    nb, c, h, w = pixels.shape
+    out = torch.empty((nb * ho * wo, kpad), dtype=BF16, device=pixels.device)
+    check(lib.vb200_im2col_nchw(pixels.data_ptr(), 1 if pixels.dtype == torch.float32 else 0, out.data_ptr(), nb, c, h, w,
+                                k, stride, pad, ho, wo, kpad, _stream()), "vb200_im2col_nchw")
+    _launches[0] += 1
+    return out
+
+
+def pack_dwconv_weight(w):
+    """[c, 1, k, k] (torch depthwise Conv2d) -> [k*k, c] bf16 tap-major."""
+    c, one, kh, kw = w.shape
+    _req(one == 1 and kh == kw, "depthwise square kernel expected")
+    return w.reshape(c, kh * kw).t().to(BF16).contiguous()
+
+
+def dwconv_nhwc(x, wt, k, act=ACT_NONE):
+    """x: [nb, h, w, c] bf16, either contiguous or a channel slice of a contiguous [nb, h, w, ld] tensor."""
+    lib = _lib.load()
+    nb, h, w, c = x.shape
+    ld = x.stride(2)
+    _req(x.dtype == BF16 and x.stride(3) == 1 and x.stride(1) == w * ld and x.stride(0) == h * w * ld, "x must be a channel slice of an NHWC tensor")
+    _req(wt.shape == (k * k, c) and wt.is_contiguous() and wt.dtype == BF16, "weight must be [k*k, c] bf16")
+    out = torch.empty((nb, h, w, c), dtype=BF16, device=x.device)
+    check(lib.vb200_dwconv_nhwc(x.data_ptr(), ld, wt.data_ptr(), out.data_ptr(), nb, h, w, c, k, int(act), _stream()),
+          "vb200_dwconv_nhwc")
+    _launches[0] += 1
+    return out
+
+
+def colmean(x, nb, act=ACT_NONE):
+    """x [nb*t, c] (or [nb, ..., c]) contiguous bf16 -> fp32 [nb, c] = act(mean over the t rows of each batch)."""
+    lib = _lib.load()
+    _req(x.is_contiguous() and x.dtype == BF16, "x must be contiguous bf16")
+    c = x.shape[-1]
+    t = x.numel() // (nb * c)
+    out = torch.empty((nb, c), dtype=torch.float32, device=x.device)
+    need = lib.vb200_colmean_workspace_size(nb, t, c)
+    ws = workspace(need, x.device, "colmean")
+    check(lib.vb200_colmean(x.data_ptr(), out.data_ptr(), nb, t, c, int(act), ws.data_ptr(), need, _stream()), "vb200_colmean")
+    _launches[0] += 2
+    return out
+
+
+def focal_modulate(levels, gates, glob, nb, scale):
+    """levels: list of contiguous [nb*t, c] bf16; gates: bf16 column slice [nb*t, >= len(levels)+1]; glob fp32 [nb, c]."""
+    lib = _lib.load()
+    c = levels[0].shape[-1]
+    t = levels[0].numel() // (nb * c)
+    for l in levels:
+        _req(l.is_contiguous() and l.dtype == BF16 and l.numel() == nb * t * c, "bad ctx level")
+    _req(gates.dtype == BF16 and gates.stride(-1) == 1 and gates.shape[-1] >= len(levels) + 1, "bad gates")
+    _req(glob.dtype == torch.float32 and glob.is_contiguous() and glob.shape == (nb, c), "bad glob")
+    g2 = gates.reshape(-1, gates.shape[-1]) if gates.dim() != 2 else gates
+    ptrs = (C.c_void_p * len(levels))(*[l.data_ptr() for l in levels])
+    out = torch.empty((nb * t, c), dtype=BF16, device=glob.device)
+    check(lib.vb200_focal_modulate(ptrs, len(levels), g2.data_ptr(), g2.stride(0), glob.data_ptr(), out.data_ptr(), nb, t, c,
+                                   float(scale), _stream()), "vb200_focal_modulate")
+    _launches[0] += 1
+    return out
+
+
+def mul_rows(a, b):
+    """a [rows, c] (row-strided view), b [rows, c] -> a * b, contiguous bf16."""
+    lib = _lib.load()
+    _req(a.dim() == 2 and b.dim() == 2 and a.shape == b.shape and a.stride(1) == 1 and b.stride(1) == 1, "2-D operands")
+    out = torch.empty(a.shape, dtype=BF16, device=a.device)
+    check(lib.vb200_mul_rows(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), a.shape[0], a.shape[1],
+                             _stream()), "vb200_mul_rows")
+    _launches[0] += 1
+    return out
+
+
+def layernorm_add(x, weight, bias, residual, eps, out=None):
+    """residual + LayerNorm(x) * weight + bias (residual / bias may be None); out may alias residual."""
+    lib = _lib.load()
+    x2, ldx = _rows2d(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    o2, ldo = _rows2d(out)
+    r_ptr, ldr = 0, 0
+    if residual is not None:
+        r2, ldr = _rows2d(residual)
+        _req(r2.shape == x2.shape and r2.dtype == BF16, "bad residual")
+        r_ptr = r2.data_ptr()
+    check(lib.vb200_layernorm_add(x2.data_ptr(), ldx, weight.data_ptr(), _ptr(bias), r_ptr, ldr, o2.data_ptr(), ldo,
+                                  x2.shape[0], x2.shape[1], float(eps), _stream()), "vb200_layernorm_add")
+    _launches[0] += 1
+    return out

@@ -189,6 +189,47 @@ def seem_shapes(in_channels=(192, 384, 768, 1536), conv_dim=512, ffn=2048, queri
     return s
 
 
+def focalnet_shapes(cfg):
+    """Reference FocalNet parameter names / shapes (backbone/focal.py:340-437); cfg keys as oracle.restate_focal.FOCAL_L
+    (embed_dim, depths, focal_levels, focal_windows, mlp_ratio, use_conv_embed, use_postln_in_modulation,
+    use_layerscale, patch_norm, out_indices)."""
+    s = {}
+    E = cfg["embed_dim"]
+    k = 7 if cfg["use_conv_embed"] else cfg["patch_size"]
+    s["patch_embed.proj.weight"], s["patch_embed.proj.bias"] = [E, 3, k, k], [E]
+    if cfg["patch_norm"]:
+        s["patch_embed.norm.weight"], s["patch_embed.norm.bias"] = [E], [E]
+    n = len(cfg["depths"])
+    for i in range(n):
+        C = E * 2 ** i
+        L, win = cfg["focal_levels"][i], cfg["focal_windows"][i]
+        hid = int(C * cfg["mlp_ratio"])
+        for j in range(cfg["depths"][i]):
+            p = f"layers.{i}.blocks.{j}."
+            for nm in ("norm1", "norm2"):
+                s[p + nm + ".weight"], s[p + nm + ".bias"] = [C], [C]
+            s[p + "modulation.f.weight"], s[p + "modulation.f.bias"] = [2 * C + L + 1, C], [2 * C + L + 1]
+            s[p + "modulation.h.weight"], s[p + "modulation.h.bias"] = [C, C, 1, 1], [C]
+            s[p + "modulation.proj.weight"], s[p + "modulation.proj.bias"] = [C, C], [C]
+            if cfg["use_postln_in_modulation"]:
+                s[p + "modulation.ln.weight"], s[p + "modulation.ln.bias"] = [C], [C]
+            for l in range(L):
+                kk = 2 * l + win
+                s[p + f"modulation.focal_layers.{l}.0.weight"] = [C, 1, kk, kk]
+            s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"] = [hid, C], [hid]
+            s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"] = [C, hid], [C]
+            if cfg["use_layerscale"]:
+                s[p + "gamma_1"], s[p + "gamma_2"] = [C], [C]
+        if i < n - 1:
+            p = f"layers.{i}.downsample."
+            kd = 3 if cfg["use_conv_embed"] else 2
+            s[p + "proj.weight"], s[p + "proj.bias"] = [2 * C, C, kd, kd], [2 * C]
+            s[p + "norm.weight"], s[p + "norm.bias"] = [2 * C], [2 * C]
+        if i in cfg["out_indices"]:
+            s[f"norm{i}.weight"], s[f"norm{i}.bias"] = [C], [C]
+    return s
+
+
 def random_state_dict(shapes, device, seed=0, std=0.02):
     """N(0, std) weights, unit norm gains, zero biases, generated on `device`."""
     g = torch.Generator(device=device).manual_seed(seed)
