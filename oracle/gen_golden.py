@@ -240,7 +240,32 @@ def gen_focal(seed=51):
     print("focal_tiny.pt", {k: (tuple(v.shape), round(float(v.abs().max()), 3)) for k, v in outs.items()})
 
 
-GENERATORS = {"vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen, "seem": gen_seem, "focal": gen_focal}
+VAE_TINY = dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=64, ch_mult=(1, 2, 2),
+                num_res_blocks=1, attn_resolutions=[], dropout=0.0)
+
+
+def build_reference_vae(ddconfig, seed):
+    AE = refshim.i2vgen_autoencoder_class()
+    ae = AE(ddconfig=dict(ddconfig), embed_dim=4).eval()
+    shapes = _load_seeded(ae, seed, gain=0.8)
+    return ae, seeded_state_dict(shapes, seed, 0.8), shapes
+
+
+def gen_vae(seed=61):
+    """AutoencoderKL encode (posterior moments) + decode through the unmodified reference class."""
+    ae, sd, shapes = build_reference_vae(VAE_TINY, seed)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((2, 3, 32, 48), generator=g)
+    z = torch.randn((2, 4, 8, 12), generator=g)
+    with torch.no_grad():
+        post = ae.encode(x)
+        dec = ae.decode(z)
+    torch.save(dict(seed=seed, ddconfig=dict(VAE_TINY), shapes=shapes, x=x, z=z, mean=post.mean, logvar=post.logvar,
+                    std=post.std, dec=dec), os.path.join(OUT, "vae_tiny.pt"))
+    print("vae_tiny.pt", tuple(post.mean.shape), float(post.mean.abs().max()), tuple(dec.shape), float(dec.abs().max()))
+
+
+GENERATORS = {"vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen, "seem": gen_seem, "focal": gen_focal, "vae": gen_vae}
 
 
 def main(argv):

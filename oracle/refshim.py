@@ -232,6 +232,14 @@ def i2vgen_unet_class():
     return mod.UNetSD_I2VGen
 
 
+def i2vgen_autoencoder_class():
+    """Unmodified tools/modules/autoencoder.py::AutoencoderKL (its `utils.registry_class` import resolves inside
+    modules/i2vgen-xl, which setup_i2vgen puts on sys.path)."""
+    setup_i2vgen()
+    mod = importlib.import_module("tools.modules.autoencoder")
+    return mod.AutoencoderKL
+
+
 def i2vgen_ddim_class():
     setup_i2vgen()
     base = os.path.join(REF, "modules/i2vgen-xl")

@@ -295,3 +295,33 @@ def test_focal_restatement_matches_live_reference():
     outs = FR.focalnet_forward(sd, x, cfg)
     for k, v in ref.items():
         assert torch.allclose(outs[k], v, atol=2e-4, rtol=1e-4), k
+
+
+def test_vae_restatement_matches_reference_golden():
+    """§8(f2) i2vgen first-stage AutoencoderKL: restatement == unmodified reference class (golden)."""
+    from oracle import restate_vae as V
+    fx = load("vae_tiny.pt")
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    mean, logvar, std = V.encode_moments(sd, fx["x"], fx["ddconfig"])
+    assert torch.allclose(mean, fx["mean"], atol=2e-4, rtol=1e-4)
+    assert torch.allclose(logvar, fx["logvar"], atol=2e-4, rtol=1e-4)
+    assert torch.allclose(std, fx["std"], atol=2e-4, rtol=1e-4)
+    assert torch.allclose(V.decode(sd, fx["z"], fx["ddconfig"]), fx["dec"], atol=2e-4, rtol=1e-4)
+
+
+def test_vae_restatement_matches_live_reference():
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    from oracle import gen_golden as G, restate_vae as V
+    dd = dict(G.VAE_TINY, ch=32, ch_mult=(1, 2, 4, 4), num_res_blocks=2)
+    ae, sd, _ = G.build_reference_vae(dd, seed=99)
+    g = torch.Generator().manual_seed(8)
+    x, z = torch.randn((1, 3, 40, 24), generator=g), torch.randn((1, 4, 5, 3), generator=g)
+    with torch.no_grad():
+        post, dec = ae.encode(x), ae.decode(z)
+        zz = ae.encode_firsr_stage(x, 0.18215)
+    mean, logvar, std = V.encode_moments(sd, x, dd)
+    assert torch.allclose(mean, post.mean, atol=2e-4, rtol=1e-4) and torch.allclose(std, post.std, atol=2e-4, rtol=1e-4)
+    assert torch.allclose(V.decode(sd, z, dd), dec, atol=2e-4, rtol=1e-4)
+    assert zz.shape == mean.shape  # encode_firsr_stage = scale_factor * posterior.sample(): stochastic, shape only
