@@ -213,6 +213,12 @@ int vb200_region_mask_pool(const void* feats, const float* boxes, void* out, int
 int vb200_seem_attn_mask(const float* mask_logits, uint8_t* out_mask, int64_t Q, int64_t H,
                          int64_t W, int64_t h2, int64_t w2, cudaStream_t stream);
 
+/* out = softmax over the last dim of fp32 x [rows, n] (row stride ldx) -> bf16 [rows, n] (row stride ldo): the
+ * single-head c-channel attention of the first-stage VAE's AttnBlock (i2vgen-xl tools/modules/autoencoder.py:418-442),
+ * whose QK^T and PV are vb200_gemm_bf16 calls. */
+int vb200_softmax_rows(const float* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int64_t n,
+                       cudaStream_t stream);
+
 /* ---- FocalNet backbone glue (focal.cu) — SEEM backbone, SURVEY.md §8(f1) -------------------------
  * reference: modules/SEEM/demo_code/xdecoder/backbone/focal.py */
 #define VB_FOCAL_MAX_LEVELS 6

@@ -117,9 +117,35 @@ def conv_nhwc(x, wt, kh, kw, stride=1, pad_h=None, pad_w=None, bias=None, act=AC
     return y.to(BF16).contiguous()
 
 
+def groupnorm_nhwc(x, weight, bias, groups, eps, act=ACT_NONE, n=None, out=None):
+    c = x.shape[-1]
+    n = x.shape[0] if n is None else n
+    y = F.group_norm(x.float().reshape(n, -1, c).permute(0, 2, 1), groups, weight.float(), bias.float(), eps)
+    return _act(y, act).permute(0, 2, 1).reshape(x.shape).to(BF16).contiguous()
+
+
+def conv_nhwc_direct(x, w_khwc, bias, kh, kw, stride=1, pad_h=None, pad_w=None):
+    cout, taps, cin = w_khwc.shape
+    wc = w_khwc.float().reshape(cout, kh, kw, cin).permute(0, 3, 1, 2)
+    pad_h = kh // 2 if pad_h is None else pad_h
+    pad_w = kw // 2 if pad_w is None else pad_w
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wc, None if bias is None else bias.float(), stride=stride, padding=(pad_h, pad_w))
+    return y.permute(0, 2, 3, 1).to(BF16).contiguous()
+
+
+def upsample2x_nhwc(x):
+    return x.repeat_interleave(2, 1).repeat_interleave(2, 2).contiguous()
+
+
+def softmax_rows(x, out=None):
+    assert x.dtype == torch.float32
+    return F.softmax(x, dim=-1).to(BF16)
+
+
 def install(monkeypatch):
     """Replace the kernel-launching entry points of vitron_b200.ops with the statements above."""
     from vitron_b200 import ops
     for name in ("gemm", "layernorm", "layernorm_add", "pack_dwconv_weight", "dwconv_nhwc", "colmean", "focal_modulate",
-                 "mul_rows", "im2col_nchw", "pack_conv_weight", "conv_nhwc"):
+                 "mul_rows", "im2col_nchw", "pack_conv_weight", "conv_nhwc", "groupnorm_nhwc", "conv_nhwc_direct",
+                 "upsample2x_nhwc", "softmax_rows"):
         monkeypatch.setattr(ops, name, globals()[name])

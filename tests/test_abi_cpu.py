@@ -169,3 +169,32 @@ def test_focalnet_host_logic_preln_and_ragged(monkeypatch):
     for k, r in ref.items():
         e_inf, e_l2 = _rel(outs[k], r)
         assert e_inf < 0.04 and e_l2 < 0.03, (k, e_inf, e_l2)
+
+
+def test_autoencoder_host_logic_against_reference_golden(monkeypatch):
+    """Host side of vitron_b200.autoencoder.AutoencoderKL (quant_conv folding, channel padding, transposed-V attention,
+    asymmetric downsample padding) with the kernels replaced by torch statements: reproduces the unmodified
+    reference's golden encode moments and decode output to bf16 accuracy."""
+    import os
+    import torch
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200.autoencoder import AutoencoderKL
+    cpu_ops_emulator.install(monkeypatch)
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vae_tiny.pt"), weights_only=False)
+    ae = AutoencoderKL(fx["ddconfig"], 4, device="cpu").load_state_dict(seeded_state_dict(fx["shapes"], fx["seed"], 0.8))
+    post = ae.encode(fx["x"])
+    for got, ref, what in ((post.mean, fx["mean"], "mean"), (post.std, fx["std"], "std"), (ae.decode(fx["z"]), fx["dec"], "dec")):
+        assert got.shape == ref.shape
+        e_inf, e_l2 = _rel(got, ref)
+        assert e_inf < 0.05 and e_l2 < 0.04, (what, e_inf, e_l2)
+    z = ae.encode_firsr_stage(fx["x"], 0.18215, generator=torch.Generator().manual_seed(0))
+    assert z.shape == fx["mean"].shape
+
+
+def test_vae_shape_table_matches_reference_names():
+    import os
+    import torch
+    from vitron_b200 import param_shapes
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vae_tiny.pt"), weights_only=False)
+    assert param_shapes.vae_shapes(fx["ddconfig"]) == fx["shapes"]

@@ -220,9 +220,54 @@ __global__ void conv_direct_kernel(const bf16* __restrict__ x, const bf16* __res
   out[idx] = __float2bfloat16(acc);
 }
 
+// ------------------------------------------------------------------ row softmax (VAE AttnBlock)
+// out[row, :] = softmax(x[row, :]) ; x fp32 [rows, ldx], out bf16 [rows, ldo]; one CTA per row, online
+// max/sum in one read, second read (L1/L2 resident) writes the probabilities.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ out,
+                                                           long long ldo, int n) {
+  __shared__ float sm[8], ss[8];
+  const float* xr = x + blockIdx.x * ldx;
+  bf16* orow = out + blockIdx.x * ldo;
+  float m = -INFINITY, s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float v = xr[i];
+    const float mn = fmaxf(m, v);
+    s = s * __expf(m - mn) + __expf(v - mn);
+    m = mn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, m, o), so = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, mo);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (mo == -INFINITY ? 0.f : so * __expf(mo - mn));
+    m = mn;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sm[warp] = m; ss[warp] = s; }
+  __syncthreads();
+  float gm = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) gm = fmaxf(gm, sm[w]);
+  float gs = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) gs += sm[w] == -INFINITY ? 0.f : ss[w] * __expf(sm[w] - gm);
+  const float inv = 1.0f / gs;
+  for (int i = threadIdx.x; i < n; i += 256) orow[i] = __float2bfloat16(__expf(xr[i] - gm) * inv);
+}
+
 }  // namespace vb
 
 using namespace vb;
+
+extern "C" int vb200_softmax_rows(const float* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int64_t n,
+                                  cudaStream_t stream) {
+  VB_CHECK_ARG(x && out && rows >= 0 && n > 0 && ldx >= n && ldo >= n && n < (1ll << 31));
+  if (rows == 0) return VB_OK;
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, ldx, reinterpret_cast<bf16*>(out), ldo,
+                                                                       static_cast<int>(n));
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
 
 extern "C" int vb200_patchify(const void* pixels, int in_is_fp32, void* out, int64_t nb, int64_t c, int64_t h,
                               int64_t w, int64_t patch, int64_t kpad, cudaStream_t stream) {

@@ -584,3 +584,15 @@ def layernorm_add(x, weight, bias, residual, eps, out=None):
                                   x2.shape[0], x2.shape[1], float(eps), _stream()), "vb200_layernorm_add")
     _launches[0] += 1
     return out
+
+
+def softmax_rows(x, out=None):
+    """fp32 [rows, n] -> bf16 softmax over the last dim."""
+    lib = _lib.load()
+    _req(x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1, "x must be fp32 [rows, n]")
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(lib.vb200_softmax_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1], _stream()),
+          "vb200_softmax_rows")
+    _launches[0] += 1
+    return out

@@ -230,6 +230,57 @@ def focalnet_shapes(cfg):
     return s
 
 
+def vae_shapes(dd, embed_dim=4):
+    """Reference AutoencoderKL parameter names / shapes (i2vgen-xl tools/modules/autoencoder.py:31-62, 483-651)."""
+    s = {}
+    ch, mult, nrb, z = dd["ch"], tuple(dd["ch_mult"]), dd["num_res_blocks"], dd["z_channels"]
+
+    def conv(p, cout, cin, k):
+        s[p + "weight"], s[p + "bias"] = [cout, cin, k, k], [cout]
+
+    def norm(p, c):
+        s[p + "weight"], s[p + "bias"] = [c], [c]
+
+    def res(p, cin, cout):
+        norm(p + "norm1.", cin); conv(p + "conv1.", cout, cin, 3); norm(p + "norm2.", cout); conv(p + "conv2.", cout, cout, 3)
+        if cin != cout:
+            conv(p + "nin_shortcut.", cout, cin, 1)
+
+    def attn(p, c):
+        norm(p + "norm.", c)
+        for n in ("q.", "k.", "v.", "proj_out."):
+            conv(p + n, c, c, 1)
+
+    conv("encoder.conv_in.", ch, dd["in_channels"], 3)
+    in_mult = (1,) + mult
+    block_in = ch
+    for i in range(len(mult)):
+        block_in, block_out = ch * in_mult[i], ch * mult[i]
+        for j in range(nrb):
+            res(f"encoder.down.{i}.block.{j}.", block_in, block_out)
+            block_in = block_out
+        if i != len(mult) - 1:
+            conv(f"encoder.down.{i}.downsample.conv.", block_in, block_in, 3)
+    res("encoder.mid.block_1.", block_in, block_in); attn("encoder.mid.attn_1.", block_in); res("encoder.mid.block_2.", block_in, block_in)
+    norm("encoder.norm_out.", block_in)
+    conv("encoder.conv_out.", 2 * z if dd["double_z"] else z, block_in, 3)
+    block_in = ch * mult[-1]
+    conv("decoder.conv_in.", block_in, z, 3)
+    res("decoder.mid.block_1.", block_in, block_in); attn("decoder.mid.attn_1.", block_in); res("decoder.mid.block_2.", block_in, block_in)
+    for i in reversed(range(len(mult))):
+        block_out = ch * mult[i]
+        for j in range(nrb + 1):
+            res(f"decoder.up.{i}.block.{j}.", block_in, block_out)
+            block_in = block_out
+        if i != 0:
+            conv(f"decoder.up.{i}.upsample.conv.", block_in, block_in, 3)
+    norm("decoder.norm_out.", block_in)
+    conv("decoder.conv_out.", dd["out_ch"], block_in, 3)
+    conv("quant_conv.", 2 * embed_dim, 2 * z, 1)
+    conv("post_quant_conv.", z, embed_dim, 1)
+    return s
+
+
 def random_state_dict(shapes, device, seed=0, std=0.02):
     """N(0, std) weights, unit norm gains, zero biases, generated on `device`."""
     g = torch.Generator(device=device).manual_seed(seed)
