@@ -219,6 +219,20 @@ int vb200_seem_attn_mask(const float* mask_logits, uint8_t* out_mask, int64_t Q,
 int vb200_softmax_rows(const float* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int64_t n,
                        cudaStream_t stream);
 
+/* ---- input pre-processing (preprocess.cu) — SURVEY.md §8(f3) ------------------------------------
+ * LanguageBind image transform ToTensor -> Resize(224, BICUBIC) -> CenterCrop(224) -> Normalize
+ * (languagebind/image/processing_image.py:15-25) and video transform /255 -> NormalizeVideo -> ShortSideScale(224)
+ * -> CenterCropVideo(224) -> horizontal flip (video/processing_video.py:26-70), fused: uint8 HWC frames
+ * [n, h, w, 3] -> normalised planar output, dst element offset = frame*dst_n + channel*dst_c + y*ow + x
+ * (image batch [n,3,oh,ow]: dst_n = 3*oh*ow, dst_c = oh*ow; video clip [3,n,oh,ow]: dst_n = oh*ow, dst_c = n*oh*ow).
+ * (rh, rw) = size of the virtual resized frame, (top, left) = crop offset inside it. mode: 0 bilinear,
+ * 1 bicubic (A = -0.75, torchvision 0.15 tensor path = the version the reference pins), 2 antialiased bicubic
+ * (torchvision >= 0.17 default). mean3 / std3 are HOST pointers to 3 floats. */
+int vb200_preprocess_frames(const uint8_t* src, void* dst, int64_t n, int64_t h, int64_t w, int64_t rh,
+                            int64_t rw, int64_t top, int64_t left, int64_t oh, int64_t ow, int64_t dst_n,
+                            int64_t dst_c, const float* mean3, const float* std3, int mode, int flip,
+                            int out_bf16, cudaStream_t stream);
+
 /* ---- FocalNet backbone glue (focal.cu) — SEEM backbone, SURVEY.md §8(f1) -------------------------
  * reference: modules/SEEM/demo_code/xdecoder/backbone/focal.py */
 #define VB_FOCAL_MAX_LEVELS 6
@@ -231,6 +245,10 @@ int vb200_im2col_nchw(const void* pixels, int in_is_fp32, void* out, int64_t nb,
 /* depthwise Conv2d(c, c, k, padding=k/2, groups=c, bias=False) [+ GELU] on NHWC bf16 (focal.py:80-89,105).
  * x: [nb, h, w, ld_in] view (first c channels of every pixel row), wt: [k*k, c] tap-major, out: [nb, h, w, c].
  * k in {3, 5, 7, 9, 11}; act = VB_ACT_NONE | VB_ACT_GELU. */
+/* kernel selection for vb200_dwconv_nhwc: 0 = automatic (default), 1 = 8-channel-per-thread kernel, 2 / 3 = channel-pair
+ * kernel with 16 / 32-pixel strips. All compute the same function (the switch lets the parity tests and the bench pin
+ * each one). Returns the previous setting. */
+int vb200_set_dwconv_impl(int impl);
 int vb200_dwconv_nhwc(const void* x, int64_t ld_in, const void* wt, void* out, int64_t nb, int64_t h,
                       int64_t w, int64_t c, int64_t k, int act, cudaStream_t stream);
 /* out[b, ch] = act(mean over the t rows of x[b]) in fp32, x [nb, t, c] bf16 (ctx.mean(2).mean(3) + GELU,

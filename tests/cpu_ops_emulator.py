@@ -142,10 +142,65 @@ def softmax_rows(x, out=None):
     return F.softmax(x, dim=-1).to(BF16)
 
 
+def preprocess_frames(frames, rh, rw, top, left, oh, ow, mean, std, mode, flip=False, layout="image", dtype=torch.float32):
+    """Transcription of preprocess.cu::preprocess_kernel (same formulas, fp64 accumulation), vectorised over pixels."""
+    import numpy as np
+    f = frames.cpu().numpy().astype(np.float64)
+    n, h, w, _ = f.shape
+    sy, sx = np.float32(h) / np.float32(rh), np.float32(w) / np.float32(rw)
+    oy, ox = np.meshgrid(np.arange(oh), np.arange(ow), indexing="ij")
+    ry = (oy + top).astype(np.float32)
+    rx = ((ow - 1 - ox if flip else ox) + left).astype(np.float32)
+    acc = np.zeros((n, oh, ow, 3))
+    if mode == 0:
+        fy, fx = np.maximum(sy * (ry + 0.5) - 0.5, 0), np.maximum(sx * (rx + 0.5) - 0.5, 0)
+        y0, x0 = np.minimum(fy.astype(int), h - 1), np.minimum(fx.astype(int), w - 1)
+        y1, x1 = np.minimum(y0 + 1, h - 1), np.minimum(x0 + 1, w - 1)
+        ly, lx = (fy - y0)[None, ..., None], (fx - x0)[None, ..., None]
+        acc = f[:, y0, x0] * (1 - ly) * (1 - lx) + f[:, y0, x1] * (1 - ly) * lx + f[:, y1, x0] * ly * (1 - lx) + f[:, y1, x1] * ly * lx
+    elif mode == 1:
+        A = -0.75
+
+        def coeffs(t):
+            x0, x1, x2, x3 = t + 1, t, 1 - t, 2 - t
+            return [((A * x0 - 5 * A) * x0 + 8 * A) * x0 - 4 * A, ((A + 2) * x1 - (A + 3)) * x1 * x1 + 1,
+                    ((A + 2) * x2 - (A + 3)) * x2 * x2 + 1, ((A * x3 - 5 * A) * x3 + 8 * A) * x3 - 4 * A]
+        fy, fx = sy * (ry + 0.5) - 0.5, sx * (rx + 0.5) - 0.5
+        yf, xf = np.floor(fy), np.floor(fx)
+        cy, cx = coeffs(fy - yf), coeffs(fx - xf)
+        for a in range(4):
+            yy = np.clip(yf.astype(int) - 1 + a, 0, h - 1)
+            for b in range(4):
+                xx = np.clip(xf.astype(int) - 1 + b, 0, w - 1)
+                acc += f[:, yy, xx] * (cy[a] * cx[b])[None, ..., None]
+    else:
+        def aa(x):
+            a = -0.5
+            x = np.abs(x)
+            return np.where(x < 1, ((a + 2) * x - (a + 3)) * x * x + 1, np.where(x < 2, (((x - 5) * x + 8) * x - 4) * a, 0.0))
+
+        def axis_weights(coord, scale, size):
+            sc = max(float(scale), 1.0)
+            sup = 2.0 * sc
+            W = np.zeros((coord.shape[0], size))
+            for i, c in enumerate(coord):
+                ctr = float(scale) * (float(c) + 0.5)
+                lo, hi = max(int(ctr - sup + 0.5), 0), min(int(ctr + sup + 0.5), size)
+                ws = aa((np.arange(lo, hi) - ctr + 0.5) / sc)
+                W[i, lo:hi] = ws / ws.sum()
+            return W
+        Wy = axis_weights(ry[:, 0], sy, h)            # [oh, h]
+        Wx = axis_weights(rx[0, :], sx, w)            # [ow, w]
+        acc = np.einsum("nyxc->nyxc", np.tensordot(np.tensordot(Wy, f, axes=([1], [1])), Wx, axes=([2], [1])).transpose(1, 0, 3, 2))
+    v = (acc / 255.0 - np.asarray(mean)[None, None, None]) / np.asarray(std)[None, None, None]
+    out = torch.from_numpy(v).permute(0, 3, 1, 2).to(dtype)
+    return out.contiguous() if layout == "image" else out.permute(1, 0, 2, 3).contiguous()
+
+
 def install(monkeypatch):
     """Replace the kernel-launching entry points of vitron_b200.ops with the statements above."""
     from vitron_b200 import ops
     for name in ("gemm", "layernorm", "layernorm_add", "pack_dwconv_weight", "dwconv_nhwc", "colmean", "focal_modulate",
                  "mul_rows", "im2col_nchw", "pack_conv_weight", "conv_nhwc", "groupnorm_nhwc", "conv_nhwc_direct",
-                 "upsample2x_nhwc", "softmax_rows"):
+                 "upsample2x_nhwc", "softmax_rows", "preprocess_frames"):
         monkeypatch.setattr(ops, name, globals()[name])

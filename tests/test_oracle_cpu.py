@@ -325,3 +325,46 @@ def test_vae_restatement_matches_live_reference():
     assert torch.allclose(mean, post.mean, atol=2e-4, rtol=1e-4) and torch.allclose(std, post.std, atol=2e-4, rtol=1e-4)
     assert torch.allclose(V.decode(sd, z, dd), dec, atol=2e-4, rtol=1e-4)
     assert zz.shape == mean.shape  # encode_firsr_stage = scale_factor * posterior.sample(): stochastic, shape only
+
+
+def _rand_u8(shape, seed):
+    return torch.randint(0, 256, shape, generator=torch.Generator().manual_seed(seed), dtype=torch.uint8)
+
+
+def test_image_transform_restatement_matches_reference_transform():
+    """§8(f3): the restated image transform (antialiased variant) == the reference's own get_image_transform run with
+    this image's torchvision (processing_image.py:15-25)."""
+    from oracle import refshim, restate_preprocess as P
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    import types
+    from PIL import Image
+    mod = refshim.load_file("ref_lb_processing_image", "vitron/model/multimodal_encoder/languagebind/image/processing_image.py")
+    tf = mod.get_image_transform(types.SimpleNamespace(vision_config=None))
+    for (h, w), seed in (((336, 336), 1), ((300, 451), 2), ((500, 333), 3), ((224, 224), 4), ((100, 150), 5)):
+        u8 = _rand_u8((h, w, 3), seed)
+        ref = tf(Image.fromarray(u8.numpy()))
+        got = P.image_transform(u8, antialias=True)
+        assert got.shape == ref.shape == (3, 224, 224)
+        assert torch.allclose(got, ref, atol=1e-5), (h, w, (got - ref).abs().max())
+
+
+def test_preprocess_kernel_formulas_match_oracle(monkeypatch):
+    """The arithmetic coded in preprocess.cu (transcribed in tests/cpu_ops_emulator.py) reproduces ATen's bicubic /
+    antialiased bicubic / bilinear resize through the host-side processors (geometry, crop, flip, layout)."""
+    from oracle import restate_preprocess as P
+    from tests import cpu_ops_emulator
+    from vitron_b200 import processing
+    cpu_ops_emulator.install(monkeypatch)
+    for (h, w), seed in (((336, 336), 1), ((120, 181), 2), ((260, 230), 3), ((90, 64), 4)):
+        u8 = _rand_u8((h, w, 3), seed)
+        for aa in (False, True):
+            got = processing.LanguageBindImageProcessor(device="cpu", antialias=aa).preprocess(u8.numpy())["pixel_values"][0]
+            ref = P.image_transform(u8, antialias=aa)
+            assert torch.allclose(got, ref, atol=2e-4), (h, w, aa, (got - ref).abs().max())
+    for (h, w), seed, flip in (((240, 320), 5, False), ((300, 225), 6, True), ((224, 224), 7, True)):
+        u8 = _rand_u8((4, h, w, 3), seed)
+        got = processing.LanguageBindVideoProcessor(device="cpu").preprocess(u8, flip=flip)["pixel_values"][0]
+        ref = P.video_transform(u8, flip)
+        assert got.shape == ref.shape == (3, 4, 224, 224)
+        assert torch.allclose(got, ref, atol=2e-4), (h, w, flip, (got - ref).abs().max())

@@ -41,9 +41,20 @@ def assert_close(got, ref, what, rel_inf=0.04, rel_l2=0.03):
 
 
 # ------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 @pytest.mark.parametrize("k", [3, 5, 7, 9, 11])
-@pytest.mark.parametrize("nb,h,w,c,ld_extra", [(1, 16, 24, 64, 0), (2, 9, 13, 72, 80), (1, 33, 5, 8, 8), (1, 64, 64, 192, 200)])
-def test_dwconv_gelu(cuda, k, nb, h, w, c, ld_extra):
+@pytest.mark.parametrize("nb,h,w,c,ld_extra", [(1, 16, 24, 64, 0), (2, 9, 13, 72, 80), (1, 33, 5, 8, 8), (1, 64, 64, 192, 200),
+                                               (1, 40, 300, 16, 0)])
+def test_dwconv_gelu(cuda, k, nb, h, w, c, ld_extra, impl):
+    from vitron_b200 import ops
+    prev = ops.set_dwconv_impl(impl)
+    try:
+        _dwconv_case(cuda, k, nb, h, w, c, ld_extra)
+    finally:
+        ops.set_dwconv_impl(prev)
+
+
+def _dwconv_case(cuda, k, nb, h, w, c, ld_extra):
     from vitron_b200 import ops
     ld = c + ld_extra
     buf = rnd((nb, h, w, ld), cuda, 1)

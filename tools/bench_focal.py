@@ -100,21 +100,31 @@ def main():
                              "launches_per_image": launches, "finite": finite, "gemm_tflop": round(gflop / 1e12, 3),
                              "dwconv_gflop": round(dwflop / 1e9, 1), "achieved_tflops_gemm_only": round(gflop / 1e12 / (ms * 1e-3), 1),
                              "h2d_bytes": img.numel() * 4, "shapes": {k: list(v.shape) for k, v in feats.items()}}
-        # depthwise focal conv, stage-0 shape of a 1024^2 image: T = 256*256, C = 192, read in place from the f output
-        T_h = T_w = a.size // 4
-        C = 192
-        fo = torch.randn((1, T_h, T_w, 2 * C + 8), device=dev).to(torch.bfloat16)
+        # depthwise focal conv at the stage-0 and stage-2 shapes of a 1024^2 image, every kernel variant
         rows = []
-        for k in (3, 5, 7, 9):
-            wt = ops.pack_dwconv_weight(torch.randn((C, 1, k, k), device=dev) / k)
-            src = fo[..., C:2 * C] if k == 3 else torch.randn((1, T_h, T_w, C), device=dev).to(torch.bfloat16)
-            t = graph_time(lambda: ops.dwconv_nhwc(src, wt, k, act=ops.ACT_GELU), 10)
-            byts = 2.0 * T_h * T_w * C * 2
-            fma = float(T_h * T_w * C * k * k)
-            rows.append({"k": k, "us": round(t * 1e3, 2), "algorithmic_bytes": byts, "achieved_gbs": round(byts / (t * 1e-3) / 1e9, 1),
-                         "frac_of_hbm_peak": round(byts / (t * 1e-3) / 1e9 / hbm, 3), "tfma_per_s": round(fma / (t * 1e-3) / 1e12, 2)})
-        out["dwconv_stage0"] = {"shape": [1, T_h, T_w, C], "hbm_peak_gbs": hbm, "fp32_fma_peak_tfma_s": round(148 * 128 * 1.965e9 / 1e12, 1),
-                                "levels": rows}
+        for (T_h, C) in ((a.size // 4, 192), (a.size // 16, 768)):
+            T_w = T_h
+            fo = torch.randn((1, T_h, T_w, 2 * C + 8), device=dev).to(torch.bfloat16)
+            for k in (3, 5, 7, 9):
+                wt = ops.pack_dwconv_weight(torch.randn((C, 1, k, k), device=dev) / k)
+                src = fo[..., C:2 * C] if k == 3 else torch.randn((1, T_h, T_w, C), device=dev).to(torch.bfloat16)
+                byts = 2.0 * T_h * T_w * C * 2
+                fma = float(T_h * T_w * C * k * k)
+                row = {"shape": [1, T_h, T_w, C], "k": k, "algorithmic_bytes": byts}
+                for impl, name in ((0, "auto"), (1, "vec8"), (2, "pair16"), (3, "pair32")):
+                    ops.set_dwconv_impl(impl)
+                    t = graph_time(lambda: ops.dwconv_nhwc(src, wt, k, act=ops.ACT_GELU), 10)
+                    row[name + "_us"] = round(t * 1e3, 2)
+                ops.set_dwconv_impl(0)
+                t = row["auto_us"] * 1e-3
+                row.update({"achieved_gbs": round(byts / (t * 1e-3) / 1e9, 1), "frac_of_hbm_peak": round(byts / (t * 1e-3) / 1e9 / hbm, 3),
+                            "tfma_per_s": round(fma / (t * 1e-3) / 1e12, 2)})
+                rows.append(row)
+        out["dwconv"] = {"hbm_peak_gbs": hbm, "fp32_fma_peak_tfma_s": round(148 * 128 * 1.965e9 / 1e12, 1), "levels": rows}
+        x0 = torch.randn((1, 256 * 256, 192), device=dev).to(torch.bfloat16)
+        x2 = torch.randn((1, 64 * 64, 768), device=dev).to(torch.bfloat16)
+        out["colmean_us"] = {"stage0_65536x192": round(graph_time(lambda: ops.colmean(x0.view(-1, 192), 1, act=ops.ACT_GELU), 10) * 1e3, 2),
+                             "stage2_4096x768": round(graph_time(lambda: ops.colmean(x2.view(-1, 768), 1, act=ops.ACT_GELU), 10) * 1e3, 2)}
         print(json.dumps(out), flush=True)
         if a.no_seem:
             return

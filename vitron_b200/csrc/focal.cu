@@ -145,6 +145,67 @@ __global__ void __launch_bounds__(128) dwconv_gelu_kernel(const bf16* __restrict
   }
 }
 
+// v2 (default): one thread = ONE bf16 channel pair x S consecutive output pixels of a row. A warp's 32 lanes
+// read 128 contiguous bytes of a pixel (full sectors); every input word is converted to a packed fp32 pair once
+// (2 ALU ops) and feeds up to K FFMA2, the K weights of the kernel row sit in registers: (S+K-1)*2 + K*2 ALU ops
+// per S*K FFMA2 (S = 32, K = 9: 98 vs 288) instead of the 1 : 1 of the 8-channel variant above.
+template <int K, int S>
+__global__ void __launch_bounds__(128) dwconv_gelu_pair_kernel(const bf16* __restrict__ x, long long ld_in,
+                                                               const bf16* __restrict__ wt, bf16* __restrict__ out,
+                                                               int nb, int h, int w, int c, int apply_gelu) {
+  const int c2n = c / 2;
+  const int nxs = (w + S - 1) / S;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(nb) * h * nxs * c2n;
+  if (idx >= total) return;
+  const int cp = static_cast<int>(idx % c2n);
+  long long r = idx / c2n;
+  const int xs = static_cast<int>(r % nxs); r /= nxs;
+  const int y = static_cast<int>(r % h);
+  const long long n = r / h;
+  const int x0 = xs * S;
+  constexpr int R = K / 2;
+  const long long ldw = ld_in / 2;  // pixel stride in 32-bit words
+  const uint32_t* wt32 = reinterpret_cast<const uint32_t*>(wt) + cp;
+
+  unsigned long long acc[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) acc[s] = 0ull;
+
+#pragma unroll 1
+  for (int ky = 0; ky < K; ++ky) {
+    const int iy = y + ky - R;
+    if (iy < 0 || iy >= h) continue;
+    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(x + ((n * h + iy) * static_cast<long long>(w)) * ld_in) + cp;
+    uint32_t pk[S + K - 1];
+#pragma unroll
+    for (int i = 0; i < S + K - 1; ++i) {
+      const int ix = x0 - R + i;
+      pk[i] = (ix >= 0 && ix < w) ? __ldg(rowp + static_cast<long long>(ix) * ldw) : 0u;
+    }
+    unsigned long long wv[K];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) wv[kx] = bf2_to_f2(__ldg(wt32 + static_cast<long long>(ky * K + kx) * c2n));
+#pragma unroll
+    for (int i = 0; i < S + K - 1; ++i) {
+      const unsigned long long v = bf2_to_f2(pk[i]);
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int s = i - kx;
+        if (s >= 0 && s < S) acc[s] = fma2(v, wv[kx], acc[s]);
+      }
+    }
+  }
+  uint32_t* orow = reinterpret_cast<uint32_t*>(out + ((n * h + y) * static_cast<long long>(w)) * c) + cp;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    if (x0 + s >= w) break;
+    float2 t = unpack2(acc[s]);
+    if (apply_gelu) { t.x = gelu_erf_fast(t.x); t.y = gelu_erf_fast(t.y); }
+    orow[static_cast<long long>(x0 + s) * c2n] = pack_bf16(t.x, t.y);
+  }
+}
+
 // ------------------------------------------------------------------ column sums (global context)
 // x [nb, t, c] contiguous bf16 -> partial [nb, nchunks, c] fp32 (sum over the chunk's rows). grid (nchunks, nb).
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const bf16* __restrict__ x, float* __restrict__ partial,
@@ -160,14 +221,22 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const bf16* __restr
   for (int j = 0; j < 8; ++j) s[j] = 0.f;
   if (rl < nrl) {
     const bf16* base = x + (static_cast<long long>(blockIdx.y) * t) * c + cg * 8;
-    for (long long r = r0 + rl; r < r1; r += nrl) {
-      const uint4 u = ldg16(base + r * c);
+    auto add8 = [&](const uint4 u) {
       float2 f;
       f = unpack_bf16(u.x); s[0] += f.x; s[1] += f.y;
       f = unpack_bf16(u.y); s[2] += f.x; s[3] += f.y;
       f = unpack_bf16(u.z); s[4] += f.x; s[5] += f.y;
       f = unpack_bf16(u.w); s[6] += f.x; s[7] += f.y;
+    };
+    long long r = r0 + rl;
+    for (; r + 3ll * nrl < r1; r += 4ll * nrl) {  // four independent 16-byte loads in flight
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = ldg16(base + (r + static_cast<long long>(k) * nrl) * c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) add8(u[k]);
     }
+    for (; r < r1; r += nrl) add8(ldg16(base + r * c));
 #pragma unroll
     for (int j = 0; j < 8; ++j) sred[rl * c + cg * 8 + j] = s[j];
   }
@@ -187,9 +256,16 @@ __global__ void colmean_finalize_kernel(const float* __restrict__ partial, float
   if (idx >= nb * c) return;
   const int b = idx / c, ch = idx % c;
   const float* p = partial + static_cast<long long>(b) * nchunks * c + ch;
-  float a = 0.f;
-  for (int k = 0; k < nchunks; ++k) a += p[static_cast<long long>(k) * c];
-  a *= inv_t;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 3 < nchunks; k += 4) {  // independent loads; the summation order is fixed -> deterministic
+    a0 += p[static_cast<long long>(k) * c];
+    a1 += p[static_cast<long long>(k + 1) * c];
+    a2 += p[static_cast<long long>(k + 2) * c];
+    a3 += p[static_cast<long long>(k + 3) * c];
+  }
+  for (; k < nchunks; ++k) a0 += p[static_cast<long long>(k) * c];
+  float a = ((a0 + a1) + (a2 + a3)) * inv_t;
   glob[idx] = apply_gelu ? gelu_erf(a) : a;
 }
 
@@ -343,6 +419,36 @@ static int launch_dwconv(const void* x, int64_t ld_in, const void* wt, void* out
   return VB_OK;
 }
 
+static int g_dwconv_impl = 0;  // 0 = automatic, 1 = 8-channel kernel, 2 / 3 = channel-pair kernel with 16 / 32-pixel strips
+extern "C" int vb200_set_dwconv_impl(int impl) {
+  const int prev = g_dwconv_impl;
+  if (impl >= 0 && impl <= 3) g_dwconv_impl = impl;
+  return prev;
+}
+
+template <int K>
+static int launch_dwconv_pair(const void* x, int64_t ld_in, const void* wt, void* out, int64_t nb, int64_t h, int64_t w,
+                              int64_t c, int act, cudaStream_t stream) {
+  const long long c2n = c / 2;
+  const long long t32 = nb * h * ((w + 31) / 32) * c2n;
+  const bf16* xp = reinterpret_cast<const bf16*>(x);
+  const bf16* wp = reinterpret_cast<const bf16*>(wt);
+  bf16* op = reinterpret_cast<bf16*>(out);
+  // 32-pixel strips re-read the fewest halo columns but need ~250 registers; they pay off only when there are
+  // enough strips to fill the machine several times over and the kernel is small enough not to spill
+  const bool wide = g_dwconv_impl == 3 || (g_dwconv_impl == 0 && K <= 7 && t32 >= 148ll * 2048);
+  if (wide) {
+    dwconv_gelu_pair_kernel<K, 32><<<static_cast<unsigned>((t32 + 127) / 128), 128, 0, stream>>>(xp, ld_in, wp, op, (int)nb,
+                                                                                                  (int)h, (int)w, (int)c, act);
+  } else {
+    const long long t16 = nb * h * ((w + 15) / 16) * c2n;
+    dwconv_gelu_pair_kernel<K, 16><<<static_cast<unsigned>((t16 + 127) / 128), 128, 0, stream>>>(xp, ld_in, wp, op, (int)nb,
+                                                                                                  (int)h, (int)w, (int)c, act);
+  }
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
 extern "C" int vb200_dwconv_nhwc(const void* x, int64_t ld_in, const void* wt, void* out, int64_t nb, int64_t h,
                                  int64_t w, int64_t c, int64_t k, int act, cudaStream_t stream) {
   VB_CHECK_ARG(x && wt && out && nb > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && ld_in % 8 == 0 && ld_in >= c);
@@ -350,6 +456,16 @@ extern "C" int vb200_dwconv_nhwc(const void* x, int64_t ld_in, const void* wt, v
   VB_CHECK_ARG(act == VB_ACT_NONE || act == VB_ACT_GELU);
   VB_CHECK_ARG(nb * h * ((w + 3) / 4) * (c / 8) < (1ll << 31) * 128);
   const int g = act == VB_ACT_GELU ? 1 : 0;
+  if (g_dwconv_impl != 1) {
+    switch (k) {
+      case 3: return launch_dwconv_pair<3>(x, ld_in, wt, out, nb, h, w, c, g, stream);
+      case 5: return launch_dwconv_pair<5>(x, ld_in, wt, out, nb, h, w, c, g, stream);
+      case 7: return launch_dwconv_pair<7>(x, ld_in, wt, out, nb, h, w, c, g, stream);
+      case 9: return launch_dwconv_pair<9>(x, ld_in, wt, out, nb, h, w, c, g, stream);
+      case 11: return launch_dwconv_pair<11>(x, ld_in, wt, out, nb, h, w, c, g, stream);
+      default: return VB_ERR_UNSUPPORTED;
+    }
+  }
   switch (k) {
     case 3: return launch_dwconv<3, 8>(x, ld_in, wt, out, nb, h, w, c, g, stream);
     case 5: return launch_dwconv<5, 8>(x, ld_in, wt, out, nb, h, w, c, g, stream);
@@ -361,8 +477,10 @@ extern "C" int vb200_dwconv_nhwc(const void* x, int64_t ld_in, const void* wt, v
 }
 
 static inline int colsum_chunks(int64_t t) {
-  int64_t n = (t + 255) / 256;
-  return static_cast<int>(n < 1 ? 1 : (n > 512 ? 512 : n));
+  // enough CTAs to cover the machine twice (the reduction is latency bound per thread), >= 16 rows per chunk
+  int64_t n = (t + 15) / 16;
+  const int64_t cap = 2 * static_cast<int64_t>(vb_num_sms());
+  return static_cast<int>(n < 1 ? 1 : (n > cap ? cap : n));
 }
 
 extern "C" size_t vb200_colmean_workspace_size(int64_t nb, int64_t t, int64_t c) {

@@ -511,6 +511,11 @@ def pack_dwconv_weight(w):
     return w.reshape(c, kh * kw).t().to(BF16).contiguous()
 
 
+def set_dwconv_impl(impl):
+    """0 = automatic (default), 1 = 8-channel kernel, 2 / 3 = channel-pair kernel with 16 / 32-pixel strips."""
+    return _lib.load().vb200_set_dwconv_impl(int(impl))
+
+
 def dwconv_nhwc(x, wt, k, act=ACT_NONE):
     """x: [nb, h, w, c] bf16, either contiguous or a channel slice of a contiguous [nb, h, w, ld] tensor."""
     lib = _lib.load()
@@ -594,5 +599,25 @@ def softmax_rows(x, out=None):
         out = torch.empty(x.shape, dtype=BF16, device=x.device)
     check(lib.vb200_softmax_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1], _stream()),
           "vb200_softmax_rows")
+    _launches[0] += 1
+    return out
+
+
+def preprocess_frames(frames, rh, rw, top, left, oh, ow, mean, std, mode, flip=False, layout="image", dtype=torch.float32):
+    """frames uint8 [n, h, w, 3] (device) -> normalised [n, 3, oh, ow] (layout "image") or [3, n, oh, ow] ("video")."""
+    lib = _lib.load()
+    _req(frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and frames.is_contiguous(), "uint8 [n,h,w,3]")
+    _req(dtype in (torch.float32, BF16), "fp32 or bf16 output")
+    n, h, w, _ = frames.shape
+    if layout == "image":
+        out = torch.empty((n, 3, oh, ow), dtype=dtype, device=frames.device)
+        dn, dc = 3 * oh * ow, oh * ow
+    else:
+        out = torch.empty((3, n, oh, ow), dtype=dtype, device=frames.device)
+        dn, dc = oh * ow, n * oh * ow
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    check(lib.vb200_preprocess_frames(frames.data_ptr(), out.data_ptr(), n, h, w, rh, rw, top, left, oh, ow, dn, dc, m3, s3,
+                                      int(mode), 1 if flip else 0, 1 if dtype == BF16 else 0, _stream()), "vb200_preprocess_frames")
     _launches[0] += 1
     return out
