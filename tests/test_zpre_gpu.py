@@ -48,5 +48,8 @@ def test_processed_pixels_feed_the_tower_entry(cuda):
     from vitron_b200.processing import LanguageBindImageProcessor
     out = LanguageBindImageProcessor(device=cuda).preprocess([u8((336, 336, 3), 1).numpy()] * 3)["pixel_values"]
     assert out.is_cuda and out.is_contiguous() and tuple(out.shape) == (3, 3, 224, 224)
+    batch = torch.stack([u8((336, 336, 3), 1)] * 3)
+    one = LanguageBindImageProcessor(device=cuda).preprocess(batch)["pixel_values"]
+    assert torch.equal(one, out), "batched launch == per-image launches"
     with pytest.raises(ValueError):
         LanguageBindImageProcessor(device=cuda)(images=None, text=None)

@@ -76,13 +76,17 @@ class LanguageBindImageProcessor:
         self.image_mean = OPENAI_DATASET_MEAN
         self.crop_size = {"height": 224, "width": 224}
 
-    def transform(self, image):
-        f = _as_uint8_frames(image, self.device)
+    def transform_batch(self, frames):
+        """uint8 [n, h, w, 3] (equal-sized images) -> [n, 3, 224, 224] with ONE kernel launch."""
+        f = _as_uint8_frames(frames, self.device)
         _, h, w, _ = f.shape
         rh, rw, top, left = image_resize_geometry(h, w)
         mode = MODE_BICUBIC_AA if self.antialias else MODE_BICUBIC
         return ops.preprocess_frames(f, rh, rw, top, left, 224, 224, OPENAI_DATASET_MEAN, OPENAI_DATASET_STD, mode,
-                                     layout="image", dtype=self.dtype)[0]
+                                     layout="image", dtype=self.dtype)
+
+    def transform(self, image):
+        return self.transform_batch(image)[0]
 
     def __call__(self, images=None, text=None, context_length=77, return_tensors=None, **kwargs):
         if text is None and images is None:
@@ -94,8 +98,11 @@ class LanguageBindImageProcessor:
             encoding = self.tokenizer(text, max_length=context_length, padding="max_length", truncation=True,
                                       return_tensors=return_tensors, **kwargs)
         if images is not None:
-            images = images if isinstance(images, list) else [images]
-            feats = torch.stack([self.transform(i) for i in images])
+            if torch.is_tensor(images) and images.dim() == 4:   # a batch of equal-sized decoded images: one launch
+                feats = self.transform_batch(images)
+            else:
+                images = images if isinstance(images, list) else [images]
+                feats = torch.stack([self.transform(i) for i in images])
             if encoding is not None:
                 encoding["pixel_values"] = feats
                 return encoding
