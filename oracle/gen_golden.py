@@ -265,7 +265,45 @@ def gen_vae(seed=61):
     print("vae_tiny.pt", tuple(post.mean.shape), float(post.mean.abs().max()), tuple(dec.shape), float(dec.abs().max()))
 
 
-GENERATORS = {"vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen, "seem": gen_seem, "focal": gen_focal, "vae": gen_vae}
+GLIGEN_UNET_TINY = dict(image_size=16, in_channels=4, model_channels=128, out_channels=4, num_res_blocks=1,
+                        attention_resolutions=[2, 1], channel_mult=[1, 2, 2], num_heads=2, transformer_depth=1, context_dim=96,
+                        positive_len=96, fuser_type="gatedSA", use_checkpoint=False)
+
+
+def build_reference_gligen_unet(cfg, seed):
+    import contextlib
+    import io
+    U = refshim.gligen_unet_class()
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = U(**cfg).eval()
+    shapes = _load_seeded(net, seed, gain=0.6)
+    return net, seeded_state_dict(shapes, seed, 0.6), shapes
+
+
+def gligen_unet_inputs(cfg, g, b=2, n_obj=5, hw=(16, 16), inpaint=False):
+    rn = lambda *s: torch.randn(s, generator=g)
+    inp = dict(x=rn(b, cfg["in_channels"], *hw), timesteps=torch.tensor([801, 37][:b]), context=rn(b, 9, cfg["context_dim"]),
+               boxes=torch.rand((b, n_obj, 4), generator=g), masks=(torch.rand((b, n_obj), generator=g) > 0.4).float(),
+               text_embeddings=rn(b, n_obj, cfg["positive_len"]))
+    if inpaint:
+        inp["inpainting_extra_input"] = rn(b, cfg["in_channels"] + 1, *hw)
+    return inp
+
+
+def gen_gligen_unet(seed=71):
+    """GLIGEN's grounded UNetModel forward (reference prints suppressed) through the unmodified class."""
+    import contextlib
+    import io
+    net, sd, shapes = build_reference_gligen_unet(GLIGEN_UNET_TINY, seed)
+    inp = gligen_unet_inputs(GLIGEN_UNET_TINY, torch.Generator().manual_seed(seed))
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        out = net(dict(inp))
+    torch.save(dict(seed=seed, gain=0.6, cfg=dict(GLIGEN_UNET_TINY), shapes=shapes, inputs=inp, out=out),
+               os.path.join(OUT, "gligen_unet_tiny.pt"))
+    print("gligen_unet_tiny.pt", tuple(out.shape), float(out.abs().max()), len(shapes), "tensors")
+
+
+GENERATORS = {"vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen, "seem": gen_seem, "focal": gen_focal, "vae": gen_vae, "gligen_unet": gen_gligen_unet}
 
 
 def main(argv):

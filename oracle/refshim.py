@@ -252,6 +252,16 @@ def gligen_attention():
     return load_file("ref_gligen_attention", "modules/GLIGEN/demo/gligen/ldm/modules/attention.py")
 
 
+def gligen_unet_class():
+    """Unmodified gligen/ldm/modules/diffusionmodules/openaimodel.py::UNetModel. Its imports are absolute from the
+    Vitron repo root (`modules.GLIGEN.demo.gligen.ldm...`), so the reference root goes on sys.path."""
+    chain = ["modules", "modules.GLIGEN", "modules.GLIGEN.demo", "modules.GLIGEN.demo.gligen", "modules.GLIGEN.demo.gligen.ldm"]
+    for name in chain:  # empty package modules: skips gligen/__init__.py and ldm/__init__.py (which import its trainer / evaluator stack)
+        if name not in sys.modules:
+            _pkg(name, os.path.join(REF, *name.split(".")))
+    return importlib.import_module("modules.GLIGEN.demo.gligen.ldm.modules.diffusionmodules.openaimodel").UNetModel
+
+
 def seem_pieces():
     """The importable SEEM pieces (torch/einops only)."""
     ns = types.SimpleNamespace()

@@ -15,20 +15,58 @@ def _act(x, act):
             ACT_RELU: F.relu, ACT_SILU: F.silu}[int(act)](x)
 
 
-def gemm(a, w, bias=None, act=ACT_NONE, glu=0, residual=None, alpha=1.0, out=None, out_fp32=False, **kw):
-    assert glu == 0 and not kw.get("rowbias") and not kw.get("rowscale") and not kw.get("rms_eps")
+def _unglu(v):
+    """Columns of a GEMM against an ops.pack_glu_weight matrix: 16-column blocks alternate a | b."""
+    n = v.shape[-1]
+    blk = v.reshape(*v.shape[:-1], n // 32, 2, 16)
+    return blk[..., 0, :].reshape(*v.shape[:-1], n // 2), blk[..., 1, :].reshape(*v.shape[:-1], n // 2)
+
+
+def gemm(a, w, bias=None, act=ACT_NONE, glu=0, residual=None, alpha=1.0, rowbias=None, rowbias_rows=0, out=None,
+         out_fp32=False, rowscale=None, rms_eps=0.0):
+    assert rowscale is None and not rms_eps
     assert a.dtype == BF16 and w.dtype == BF16 and a.shape[-1] == w.shape[1]
     v = a.float().reshape(-1, a.shape[-1]) @ w.float().t()
     if bias is not None:
         v = v + bias.float()
-    v = _act(v, act) * alpha
+    if rowbias is not None:
+        v = v + rowbias.float().repeat_interleave(int(rowbias_rows), 0)[:v.shape[0]]
+    if glu:
+        x, g = _unglu(v)
+        v = F.silu(x) * g if glu == 1 else x * F.gelu(g)
+    else:
+        v = _act(v, act)
+    v = v * alpha
     if residual is not None:
         v = residual.float().reshape(v.shape) + v
-    v = v.reshape(*a.shape[:-1], w.shape[0]).to(torch.float32 if out_fp32 else BF16)
+    v = v.reshape(*a.shape[:-1], v.shape[-1]).to(torch.float32 if out_fp32 else BF16)
     if out is not None:
         out.copy_(v.reshape(out.shape))
         return out
     return v
+
+
+def pack_glu_weight(w_a, w_b):
+    f = w_a.shape[0]
+    rest = w_a.shape[1:]
+    return torch.stack([w_a.reshape(f // 16, 16, *rest), w_b.reshape(f // 16, 16, *rest)], dim=1).reshape(2 * f, *rest).contiguous()
+
+
+def attention(q, k, v, scale=None, causal=False, kv_len=None, mask=None, out=None):
+    assert kv_len is None
+    B, Sq, H, D = q.shape
+    scale = D ** -0.5 if scale is None else scale
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale
+    if causal:
+        Skv = k.shape[1]
+        s = s.masked_fill(torch.ones(Sq, Skv, dtype=torch.bool).triu(Skv - Sq + 1), float("-inf"))
+    if mask is not None:
+        s = s.masked_fill(mask.bool(), float("-inf"))
+    o = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1).nan_to_num(), v.float()).to(BF16).contiguous()
+    if out is not None:
+        out.copy_(o)
+        return out
+    return o
 
 
 def layernorm(x, weight, bias, eps, out=None):
@@ -103,7 +141,9 @@ def pack_conv_weight(w):
     return out
 
 
-def conv_nhwc(x, wt, kh, kw, stride=1, pad_h=None, pad_w=None, bias=None, act=ACT_NONE, residual=None, alpha=1.0, **kw_):
+def conv_nhwc(x, wt, kh, kw, stride=1, pad_h=None, pad_w=None, bias=None, act=ACT_NONE, glu=0, residual=None, alpha=1.0,
+              rowbias=None, rowbias_rows=0, out=None):
+    assert glu == 0 and out is None
     nb, h, w, cin = x.shape
     cout = wt.shape[0]
     pad_h = kh // 2 if pad_h is None else pad_h
@@ -111,7 +151,11 @@ def conv_nhwc(x, wt, kh, kw, stride=1, pad_h=None, pad_w=None, bias=None, act=AC
     wc = wt.float()[:, :, :cin].reshape(cout, kh, kw, cin).permute(0, 3, 1, 2)
     y = F.conv2d(x.float().permute(0, 3, 1, 2), wc, None if bias is None else bias.float(), stride=stride,
                  padding=(pad_h, pad_w))
-    y = _act(y, act).permute(0, 2, 3, 1) * alpha
+    y = y.permute(0, 2, 3, 1)
+    if rowbias is not None:  # per (rowbias_rows consecutive output pixels) group bias over the channels
+        rb = rowbias.float().repeat_interleave(int(rowbias_rows), 0)[:y.numel() // y.shape[-1]]
+        y = y + rb.reshape(y.shape)
+    y = _act(y, act) * alpha
     if residual is not None:
         y = residual.float() + y
     return y.to(BF16).contiguous()
@@ -202,5 +246,5 @@ def install(monkeypatch):
     from vitron_b200 import ops
     for name in ("gemm", "layernorm", "layernorm_add", "pack_dwconv_weight", "dwconv_nhwc", "colmean", "focal_modulate",
                  "mul_rows", "im2col_nchw", "pack_conv_weight", "conv_nhwc", "groupnorm_nhwc", "conv_nhwc_direct",
-                 "upsample2x_nhwc", "softmax_rows", "preprocess_frames"):
+                 "upsample2x_nhwc", "softmax_rows", "preprocess_frames", "pack_glu_weight", "attention"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -198,3 +198,22 @@ def test_vae_shape_table_matches_reference_names():
     from vitron_b200 import param_shapes
     fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vae_tiny.pt"), weights_only=False)
     assert param_shapes.vae_shapes(fx["ddconfig"]) == fx["shapes"]
+
+
+def test_gligen_unet_shape_table_and_host_logic(monkeypatch):
+    """vitron_b200.gligen_unet.UNetModel: reference state-dict names (shape table == unmodified class) and host logic
+    (block plan, batched time-embedding projection as conv row bias, channel padding, NHWC skip concat, position net)
+    against the reference's golden output with the kernels replaced by torch statements."""
+    import os
+    import torch
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200 import param_shapes
+    from vitron_b200.gligen_unet import UNetModel
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "gligen_unet_tiny.pt"), weights_only=False)
+    assert param_shapes.gligen_unet_shapes(fx["cfg"]) == fx["shapes"]
+    cpu_ops_emulator.install(monkeypatch)
+    net = UNetModel(**fx["cfg"], device="cpu").load_state_dict(seeded_state_dict(fx["shapes"], fx["seed"], fx["gain"]))
+    out = net(dict(fx["inputs"]))
+    e_inf, e_l2 = _rel(out, fx["out"])
+    assert out.shape == fx["out"].shape and e_inf < 0.05 and e_l2 < 0.04, (e_inf, e_l2)

@@ -368,3 +368,34 @@ def test_preprocess_kernel_formulas_match_oracle(monkeypatch):
         ref = P.video_transform(u8, flip)
         assert got.shape == ref.shape == (3, 4, 224, 224)
         assert torch.allclose(got, ref, atol=2e-4), (h, w, flip, (got - ref).abs().max())
+
+
+def test_gligen_unet_restatement_matches_reference_golden():
+    """§8(f2) GLIGEN grounded SD UNet: restatement == unmodified UNetModel (golden)."""
+    from oracle import restate_gligen_unet as G
+    fx = load("gligen_unet_tiny.pt")
+    sd = seeded_state_dict(fx["shapes"], fx["seed"], fx["gain"])
+    out = G.unet_forward(sd, fx["cfg"], fx["inputs"])
+    assert out.shape == fx["out"].shape
+    assert torch.allclose(out, fx["out"], atol=2e-5, rtol=2e-4), (out - fx["out"]).abs().max()
+
+
+def test_gligen_unet_restatement_matches_live_reference():
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    import contextlib
+    import io
+    from oracle import gen_golden as GG, restate_gligen_unet as G
+    cfg = dict(GG.GLIGEN_UNET_TINY, model_channels=32, channel_mult=[1, 2, 4], num_res_blocks=2, attention_resolutions=[4, 1],
+               num_heads=4, is_inpaint=True)
+    net, sd, _ = GG.build_reference_gligen_unet(cfg, seed=72)
+    inp = GG.gligen_unet_inputs(cfg, torch.Generator().manual_seed(5), b=1, n_obj=3, hw=(8, 12), inpaint=True)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        ref = net(dict(inp))
+        inp2 = {k: v for k, v in inp.items() if k not in ("boxes", "masks", "text_embeddings")}
+        net.max_box = 30
+        ref2 = net(dict(inp2))           # no grounding input: zero boxes -> learned null tokens (forward_position_net :393-399)
+    out = G.unet_forward(sd, cfg, inp)
+    assert torch.allclose(out, ref, atol=2e-5, rtol=2e-4), (out - ref).abs().max()
+    assert torch.allclose(G.unet_forward(sd, cfg, inp2), ref2, atol=2e-5, rtol=2e-4)

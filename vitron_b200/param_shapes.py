@@ -281,6 +281,88 @@ def vae_shapes(dd, embed_dim=4):
     return s
 
 
+def gligen_unet_shapes(cfg):
+    """Reference GLIGEN UNetModel parameter names / shapes (openaimodel.py:234-386, attention.py:285-386,
+    positionnet.py:9-28) for fuser_type='gatedSA'."""
+    s = {}
+    mc, mult, nrb = cfg["model_channels"], tuple(cfg["channel_mult"]), cfg["num_res_blocks"]
+    att, heads, depth = list(cfg["attention_resolutions"]), cfg.get("num_heads", 8), cfg.get("transformer_depth", 1)
+    ctx, pos_len = cfg["context_dim"], cfg.get("positive_len", 768)
+    ted = 4 * mc
+
+    def lin(p, o, i, bias=True):
+        s[p + "weight"] = [o, i]
+        if bias:
+            s[p + "bias"] = [o]
+
+    def conv(p, o, i, k):
+        s[p + "weight"], s[p + "bias"] = [o, i, k, k], [o]
+
+    def norm(p, c):
+        s[p + "weight"], s[p + "bias"] = [c], [c]
+
+    def res(p, cin, cout):
+        norm(p + "in_layers.0.", cin); conv(p + "in_layers.2.", cout, cin, 3); lin(p + "emb_layers.1.", cout, ted)
+        norm(p + "out_layers.0.", cout); conv(p + "out_layers.3.", cout, cout, 3)
+        if cin != cout:
+            conv(p + "skip_connection.", cout, cin, 1)
+
+    def attn(p, q, kdim, self_attn):
+        lin(p + "to_q.", q, q, False); lin(p + "to_k.", q, q if self_attn else kdim, False); lin(p + "to_v.", q, q if self_attn else kdim, False)
+        lin(p + "to_out.0.", q, q)
+
+    def ff(p, d):
+        lin(p + "net.0.proj.", 8 * d, d); lin(p + "net.2.", d, 4 * d)
+
+    def st(p, c):
+        norm(p + "norm.", c); conv(p + "proj_in.", c, c, 1); conv(p + "proj_out.", c, c, 1)
+        for d in range(depth):
+            b = p + f"transformer_blocks.{d}."
+            attn(b + "attn1.", c, c, True); ff(b + "ff.", c); attn(b + "attn2.", c, ctx, False)
+            for i in (1, 2, 3):
+                norm(b + f"norm{i}.", c)
+            f = b + "fuser."
+            lin(f + "linear.", c, ctx); attn(f + "attn.", c, c, True); ff(f + "ff.", c)
+            norm(f + "norm1.", c); norm(f + "norm2.", c)
+            s[f + "alpha_attn"], s[f + "alpha_dense"] = [], []
+
+    lin("time_embed.0.", ted, mc); lin("time_embed.2.", ted, ted)
+    tin = 2 * cfg["in_channels"] + 1 if cfg.get("is_inpaint", False) else cfg["in_channels"]
+    conv("input_blocks.0.0.", mc, tin, 3)
+    chans, ch, ds, idx = [mc], mc, 1, 1
+    for level, m in enumerate(mult):
+        for _ in range(nrb):
+            res(f"input_blocks.{idx}.0.", ch, m * mc)
+            ch = m * mc
+            if ds in att:
+                st(f"input_blocks.{idx}.1.", ch)
+            chans.append(ch)
+            idx += 1
+        if level != len(mult) - 1:
+            conv(f"input_blocks.{idx}.0.op.", ch, ch, 3)
+            chans.append(ch)
+            ds *= 2
+            idx += 1
+    res("middle_block.0.", ch, ch); st("middle_block.1.", ch); res("middle_block.2.", ch, ch)
+    idx = 0
+    for level, m in list(enumerate(mult))[::-1]:
+        for i in range(nrb + 1):
+            res(f"output_blocks.{idx}.0.", ch + chans.pop(), mc * m)
+            ch = mc * m
+            j = 1
+            if ds in att:
+                st(f"output_blocks.{idx}.{j}.", ch)
+                j += 1
+            if level and i == nrb:
+                conv(f"output_blocks.{idx}.{j}.conv.", ch, ch, 3)
+                ds //= 2
+            idx += 1
+    norm("out.0.", ch); conv("out.2.", cfg["out_channels"], mc, 3)
+    lin("position_net.linears.0.", 512, pos_len + 64); lin("position_net.linears.2.", 512, 512); lin("position_net.linears.4.", ctx, 512)
+    s["position_net.null_positive_feature"], s["position_net.null_position_feature"] = [pos_len], [64]
+    return s
+
+
 def random_state_dict(shapes, device, seed=0, std=0.02):
     """N(0, std) weights, unit norm gains, zero biases, generated on `device`."""
     g = torch.Generator(device=device).manual_seed(seed)
