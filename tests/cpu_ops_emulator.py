@@ -241,10 +241,43 @@ def preprocess_frames(frames, rh, rw, top, left, oh, ow, mean, std, mode, flip=F
     return out.contiguous() if layout == "image" else out.permute(1, 0, 2, 3).contiguous()
 
 
+def splice_multimodal(embed, feats, srcmap, out=None):
+    src = srcmap.long()
+    assert feats is None and bool((src >= 0).all())
+    v = embed[src.reshape(-1)].reshape(*srcmap.shape, embed.shape[1])
+    if out is not None:
+        out.copy_(v.reshape(out.shape))
+        return out
+    return v
+
+
+def add(a, b, out=None):
+    v = (a.float().reshape(-1, b.numel()) + b.float().reshape(1, -1)).reshape(a.shape).to(BF16)
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v
+
+
+def patchify(pixels, patch, kpad):
+    nb, c, h, w = pixels.shape
+    cols = F.unfold(pixels.float(), patch, stride=patch).transpose(1, 2).reshape(-1, c * patch * patch)
+    out = torch.zeros((cols.shape[0], kpad), dtype=BF16)
+    out[:, :cols.shape[1]] = cols.to(BF16)
+    return out
+
+
+def vit_embed_ln(patch_out, cls, pos, ln_w, ln_b, nb, npatch, eps):
+    d = patch_out.shape[-1]
+    x = torch.cat([cls.float().view(1, 1, d).expand(nb, 1, d), patch_out.float().view(nb, npatch, d)], 1) + pos.float()[None]
+    return F.layer_norm(x, (d,), ln_w.float(), ln_b.float(), eps).to(BF16)
+
+
 def install(monkeypatch):
     """Replace the kernel-launching entry points of vitron_b200.ops with the statements above."""
     from vitron_b200 import ops
     for name in ("gemm", "layernorm", "layernorm_add", "pack_dwconv_weight", "dwconv_nhwc", "colmean", "focal_modulate",
                  "mul_rows", "im2col_nchw", "pack_conv_weight", "conv_nhwc", "groupnorm_nhwc", "conv_nhwc_direct",
-                 "upsample2x_nhwc", "softmax_rows", "preprocess_frames", "pack_glu_weight", "attention"):
+                 "upsample2x_nhwc", "softmax_rows", "preprocess_frames", "pack_glu_weight", "attention",
+                 "splice_multimodal", "add", "patchify", "vit_embed_ln"):
         monkeypatch.setattr(ops, name, globals()[name])

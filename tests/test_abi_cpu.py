@@ -217,3 +217,33 @@ def test_gligen_unet_shape_table_and_host_logic(monkeypatch):
     out = net(dict(fx["inputs"]))
     e_inf, e_l2 = _rel(out, fx["out"])
     assert out.shape == fx["out"].shape and e_inf < 0.05 and e_l2 < 0.04, (e_inf, e_l2)
+
+
+def test_clip_embedder_host_logic_against_oracle(monkeypatch):
+    """vitron_b200.clip_embedder (open_clip state-dict names, penultimate-layer rule, EOS pooling, image tower through the
+    LanguageBind ViT path) against the restated / transformers-cross-checked oracle, kernels replaced by torch statements."""
+    import torch
+    from oracle import restate_openclip as OC
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from tests.test_oracle_cpu import OPENCLIP_TINY as cfg
+    from vitron_b200.clip_embedder import FrozenOpenCLIPEmbedder, FrozenOpenCLIPTtxtVisualEmbedder
+    cpu_ops_emulator.install(monkeypatch)
+    sd = seeded_state_dict(OC.openclip_shapes(cfg), 3)
+    g = torch.Generator().manual_seed(2)
+    tokens = torch.randint(1, 298, (2, 16), generator=g)
+    tokens[0, 9], tokens[1, 15] = 299, 299
+    tokens[0, 10:] = 0
+    img = torch.randn((2, 3, 56, 56), generator=g)
+    both = FrozenOpenCLIPTtxtVisualEmbedder(None, device="cpu", layer="penultimate", arch_cfg=cfg).load_state_dict(sd)
+    xi, xt, x = both(image=img, text=tokens)
+    rt, rx = OC.encode_text(sd, tokens, cfg, layer_idx=1)
+    for got, ref, what in ((x, rx, "tokens"), (xt, rt, "pooled text"), (xi, OC.encode_image(sd, img, cfg), "image")):
+        e_inf, e_l2 = _rel(got, ref)
+        assert got.shape == ref.shape and e_inf < 0.04 and e_l2 < 0.03, (what, e_inf, e_l2)
+    emb = FrozenOpenCLIPEmbedder(None, device="cpu", layer="last", arch_cfg=cfg).load_state_dict(sd)
+    e_inf, e_l2 = _rel(emb(tokens), OC.encode_text(sd, tokens, cfg, layer_idx=0)[1])
+    assert e_inf < 0.04 and e_l2 < 0.03
+    import pytest
+    with pytest.raises(ValueError):
+        emb("a caption")

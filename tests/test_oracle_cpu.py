@@ -399,3 +399,75 @@ def test_gligen_unet_restatement_matches_live_reference():
     out = G.unet_forward(sd, cfg, inp)
     assert torch.allclose(out, ref, atol=2e-5, rtol=2e-4), (out - ref).abs().max()
     assert torch.allclose(G.unet_forward(sd, cfg, inp2), ref2, atol=2e-5, rtol=2e-4)
+
+
+OPENCLIP_TINY = dict(embed_dim=96, text=dict(width=128, layers=3, heads=2, context_length=16, vocab_size=300),
+                     vision=dict(width=128, layers=2, heads=2, patch_size=14, image_size=56, mlp=256))
+
+
+def test_openclip_restatement_matches_transformers_clip():
+    """open_clip is absent (third-party): the restated published algorithm is cross-checked against the independent
+    CLIP implementation in `transformers` with the same weights mapped (text: causal, EOS = argmax pooling; vision: CLS)."""
+    from transformers import CLIPTextConfig, CLIPTextModelWithProjection, CLIPVisionConfig, CLIPVisionModelWithProjection
+    from oracle import restate_openclip as OC
+    cfg = OPENCLIP_TINY
+    sd = seeded_state_dict(OC.openclip_shapes(cfg), 3)
+    t, v = cfg["text"], cfg["vision"]
+
+    def map_blocks(src, dst, n, d):
+        out = {}
+        for i in range(n):
+            p, q = src + f"resblocks.{i}.", dst + f"encoder.layers.{i}."
+            w, b = sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"]
+            for j, nm in enumerate("qkv"):
+                out[q + f"self_attn.{nm}_proj.weight"], out[q + f"self_attn.{nm}_proj.bias"] = w[j * d:(j + 1) * d], b[j * d:(j + 1) * d]
+            out[q + "self_attn.out_proj.weight"], out[q + "self_attn.out_proj.bias"] = sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"]
+            for a, bname in (("ln_1", "layer_norm1"), ("ln_2", "layer_norm2")):
+                out[q + bname + ".weight"], out[q + bname + ".bias"] = sd[p + a + ".weight"], sd[p + a + ".bias"]
+            out[q + "mlp.fc1.weight"], out[q + "mlp.fc1.bias"] = sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"]
+            out[q + "mlp.fc2.weight"], out[q + "mlp.fc2.bias"] = sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"]
+        return out
+
+    tm = CLIPTextModelWithProjection(CLIPTextConfig(vocab_size=t["vocab_size"], hidden_size=t["width"], intermediate_size=4 * t["width"],
+                                                    num_hidden_layers=t["layers"], num_attention_heads=t["heads"],
+                                                    max_position_embeddings=t["context_length"], hidden_act="gelu",
+                                                    projection_dim=cfg["embed_dim"], eos_token_id=t["vocab_size"] - 1,
+                                                    attn_implementation="eager")).eval()
+    hf = map_blocks("model.transformer.", "text_model.", t["layers"], t["width"])
+    hf.update({"text_model.embeddings.token_embedding.weight": sd["model.token_embedding.weight"],
+               "text_model.embeddings.position_embedding.weight": sd["model.positional_embedding"],
+               "text_model.final_layer_norm.weight": sd["model.ln_final.weight"], "text_model.final_layer_norm.bias": sd["model.ln_final.bias"],
+               "text_projection.weight": sd["model.text_projection"].t().contiguous()})
+    missing, unexpected = tm.load_state_dict(hf, strict=False)
+    assert not unexpected and all("position_ids" in m for m in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(2)
+    tokens = torch.randint(1, t["vocab_size"] - 1, (2, t["context_length"]), generator=g)
+    tokens[0, 9], tokens[1, 15] = t["vocab_size"] - 1, t["vocab_size"] - 1       # EOS = highest id (argmax pooling)
+    tokens[0, 10:] = 0
+    with torch.no_grad():
+        ref = tm(input_ids=tokens, output_hidden_states=True)
+    xt, x = OC.encode_text(sd, tokens, cfg, layer_idx=0)
+    assert torch.allclose(x, ref.last_hidden_state, atol=2e-4, rtol=1e-4)
+    assert torch.allclose(xt, ref.text_embeds, atol=2e-4, rtol=1e-4)
+    _, xp = OC.encode_text(sd, tokens, cfg, layer_idx=1)                            # "penultimate": ln_final(hidden_states[-2])
+    with torch.no_grad():
+        pen = tm.text_model.final_layer_norm(ref.hidden_states[-2])
+    assert torch.allclose(xp, pen, atol=2e-4, rtol=1e-4)
+
+    vm = CLIPVisionModelWithProjection(CLIPVisionConfig(hidden_size=v["width"], intermediate_size=v["mlp"], num_hidden_layers=v["layers"],
+                                                        num_attention_heads=v["heads"], image_size=v["image_size"],
+                                                        patch_size=v["patch_size"], hidden_act="gelu", projection_dim=cfg["embed_dim"],
+                                                        attn_implementation="eager")).eval()
+    hf = map_blocks("model.visual.transformer.", "vision_model.", v["layers"], v["width"])
+    hf.update({"vision_model.embeddings.patch_embedding.weight": sd["model.visual.conv1.weight"],
+               "vision_model.embeddings.class_embedding": sd["model.visual.class_embedding"],
+               "vision_model.embeddings.position_embedding.weight": sd["model.visual.positional_embedding"],
+               "vision_model.pre_layrnorm.weight": sd["model.visual.ln_pre.weight"], "vision_model.pre_layrnorm.bias": sd["model.visual.ln_pre.bias"],
+               "vision_model.post_layernorm.weight": sd["model.visual.ln_post.weight"], "vision_model.post_layernorm.bias": sd["model.visual.ln_post.bias"],
+               "visual_projection.weight": sd["model.visual.proj"].t().contiguous()})
+    missing, unexpected = vm.load_state_dict(hf, strict=False)
+    assert not unexpected and all("position_ids" in m for m in missing), (missing, unexpected)
+    img = torch.randn((2, 3, 56, 56), generator=g)
+    with torch.no_grad():
+        iref = vm(pixel_values=img).image_embeds
+    assert torch.allclose(OC.encode_image(sd, img, cfg), iref, atol=2e-4, rtol=1e-4)
