@@ -88,11 +88,11 @@ __global__ void __launch_bounds__(128) dwconv_gelu_kernel(const bf16* __restrict
                                                           int h, int w, int c, int apply_gelu) {
   const int g8 = c / 8;
   const int nxs = (w + S - 1) / S;
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(nb) * h * nxs * g8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // the launcher guarantees total < 2^31: 32-bit div / mod
+  const unsigned total = static_cast<unsigned>(nb) * h * nxs * g8;
   if (idx >= total) return;
   const int cg = static_cast<int>(idx % g8);
-  long long r = idx / g8;
+  unsigned r = idx / g8;
   const int xs = static_cast<int>(r % nxs); r /= nxs;
   const int y = static_cast<int>(r % h);
   const long long n = r / h;
@@ -155,18 +155,20 @@ __global__ void __launch_bounds__(128) dwconv_gelu_pair_kernel(const bf16* __res
                                                                int nb, int h, int w, int c, int apply_gelu) {
   const int c2n = c / 2;
   const int nxs = (w + S - 1) / S;
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(nb) * h * nxs * c2n;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // the launcher guarantees total < 2^31: 32-bit div / mod
+  const unsigned total = static_cast<unsigned>(nb) * h * nxs * c2n;
   if (idx >= total) return;
   const int cp = static_cast<int>(idx % c2n);
-  long long r = idx / c2n;
+  unsigned r = idx / c2n;
   const int xs = static_cast<int>(r % nxs); r /= nxs;
   const int y = static_cast<int>(r % h);
   const long long n = r / h;
   const int x0 = xs * S;
   constexpr int R = K / 2;
-  const long long ldw = ld_in / 2;  // pixel stride in 32-bit words
+  const int ldw = static_cast<int>(ld_in / 2);  // pixel stride in 32-bit words (32-bit: one IMAD.WIDE per address)
   const uint32_t* wt32 = reinterpret_cast<const uint32_t*>(wt) + cp;
+  // strips whose whole input window lies inside the row take the predicate-free path
+  const bool interior = (x0 - R >= 0) && (x0 + S - 1 + R < w);
 
   unsigned long long acc[S];
 #pragma unroll
@@ -176,16 +178,23 @@ __global__ void __launch_bounds__(128) dwconv_gelu_pair_kernel(const bf16* __res
   for (int ky = 0; ky < K; ++ky) {
     const int iy = y + ky - R;
     if (iy < 0 || iy >= h) continue;
-    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(x + ((n * h + iy) * static_cast<long long>(w)) * ld_in) + cp;
+    // first word of the window (may lie left of the row start for edge strips: only dereferenced when in range)
+    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(x + ((n * h + iy) * static_cast<long long>(w)) * ld_in) + cp +
+                         static_cast<long long>(x0 - R) * ldw;
     uint32_t pk[S + K - 1];
+    if (interior) {
 #pragma unroll
-    for (int i = 0; i < S + K - 1; ++i) {
-      const int ix = x0 - R + i;
-      pk[i] = (ix >= 0 && ix < w) ? __ldg(rowp + static_cast<long long>(ix) * ldw) : 0u;
+      for (int i = 0; i < S + K - 1; ++i) pk[i] = __ldg(p0 + i * ldw);
+    } else {
+#pragma unroll
+      for (int i = 0; i < S + K - 1; ++i) {
+        const int ix = x0 - R + i;
+        pk[i] = (ix >= 0 && ix < w) ? __ldg(p0 + i * ldw) : 0u;
+      }
     }
     unsigned long long wv[K];
 #pragma unroll
-    for (int kx = 0; kx < K; ++kx) wv[kx] = bf2_to_f2(__ldg(wt32 + static_cast<long long>(ky * K + kx) * c2n));
+    for (int kx = 0; kx < K; ++kx) wv[kx] = bf2_to_f2(__ldg(wt32 + (ky * K + kx) * c2n));
 #pragma unroll
     for (int i = 0; i < S + K - 1; ++i) {
       const unsigned long long v = bf2_to_f2(pk[i]);
@@ -249,24 +258,28 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const bf16* __restr
   }
 }
 
-// glob[b, ch] = act(sum_chunks partial / t)
-__global__ void colmean_finalize_kernel(const float* __restrict__ partial, float* __restrict__ glob, int nb, int nchunks,
-                                        int c, float inv_t, int apply_gelu) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nb * c) return;
-  const int b = idx / c, ch = idx % c;
-  const float* p = partial + static_cast<long long>(b) * nchunks * c + ch;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int k = 0;
-  for (; k + 3 < nchunks; k += 4) {  // independent loads; the summation order is fixed -> deterministic
-    a0 += p[static_cast<long long>(k) * c];
-    a1 += p[static_cast<long long>(k + 1) * c];
-    a2 += p[static_cast<long long>(k + 2) * c];
-    a3 += p[static_cast<long long>(k + 3) * c];
+// glob[b, ch] = act(sum_chunks partial / t). grid (c / 32, nb), block (32 channels, 32 chunk lanes): every lane adds
+// its strided share of the chunks, then a fixed-order shared-memory tree -> deterministic, and ~nchunks/32 dependent
+// loads per thread instead of nchunks.
+__global__ void __launch_bounds__(1024) colmean_finalize_kernel(const float* __restrict__ partial, float* __restrict__ glob,
+                                                                int nchunks, int c, float inv_t, int apply_gelu) {
+  __shared__ float red[32][33];
+  const int ch = blockIdx.x * 32 + threadIdx.x;
+  const int b = blockIdx.y;
+  float a = 0.f;
+  if (ch < c) {
+    const float* p = partial + static_cast<long long>(b) * nchunks * c + ch;
+    for (int k = threadIdx.y; k < nchunks; k += 32) a += p[static_cast<long long>(k) * c];
   }
-  for (; k < nchunks; ++k) a0 += p[static_cast<long long>(k) * c];
-  float a = ((a0 + a1) + (a2 + a3)) * inv_t;
-  glob[idx] = apply_gelu ? gelu_erf(a) : a;
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < c) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[k][threadIdx.x];
+    t *= inv_t;
+    glob[b * c + ch] = apply_gelu ? gelu_erf(t) : t;
+  }
 }
 
 // ------------------------------------------------------------------ focal modulation
@@ -326,66 +339,86 @@ __global__ void mul_rows_kernel(const bf16* __restrict__ a, long long ld_a, cons
 }
 
 // ------------------------------------------------------------------ LayerNorm (+ residual)
-// out[row] = res[row] + LN(x[row]) * w + b ; one warp per row, row held in registers (d <= 2048, d % 8 == 0),
-// statistics in fp32, two passes over the registers (mean, then centred variance).
-constexpr int LN_MAXV = 8;
+// out[row] = res[row] + LN(x[row]) * w + b ; one warp per ROWS rows, rows held in registers (d <= 256 * MAXV, d % 8 == 0),
+// statistics in fp32, two passes over the registers (mean, then centred variance). Every global load of the warp's
+// rows (x AND the residual) is issued before the first reduction, so a warp has ROWS * MAXV * 2 loads in flight.
+template <int MAXV, int ROWS>
 __global__ void __launch_bounds__(256) layernorm_add_kernel(const bf16* __restrict__ x, long long ldx,
                                                             const bf16* __restrict__ w, const bf16* __restrict__ b,
                                                             const bf16* __restrict__ res, long long ldr,
                                                             bf16* __restrict__ out, long long ldo, long long rows, int d,
                                                             float eps) {
-  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long row0 = (blockIdx.x * 8ll + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nvec = d / 8;
-  uint4 u[LN_MAXV];
-  float sum = 0.f;
+  uint4 u[ROWS][MAXV], ur[ROWS][MAXV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int v = lane + 32 * i;
-    u[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (v < nvec) {
-      u[i] = ldg16(x + row * ldx + v * 8);
-      float2 f;
-      f = unpack_bf16(u[i].x); sum += f.x + f.y;
-      f = unpack_bf16(u[i].y); sum += f.x + f.y;
-      f = unpack_bf16(u[i].z); sum += f.x + f.y;
-      f = unpack_bf16(u[i].w); sum += f.x + f.y;
+  for (int r = 0; r < ROWS; ++r) {
+    const bool live = row0 + r < rows;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + 32 * i;
+      u[r][i] = make_uint4(0u, 0u, 0u, 0u);
+      ur[r][i] = make_uint4(0u, 0u, 0u, 0u);
+      if (live && v < nvec) {
+        u[r][i] = ldg16(x + (row0 + r) * ldx + v * 8);
+        if (res) ur[r][i] = ldg16(res + (row0 + r) * ldr + v * 8);
+      }
     }
   }
-  const float mean = warp_sum(sum) / static_cast<float>(d);
-  float sq = 0.f;
+  float mean[ROWS], rstd[ROWS];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int v = lane + 32 * i;
-    if (v < nvec) {
+  for (int r = 0; r < ROWS; ++r) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
       float2 f;
-      f = unpack_bf16(u[i].x); sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
-      f = unpack_bf16(u[i].y); sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
-      f = unpack_bf16(u[i].z); sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
-      f = unpack_bf16(u[i].w); sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+      f = unpack_bf16(u[r][i].x); sum += f.x + f.y;
+      f = unpack_bf16(u[r][i].y); sum += f.x + f.y;
+      f = unpack_bf16(u[r][i].z); sum += f.x + f.y;
+      f = unpack_bf16(u[r][i].w); sum += f.x + f.y;
     }
+    mean[r] = warp_sum(sum) / static_cast<float>(d);
   }
-  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(d) + eps);
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int r = 0; r < ROWS; ++r) {
+    float sq = 0.f;
+    const float m = mean[r];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (lane + 32 * i < nvec) {
+        float2 f;
+        f = unpack_bf16(u[r][i].x); sq += (f.x - m) * (f.x - m) + (f.y - m) * (f.y - m);
+        f = unpack_bf16(u[r][i].y); sq += (f.x - m) * (f.x - m) + (f.y - m) * (f.y - m);
+        f = unpack_bf16(u[r][i].z); sq += (f.x - m) * (f.x - m) + (f.y - m) * (f.y - m);
+        f = unpack_bf16(u[r][i].w); sq += (f.x - m) * (f.x - m) + (f.y - m) * (f.y - m);
+      }
+    }
+    rstd[r] = rsqrtf(warp_sum(sq) / static_cast<float>(d) + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
     const int v = lane + 32 * i;
     if (v >= nvec) continue;
     const uint4 uw = ldg16(w + v * 8);
-    uint4 ub = make_uint4(0u, 0u, 0u, 0u), ur = make_uint4(0u, 0u, 0u, 0u);
+    uint4 ub = make_uint4(0u, 0u, 0u, 0u);
     if (b) ub = ldg16(b + v * 8);
-    if (res) ur = ldg16(res + row * ldr + v * 8);
-    const uint32_t xs[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
     const uint32_t ws[4] = {uw.x, uw.y, uw.z, uw.w};
     const uint32_t bs[4] = {ub.x, ub.y, ub.z, ub.w};
-    const uint32_t rs[4] = {ur.x, ur.y, ur.z, ur.w};
-    uint32_t os[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 fx = unpack_bf16(xs[j]), fw = unpack_bf16(ws[j]), fb = unpack_bf16(bs[j]), fr = unpack_bf16(rs[j]);
-      os[j] = pack_bf16(fr.x + (fx.x - mean) * rstd * fw.x + fb.x, fr.y + (fx.y - mean) * rstd * fw.y + fb.y);
+    for (int r = 0; r < ROWS; ++r) {
+      if (row0 + r >= rows) break;
+      const uint32_t xs[4] = {u[r][i].x, u[r][i].y, u[r][i].z, u[r][i].w};
+      const uint32_t rs[4] = {ur[r][i].x, ur[r][i].y, ur[r][i].z, ur[r][i].w};
+      uint32_t os[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fx = unpack_bf16(xs[j]), fw = unpack_bf16(ws[j]), fb = unpack_bf16(bs[j]), fr = unpack_bf16(rs[j]);
+        os[j] = pack_bf16(fr.x + (fx.x - mean[r]) * rstd[r] * fw.x + fb.x, fr.y + (fx.y - mean[r]) * rstd[r] * fw.y + fb.y);
+      }
+      *reinterpret_cast<uint4*>(out + (row0 + r) * ldo + v * 8) = make_uint4(os[0], os[1], os[2], os[3]);
     }
-    *reinterpret_cast<uint4*>(out + row * ldo + v * 8) = make_uint4(os[0], os[1], os[2], os[3]);
   }
 }
 
@@ -436,7 +469,7 @@ static int launch_dwconv_pair(const void* x, int64_t ld_in, const void* wt, void
   bf16* op = reinterpret_cast<bf16*>(out);
   // 32-pixel strips re-read the fewest halo columns but need ~250 registers; they pay off only when there are
   // enough strips to fill the machine several times over and the kernel is small enough not to spill
-  const bool wide = g_dwconv_impl == 3 || (g_dwconv_impl == 0 && K <= 7 && t32 >= 148ll * 2048);
+  const bool wide = g_dwconv_impl == 3;  // measured (profiles/r01_focalnet_dwconv_variants.jsonl): 16-pixel strips win at every k
   if (wide) {
     dwconv_gelu_pair_kernel<K, 32><<<static_cast<unsigned>((t32 + 127) / 128), 128, 0, stream>>>(xp, ld_in, wp, op, (int)nb,
                                                                                                   (int)h, (int)w, (int)c, act);
@@ -454,9 +487,12 @@ extern "C" int vb200_dwconv_nhwc(const void* x, int64_t ld_in, const void* wt, v
   VB_CHECK_ARG(x && wt && out && nb > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && ld_in % 8 == 0 && ld_in >= c);
   VB_CHECK_ARG(aligned16(x) && aligned16(wt) && aligned16(out));
   VB_CHECK_ARG(act == VB_ACT_NONE || act == VB_ACT_GELU);
-  VB_CHECK_ARG(nb * h * ((w + 3) / 4) * (c / 8) < (1ll << 31) * 128);
+  VB_CHECK_ARG(nb * h * ((w + 3) / 4) * (c / 2) < (1ll << 31) - 256);  // thread indices of every variant fit 32 bits
+  VB_CHECK_ARG(nb * h * w * ld_in < (1ll << 33));
   const int g = act == VB_ACT_GELU ? 1 : 0;
-  if (g_dwconv_impl != 1) {
+  // automatic: k = 3 is HBM/L2-bound and the 16-byte loads of the 8-channel kernel win (24 vs 32 us at [256^2, 192]);
+  // k >= 5 is instruction-bound and the channel-pair kernel wins (94 vs 119 us at k = 9)
+  if (g_dwconv_impl >= 2 || (g_dwconv_impl == 0 && k >= 5)) {
     switch (k) {
       case 3: return launch_dwconv_pair<3>(x, ld_in, wt, out, nb, h, w, c, g, stream);
       case 5: return launch_dwconv_pair<5>(x, ld_in, wt, out, nb, h, w, c, g, stream);
@@ -500,10 +536,8 @@ extern "C" int vb200_colmean(const void* x, float* out, int64_t nb, int64_t t, i
                                                                            reinterpret_cast<float*>(workspace), t, (int)c,
                                                                            rows_per_chunk);
   VB_LAUNCH_CHECK();
-  const int total = static_cast<int>(nb * c);
-  colmean_finalize_kernel<<<(total + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float*>(workspace), out, (int)nb,
-                                                                   nchunks, (int)c, 1.0f / static_cast<float>(t),
-                                                                   act == VB_ACT_GELU ? 1 : 0);
+  colmean_finalize_kernel<<<dim3(static_cast<unsigned>((c + 31) / 32), (unsigned)nb), dim3(32, 32), 0, stream>>>(
+      reinterpret_cast<const float*>(workspace), out, nchunks, (int)c, 1.0f / static_cast<float>(t), act == VB_ACT_GELU ? 1 : 0);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
@@ -542,13 +576,20 @@ extern "C" int vb200_mul_rows(const void* a, int64_t ld_a, const void* b, int64_
 extern "C" int vb200_layernorm_add(const void* x, int64_t ldx, const void* weight, const void* bias, const void* residual,
                                    int64_t ldr, void* out, int64_t ldo, int64_t rows, int64_t d, float eps,
                                    cudaStream_t stream) {
-  VB_CHECK_ARG(x && weight && out && rows >= 0 && d > 0 && d % 8 == 0 && d <= 8 * 32 * LN_MAXV);
+  VB_CHECK_ARG(x && weight && out && rows >= 0 && d > 0 && d % 8 == 0 && d <= 2048);
   VB_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0 && (residual == nullptr || ldr % 8 == 0));
   VB_CHECK_ARG(aligned16(x) && aligned16(weight) && aligned16(out) && aligned16(bias) && aligned16(residual));
   if (rows == 0) return VB_OK;
-  layernorm_add_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
-      reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(weight), reinterpret_cast<const bf16*>(bias),
-      reinterpret_cast<const bf16*>(residual), ldr, reinterpret_cast<bf16*>(out), ldo, rows, (int)d, eps);
+  const bf16* xp = reinterpret_cast<const bf16*>(x);
+  const bf16* wp = reinterpret_cast<const bf16*>(weight);
+  const bf16* bp = reinterpret_cast<const bf16*>(bias);
+  const bf16* rp = reinterpret_cast<const bf16*>(residual);
+  bf16* op = reinterpret_cast<bf16*>(out);
+  auto grid = [&](int rows_per_warp) { return static_cast<unsigned>((rows + 8ll * rows_per_warp - 1) / (8ll * rows_per_warp)); };
+  if (d <= 256) layernorm_add_kernel<1, 4><<<grid(4), 256, 0, stream>>>(xp, ldx, wp, bp, rp, ldr, op, ldo, rows, (int)d, eps);
+  else if (d <= 512) layernorm_add_kernel<2, 4><<<grid(4), 256, 0, stream>>>(xp, ldx, wp, bp, rp, ldr, op, ldo, rows, (int)d, eps);
+  else if (d <= 1024) layernorm_add_kernel<4, 2><<<grid(2), 256, 0, stream>>>(xp, ldx, wp, bp, rp, ldr, op, ldo, rows, (int)d, eps);
+  else layernorm_add_kernel<8, 1><<<grid(1), 256, 0, stream>>>(xp, ldx, wp, bp, rp, ldr, op, ldo, rows, (int)d, eps);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
