@@ -36,9 +36,13 @@ class DiagonalGaussianDistribution:
         if self.deterministic:
             self.var = self.std = torch.zeros_like(self.mean)
 
-    def sample(self, generator=None):
-        noise = torch.randn(self.mean.shape, device=self.mean.device, dtype=self.mean.dtype, generator=generator)
-        return self.mean + self.std * noise
+    def sample(self, generator=None, noise=None):
+        """mean + std * N(0, 1); `noise` (same shape) may be supplied for reproducible comparisons, `generator` may be
+        a CPU or device generator."""
+        if noise is None:
+            gdev = generator.device if generator is not None else self.mean.device
+            noise = torch.randn(self.mean.shape, device=gdev, dtype=self.mean.dtype, generator=generator)
+        return self.mean + self.std * noise.to(self.mean.device)
 
     def mode(self):
         return self.mean
@@ -200,9 +204,9 @@ class AutoencoderKL:
     def encode(self, x):
         return DiagonalGaussianDistribution(self._encode_moments(x))
 
-    def encode_firsr_stage(self, x, scale_factor=1.0, generator=None):
+    def encode_firsr_stage(self, x, scale_factor=1.0, generator=None, noise=None):
         """(sic) autoencoder.py:85-90: scale_factor * posterior.sample()."""
-        return scale_factor * self.encode(x).sample(generator)
+        return scale_factor * self.encode(x).sample(generator, noise)
 
     @torch.no_grad()
     def decode(self, z, **kwargs):
