@@ -363,6 +363,36 @@ def gligen_unet_shapes(cfg):
     return s
 
 
+def openclip_shapes(cfg):
+    """open_clip CLIP state-dict names / shapes under the embedder's `model.` attribute (cfg as clip_embedder.VIT_H_14)."""
+    s = {}
+    t, v, e = cfg["text"], cfg["vision"], cfg["embed_dim"]
+
+    def blocks(p, n, d, mlp):
+        for i in range(n):
+            q = p + f"resblocks.{i}."
+            s[q + "attn.in_proj_weight"], s[q + "attn.in_proj_bias"] = [3 * d, d], [3 * d]
+            s[q + "attn.out_proj.weight"], s[q + "attn.out_proj.bias"] = [d, d], [d]
+            for n_ in ("ln_1.", "ln_2."):
+                s[q + n_ + "weight"], s[q + n_ + "bias"] = [d], [d]
+            s[q + "mlp.c_fc.weight"], s[q + "mlp.c_fc.bias"] = [mlp, d], [mlp]
+            s[q + "mlp.c_proj.weight"], s[q + "mlp.c_proj.bias"] = [d, mlp], [d]
+
+    d = t["width"]
+    s["model.token_embedding.weight"], s["model.positional_embedding"] = [t["vocab_size"], d], [t["context_length"], d]
+    blocks("model.transformer.", t["layers"], d, 4 * d)
+    s["model.ln_final.weight"], s["model.ln_final.bias"], s["model.text_projection"] = [d], [d], [d, e]
+    d = v["width"]
+    npatch = (v["image_size"] // v["patch_size"]) ** 2
+    s["model.visual.conv1.weight"] = [d, 3, v["patch_size"], v["patch_size"]]
+    s["model.visual.class_embedding"], s["model.visual.positional_embedding"] = [d], [npatch + 1, d]
+    for n_ in ("ln_pre.", "ln_post."):
+        s["model.visual." + n_ + "weight"], s["model.visual." + n_ + "bias"] = [d], [d]
+    blocks("model.visual.transformer.", v["layers"], d, v["mlp"])
+    s["model.visual.proj"] = [d, e]
+    return s
+
+
 def random_state_dict(shapes, device, seed=0, std=0.02):
     """N(0, std) weights, unit norm gains, zero biases, generated on `device`."""
     g = torch.Generator(device=device).manual_seed(seed)
