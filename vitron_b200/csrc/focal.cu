@@ -490,9 +490,10 @@ extern "C" int vb200_dwconv_nhwc(const void* x, int64_t ld_in, const void* wt, v
   VB_CHECK_ARG(nb * h * ((w + 3) / 4) * (c / 2) < (1ll << 31) - 256);  // thread indices of every variant fit 32 bits
   VB_CHECK_ARG(nb * h * w * ld_in < (1ll << 33));
   const int g = act == VB_ACT_GELU ? 1 : 0;
-  // automatic: k = 3 is HBM/L2-bound and the 16-byte loads of the 8-channel kernel win (24 vs 32 us at [256^2, 192]);
-  // k >= 5 is instruction-bound and the channel-pair kernel wins (94 vs 119 us at k = 9)
-  if (g_dwconv_impl >= 2 || (g_dwconv_impl == 0 && k >= 5)) {
+  // automatic (measured, profiles/r01_focalnet_dwconv_variants.jsonl, [256^2, 192]): k = 3 / 5 -> the 16-byte loads of the
+  // 8-channel kernel win (23 vs 26 us, 37 vs 41 us); k >= 7 is instruction-bound and the channel-pair kernel wins
+  // (59 vs 73 us, 82 vs 122 us)
+  if (g_dwconv_impl >= 2 || (g_dwconv_impl == 0 && k >= 7)) {
     switch (k) {
       case 3: return launch_dwconv_pair<3>(x, ld_in, wt, out, nb, h, w, c, g, stream);
       case 5: return launch_dwconv_pair<5>(x, ld_in, wt, out, nb, h, w, c, g, stream);

@@ -38,10 +38,10 @@ vit_embed_ln_kernel(const bf16* __restrict__ patch_out, const bf16* __restrict__
   const long long img = row / (npatch + 1);
   const bf16* src = tok == 0 ? cls : patch_out + (img * npatch + tok - 1) * d;
   const bf16* pr = pos + static_cast<long long>(tok) * d;
-  float v[8];  // d <= 1024 -> 8 per thread at 128 threads
+  float v[16];  // d <= 2048 -> 16 per thread at 128 threads (ViT-H/14: 1280)
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const int c = threadIdx.x + i * 128;
     v[i] = c < d ? __bfloat162float(__float2bfloat16(__bfloat162float(src[c]) + __bfloat162float(pr[c]))) : 0.f;
     s += v[i];
@@ -53,7 +53,7 @@ vit_embed_ln_kernel(const bf16* __restrict__ patch_out, const bf16* __restrict__
   __syncthreads();
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const int c = threadIdx.x + i * 128;
     if (c < d) { const float t = v[i] - mean; q += t * t; }
   }
@@ -62,7 +62,7 @@ vit_embed_ln_kernel(const bf16* __restrict__ patch_out, const bf16* __restrict__
   __syncthreads();
   const float rstd = rsqrtf((red[0] + red[1] + red[2] + red[3]) / d + eps);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const int c = threadIdx.x + i * 128;
     if (c < d)
       out[row * d + c] = __float2bfloat16((v[i] - mean) * rstd * __bfloat162float(w[c]) + __bfloat162float(b[c]));
@@ -286,7 +286,7 @@ extern "C" int vb200_patchify(const void* pixels, int in_is_fp32, void* out, int
 extern "C" int vb200_vit_embed_ln(const void* patch_out, const void* cls, const void* pos, const void* ln_w,
                                   const void* ln_b, void* out, int64_t nb, int64_t npatch, int64_t d, float eps,
                                   cudaStream_t stream) {
-  VB_CHECK_ARG(patch_out && cls && pos && ln_w && ln_b && out && nb > 0 && npatch > 0 && d > 0 && d <= 1024);
+  VB_CHECK_ARG(patch_out && cls && pos && ln_w && ln_b && out && nb > 0 && npatch > 0 && d > 0 && d <= 2048);
   vit_embed_ln_kernel<<<static_cast<unsigned>(nb * (npatch + 1)), 128, 0, stream>>>(
       reinterpret_cast<const bf16*>(patch_out), reinterpret_cast<const bf16*>(cls), reinterpret_cast<const bf16*>(pos),
       reinterpret_cast<const bf16*>(ln_w), reinterpret_cast<const bf16*>(ln_b), reinterpret_cast<bf16*>(out),
