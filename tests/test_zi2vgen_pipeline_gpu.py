@@ -36,28 +36,42 @@ def test_image_to_video_chain_vs_oracle_chain(cuda):
     post_noise = torch.randn((1, 4, 8, 16), generator=g)
     noise = torch.randn((1, 4, F_, 8, 16), generator=g)
 
-    # ---- oracle chain (CPU fp32)
-    _, y_words = OC.encode_text(csd, tokens, ccfg, layer_idx=1)
-    _, y_neg = OC.encode_text(csd, neg, ccfg, layer_idx=1)
-    y_vis = OC.encode_image(csd, img_vit, ccfg).unsqueeze(1)
-    mean, _, std = V.encode_moments(vsd, img_vae, vfx["ddconfig"])
-    local = (scale * (mean + std * post_noise)).unsqueeze(2).repeat_interleave(F_, dim=2)
-    fps = torch.tensor([16])
-    kw = [dict(y=y_words, image=y_vis, local_image=local, fps=fps), dict(y=y_neg, image=torch.zeros_like(y_vis), local_image=local, fps=fps)]
-    omodel = lambda xt, t, **k: U.unet_forward(usd, ufx["cfg"], xt, t, **k)
-    lat = U.ddim_sample_loop(noise, omodel, kw, guide, steps) / scale
-    ref = V.decode(vsd, lat.permute(0, 2, 1, 3, 4).reshape(F_, 4, 8, 16), vfx["ddconfig"])
-    ref = ref.reshape(1, F_, 3, 32, 64).permute(0, 2, 1, 3, 4)
+    def oracle_chain(img_vit, img_vae, tokens, neg, post_noise, noise):
+        _, y_words = OC.encode_text(csd, tokens, ccfg, layer_idx=1)
+        _, y_neg = OC.encode_text(csd, neg, ccfg, layer_idx=1)
+        y_vis = OC.encode_image(csd, img_vit, ccfg).unsqueeze(1)
+        mean, _, std = V.encode_moments(vsd, img_vae, vfx["ddconfig"])
+        local = (scale * (mean + std * post_noise)).unsqueeze(2).repeat_interleave(F_, dim=2)
+        fps = torch.tensor([16])
+        kw = [dict(y=y_words, image=y_vis, local_image=local, fps=fps),
+              dict(y=y_neg, image=torch.zeros_like(y_vis), local_image=local, fps=fps)]
+        omodel = lambda xt, t, **k: U.unet_forward(usd, ufx["cfg"], xt, t, **k)
+        lat = U.ddim_sample_loop(noise, omodel, kw, guide, steps) / scale
+        ref = V.decode(vsd, lat.permute(0, 2, 1, 3, 4).reshape(F_, 4, 8, 16), vfx["ddconfig"])
+        return ref.reshape(1, F_, 3, 32, 64).permute(0, 2, 1, 3, 4)
 
-    # ---- product chain
     unet = UNetSD_I2VGen(**ufx["cfg"], device=cuda)
     unet.load_state_dict(usd)
     vae = AutoencoderKL(vfx["ddconfig"], 4, device=cuda).load_state_dict(vsd)
     clip = FrozenOpenCLIPTtxtVisualEmbedder(None, device=cuda, layer="penultimate", arch_cfg=ccfg).load_state_dict(csd)
     pipe = I2VGenXLPipeline(unet, vae, clip, scale_factor=scale, max_frames=F_, guide_scale=guide, ddim_timesteps=steps, decoder_bs=2)
-    video = pipe(img_vit, img_vae, tokens, neg, noise=noise, posterior_noise=post_noise)
-    assert tuple(video.shape) == (1, 3, F_, 32, 64) and bool(torch.isfinite(video).all())
-    got, r = video.float().cpu(), ref.float()
-    e_inf = ((got - r).abs().max() / (r.abs().max() + 1e-6)).item()
-    e_l2 = ((got - r).norm() / (r.norm() + 1e-6)).item()
-    assert e_inf < 0.10 and e_l2 < 0.08, (e_inf, e_l2)
+
+    def check(got, ref, what):
+        assert tuple(got.shape) == (1, 3, F_, 32, 64) and bool(torch.isfinite(got).all())
+        got, r = got.float().cpu(), ref.float()
+        e_inf = ((got - r).abs().max() / (r.abs().max() + 1e-6)).item()
+        e_l2 = ((got - r).norm() / (r.norm() + 1e-6)).item()
+        assert e_inf < 0.10 and e_l2 < 0.08, (what, e_inf, e_l2)
+
+    a1 = (img_vit, img_vae, tokens, neg, post_noise, noise)
+    check(pipe(img_vit, img_vae, tokens, neg, noise=noise, posterior_noise=post_noise), oracle_chain(*a1), "first video (graph capture)")
+    # second video: different image / prompts / noise through the SAME captured graph (conditioning rebound in place)
+    g2 = torch.Generator().manual_seed(77)
+    img_vit2, img_vae2 = torch.randn((1, 3, 56, 56), generator=g2), torch.randn((1, 3, 32, 64), generator=g2)
+    tokens2 = torch.randint(1, 511, (1, 77), generator=g2)
+    tokens2[0, 33], tokens2[0, 34:] = 511, 0
+    post2, noise2 = torch.randn((1, 4, 8, 16), generator=g2), torch.randn((1, 4, F_, 8, 16), generator=g2)
+    den = pipe._den
+    v2 = pipe(img_vit2, img_vae2, tokens2, neg, noise=noise2, posterior_noise=post2)
+    assert pipe._den is den, "the captured graph must be reused"
+    check(v2, oracle_chain(img_vit2, img_vae2, tokens2, neg, post2, noise2), "second video (rebound graph)")

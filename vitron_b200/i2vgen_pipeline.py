@@ -13,7 +13,7 @@ Every tensor between the stages stays on the device; the DDIM loop replays one C
 """
 import torch
 
-from .unet_i2vgen import DiffusionDDIM
+from .unet_i2vgen import DiffusionDDIM, GraphedCFGDenoiser
 
 BF16 = torch.bfloat16
 
@@ -29,6 +29,7 @@ class I2VGenXLPipeline:
         self.ddim_timesteps, self.decoder_bs, self.use_zero_infer, self.target_fps = ddim_timesteps, decoder_bs, use_zero_infer, target_fps
         self.use_graph = use_graph
         self.device = unet.device if hasattr(unet, "device") else torch.device("cuda")
+        self._den = None      # the captured CFG evaluation, reused across videos of the same shape (rebind)
 
     @torch.no_grad()
     def __call__(self, image_vit, image_vae, tokens, negative_tokens, noise=None, generator=None, posterior_noise=None):
@@ -47,9 +48,28 @@ class I2VGenXLPipeline:
         infer_img = torch.zeros_like(y_visual) if self.use_zero_infer else None      # black_image_feature :124
         model_kwargs = [dict(y=y_words, image=y_visual, local_image=local_image, fps=fps),
                         dict(y=zero_y_negative, image=infer_img, local_image=local_image, fps=fps)]
-        latents = self.diffusion.ddim_sample_loop(noise=noise.to(dev), model=self.unet, model_kwargs=model_kwargs,
-                                                  guide_scale=self.guide_scale, ddim_timesteps=self.ddim_timesteps, eta=0.0,
-                                                  use_graph=self.use_graph)
+        noise = noise.to(dev)
+        model = self.unet
+        if self.use_graph:
+            if self._den is not None and tuple(self._den.xt.shape) == tuple(noise.shape):
+                self._den.rebind(*model_kwargs)                       # same graph, new conditioning
+            else:
+                own = {}                                               # the denoiser owns static copies (local_image shared)
+
+                def static(d):
+                    out = {}
+                    for k, v in d.items():
+                        if torch.is_tensor(v):
+                            own.setdefault(id(v), v.clone())
+                            out[k] = own[id(v)]
+                        else:
+                            out[k] = v
+                    return out
+                self._den = GraphedCFGDenoiser(self.unet, static(model_kwargs[0]), static(model_kwargs[1]), self.guide_scale, noise,
+                                               torch.zeros((b,), dtype=torch.long, device=dev))
+            model = self._den
+        latents = self.diffusion.ddim_sample_loop(noise=noise, model=model, model_kwargs=model_kwargs,
+                                                  guide_scale=self.guide_scale, ddim_timesteps=self.ddim_timesteps, eta=0.0)
         latents = (1.0 / self.scale_factor) * latents                               # :200
         frames = latents.permute(0, 2, 1, 3, 4).reshape(b * self.max_frames, 4, h, w)   # 'b c f h w -> (b f) c h w'
         chunk = min(self.decoder_bs, frames.shape[0])

@@ -321,6 +321,22 @@ class UNetSD_I2VGen:
         self._adapter_cache = (key, out)
         return out
 
+    @torch.no_grad()
+    def refresh_adapter(self, local_image, batch, f, h, w):
+        """Recompute the cached local-image adapter output for a local_image whose storage was updated in place and write
+        it INTO the existing cache buffers: a captured CUDA graph that reads them (GraphedCFGDenoiser) stays valid."""
+        old = self._adapter_cache
+        self._adapter_cache = None
+        if local_image.ndim == 5 and local_image.size(2) > 1:
+            local_image = local_image[:, :, :1]
+        elif local_image.ndim != 5:
+            local_image = local_image.unsqueeze(2)
+        new = self._adapter(local_image, batch, f, h, w)
+        if old is not None and all(o.shape == n.shape for o, n in zip(old[1], new)):
+            for o, n in zip(old[1], new):
+                o.copy_(n)
+            self._adapter_cache = (self._adapter_cache[0], old[1])
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, x, t, y=None, image=None, local_image=None, masked=None, fps=None, video_mask=None,
@@ -376,6 +392,21 @@ class GraphedCFGDenoiser:
         self.t = t_like.detach().clone()
         self.graph = None
         self.out = None
+
+    @torch.no_grad()
+    def rebind(self, cond, uncond):
+        """New conditioning for the SAME captured graph (next video of a serving loop): the values are copied into the
+        static tensors the graph reads and the UNet's cached adapter output is refreshed in place. Shapes must match."""
+        seen = set()
+        for dst, src in ((self.cond, cond), (self.uncond, uncond)):
+            for k, v in dst.items():
+                if torch.is_tensor(v) and id(v) not in seen:
+                    seen.add(id(v))
+                    v.copy_(src[k].to(v.device))
+                elif v is None and src.get(k) is not None:
+                    raise ValueError(f"conditioning '{k}' was None when the graph was captured")
+        b, _, f, h, w = self.xt.shape
+        self.unet.refresh_adapter(self.cond["local_image"], b, f, h, w)
 
     def _eval(self):
         y = self.unet(self.xt, self.t, **self.cond).float().contiguous()
