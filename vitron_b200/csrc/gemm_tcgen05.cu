@@ -67,6 +67,8 @@ struct GemmParams {
   int act;            // VB_ACT_*
   int glu;            // VB_GLU_*
   int out_fp32;
+  int b_resident;     // > 0: small-K mode — the CTA keeps its n-block of B (all k-blocks) in shared memory for its whole
+                      // life and streams only A through a ring of `b_resident` stages (plain GEMM, no split-K)
   int swap;           // accumulator rows are output columns (decode / tiny-M path) -> workspace
   float* ws;          // split-K / swap workspace [splits, rows_c, cols_c] fp32
   long long ws_split_stride;
@@ -176,6 +178,12 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int unit) {
   TileCoord t;
+  if (p.b_resident) {  // n-block fixed per CTA (gridDim.x is a multiple of n_blocks): unit % n_blocks == blockIdx.x % n_blocks
+    t.split = 0;
+    t.n_blk = unit % p.n_blocks;
+    t.m_blk = unit / p.n_blocks;
+    return t;
+  }
   int tile = unit / p.splits;
   t.split = unit - tile * p.splits;
   // grouped rasterisation: 16 m-blocks wide so a wave of CTAs re-uses A and B tiles through L2
@@ -221,6 +229,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
   volatile int* fin_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // resident-B mode: B of this CTA's n-block has landed
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // BLOCK_N floats
 
   const int warp = threadIdx.x >> 5;
@@ -238,6 +247,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
     }
+    mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -253,7 +263,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    if (lane == 0 && p.b_resident) {
+      // ---- small-K mode: B[n-block] once, then only A tiles through a ring of p.b_resident 16 KB slots
+      uint8_t* a_ring = smem + p.num_k_blocks * B_BYTES;
+      if (static_cast<int>(blockIdx.x) < total_units) {
+        const int n_blk = static_cast<int>(blockIdx.x) % p.n_blocks;
+        mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(p.num_k_blocks) * B_BYTES);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb)
+          tma_load_2d(smem + kb * B_BYTES, &tmap_b, b_full, kb * BLOCK_K, n_blk * BLOCK_N);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        TileCoord t = decode_work(p, unit);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes);
+          tma_load_2d(a_ring + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, t.m_blk * BLOCK_M);
+          if (++stage == p.b_resident) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -295,6 +325,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int ring_stages = p.b_resident ? p.b_resident : STAGES;
+    const uint32_t a_ring = smem_u32(smem) + (p.b_resident ? p.num_k_blocks * B_BYTES : 0);
+    if (p.b_resident && static_cast<int>(blockIdx.x) < total_units) {
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+    }
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       TileCoord t = decode_work(p, unit);
       int k0, k1;
@@ -306,8 +342,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          const uint32_t sa = p.b_resident ? a_ring + stage * A_BYTES : smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = p.b_resident ? smem_u32(smem) + kb * B_BYTES : sa + A_BYTES;
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sb);
 #pragma unroll
@@ -319,7 +355,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (kb == k1 - 1) tc_commit(&tmem_full[acc]);
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == ring_stages) { stage = 0; phase ^= 1; }
       }
       if (k1 <= k0 && lane == 0) tc_commit(&tmem_full[acc]);  // degenerate (never for K>0)
       __syncwarp();
@@ -737,6 +773,13 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* 
   return r == CUDA_SUCCESS ? VB_OK : VB_ERR_DRIVER;
 }
 
+static int g_b_resident_mode = 0;  // 0 off, 1 automatic, 2 whenever structurally possible (parity tests)
+extern "C" int vb200_set_gemm_b_resident(int mode) {
+  const int prev = g_b_resident_mode;
+  if (mode >= 0 && mode <= 2) g_b_resident_mode = mode;
+  return prev;
+}
+
 template <int BN, int STAGES>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                       cudaStream_t stream) {
@@ -751,7 +794,22 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   }
   int units = p.m_blocks * p.n_blocks * p.splits;
   int grid = units < vb_num_sms() ? units : vb_num_sms();
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, tc, p);
+  GemmParams q = p;
+  q.b_resident = 0;
+  if (g_b_resident_mode != 0 && p.a_mode == 0 && p.splits == 1 && p.ws == nullptr && !p.swap && p.n_blocks <= vb_num_sms()) {
+    constexpr int A_B = BLOCK_M * BLOCK_K * 2, B_B = BN * BLOCK_K * 2, RING = STAGES * (A_B + B_B);
+    const long long left = static_cast<long long>(RING) - static_cast<long long>(p.num_k_blocks) * B_B;
+    int a_stages = left >= 2 * A_B ? static_cast<int>(left / A_B) : 0;
+    if (a_stages > STAGES) a_stages = STAGES;   // the barrier arrays hold STAGES entries
+    const int rgrid = (vb_num_sms() / p.n_blocks) * p.n_blocks;
+    // worth it when every CTA re-uses its B block over several m-blocks (mode 2 = whenever structurally possible: tests)
+    const bool pays = p.m_blocks * p.n_blocks >= 3 * rgrid;
+    if (a_stages >= 2 && (pays || g_b_resident_mode == 2)) {
+      q.b_resident = a_stages;
+      grid = units < rgrid ? ((units + p.n_blocks - 1) / p.n_blocks) * p.n_blocks : rgrid;
+    }
+  }
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, tc, q);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
