@@ -74,6 +74,8 @@ struct GemmParams {
   long long ws_split_stride;
   long long ws_ld;
   int c_box;          // > 0: bf16 output leaves through smem + TMA store in boxes of c_box (64 | 32) columns
+  int c_warp;         // 1: per-warp staging — every epilogue warp stores its own 32 x 32 chunk with its own TMA store,
+                      // no CTA-level barrier in the epilogue (plain GEMM, bf16 out, no GLU); tmap_c box = {32, 32}, 64B swizzle
   int* counters;      // one arrival counter per output tile (zero on entry, zero again on exit)
   int rows_c, cols_c; // extent of the output in C orientation (rows = tokens, cols = features)
 };
@@ -430,7 +432,131 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       } else {
         if constexpr (BLOCK_N >= 32) {
-          if (p.c_box > 0) {
+          if (p.c_warp) {
+            // -------- per-warp epilogue: TMEM chunk -> registers -> this warp's own 2 x 2 KB staging -> TMA store of a
+            // 32-row x 32-column box. No CTA-level barrier: with 3-12 k-steps per tile (K = 192-768) the tile time is
+            // the epilogue's latency chain, and the eight block-wide barriers per tile of the box path are part of it.
+            uint8_t* wbuf = cstage + (warp - 2) * 4096;
+            constexpr int NCHUNKS = BLOCK_N / 32;
+            const bf16* rb = nullptr;
+            if (p.rowbias != nullptr && orow >= 0) rb = p.rowbias + (orow / p.rowbias_rows) * static_cast<long long>(p.N);
+            const float rs = (p.rowscale != nullptr && orow >= 0) ? p.rowscale[orow] : 1.f;
+            const bf16* rrow = (p.residual != nullptr && orow >= 0) ? p.residual + orow * p.ldr + col0 : nullptr;
+            const bool res_vec = rrow != nullptr && (p.ldr & 7) == 0;
+            uint32_t v[32];
+            uint4 rnext[4];
+            auto issue = [&](int c) {
+              tmem_ld_32x32(taddr + c * 32, v);
+              if (res_vec && col0 + (c + 1) * 32 <= p.N) {
+                const uint4* rp = reinterpret_cast<const uint4*>(rrow + c * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rnext[q] = __ldg(rp + q);
+              }
+            };
+            if (ehalf < NCHUNKS) issue(ehalf);
+            int wb = 0;
+#pragma unroll 1
+            for (int ci = ehalf; ci < NCHUNKS; ci += 2) {
+              const int gc = col0 + ci * 32;
+              tmem_ld_wait();
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * rs;
+              uint4 rcur[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+              if (ci + 2 < NCHUNKS) issue(ci + 2);
+              const bool full = gc + 32 <= p.N && (p.N & 7) == 0;
+              if (p.bias != nullptr) {   // same address in every lane -> broadcast loads
+                if (full) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.bias + gc) + q);
+                    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                      const float2 b2 = unpack_bf16(uu[w]);
+                      f[q * 8 + 2 * w] += b2.x;
+                      f[q * 8 + 2 * w + 1] += b2.y;
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (gc + j < p.N) f[j] += __bfloat162float(p.bias[gc + j]);
+                }
+              }
+              if (rb != nullptr) {
+                if (full) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(rb + gc) + q);
+                    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                      const float2 r2 = unpack_bf16(uu[w]);
+                      f[q * 8 + 2 * w] += r2.x;
+                      f[q * 8 + 2 * w + 1] += r2.y;
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (gc + j < p.N) f[j] += __bfloat162float(rb[gc + j]);
+                }
+              }
+              if (p.act == VB_ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+              } else if (p.act == VB_ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = silu(f[j]);
+              } else if (p.act != VB_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+              }
+              if (rrow != nullptr) {
+                if (res_vec && gc + 32 <= p.N) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const uint32_t uu[4] = {rcur[q].x, rcur[q].y, rcur[q].z, rcur[q].w};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                      const float2 r2 = unpack_bf16(uu[w]);
+                      f[q * 8 + 2 * w] = fmaf(p.alpha, f[q * 8 + 2 * w], r2.x);
+                      f[q * 8 + 2 * w + 1] = fmaf(p.alpha, f[q * 8 + 2 * w + 1], r2.y);
+                    }
+                  }
+                } else {
+                  const bf16* rp = rrow + ci * 32;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (gc + j < p.N) f[j] = __bfloat162float(rp[j]) + p.alpha * f[j];
+                }
+              } else if (p.alpha != 1.0f) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+              }
+              if (lane == 0) bulk_wait_read<1>();        // the store that last used this buffer has read it
+              __syncwarp();
+              uint8_t* buf = wbuf + (wb & 1) * 2048;
+              ++wb;
+              uint8_t* rowp = buf + lane * 64;            // row = lane, 64 bytes, 64B swizzle: piece ^= (row >> 1) & 3
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const int piece = (j >> 3) ^ ((lane >> 1) & 3);
+                *reinterpret_cast<uint4*>(rowp + piece * 16) =
+                    make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]), pack_bf16(f[j + 4], f[j + 5]),
+                               pack_bf16(f[j + 6], f[j + 7]));
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (gc < p.N) tma_store_2d(&tmap_c, buf, gc, t.m_blk * BLOCK_M + quad * 32);
+                bulk_commit();
+              }
+            }
+          } else if (p.c_box > 0) {
             // -------- fused epilogue -> 128B/64B-swizzled smem tile -> TMA store (coalesced, clipped by the
             // tensor map at the ragged edges; conv: one 4-D box per pixel tile, mirroring the A load).
             // The two warps of a TMEM lane quadrant take alternate 32-column accumulator chunks; each keeps
@@ -585,7 +711,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         }
-        if (BLOCK_N < 32 || p.c_box == 0) {
+        if (BLOCK_N < 32 || (p.c_box == 0 && !p.c_warp)) {
         // -------- fused epilogue straight to the output tensor
         const bf16* rb = nullptr;
         if (p.rowbias != nullptr && orow >= 0)
@@ -720,6 +846,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   if (threadIdx.x == 64 && p.c_box > 0) bulk_wait<0>();  // staged tiles must be read out before smem goes away
+  if (p.c_warp && warp >= 2 && lane == 0) bulk_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -771,6 +898,13 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* 
                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? VB_OK : VB_ERR_DRIVER;
+}
+
+static int g_epilogue_mode = 0;  // 0 = CTA-staged 64-column boxes, 1 = per-warp 32 x 32 boxes (plain bf16 GEMM)
+extern "C" int vb200_set_gemm_epilogue(int mode) {
+  const int prev = g_epilogue_mode;
+  if (mode == 0 || mode == 1) g_epilogue_mode = mode;
+  return prev;
 }
 
 static int g_b_resident_mode = 0;  // 0 off, 1 automatic, 2 whenever structurally possible (parity tests)
@@ -988,6 +1122,14 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   if (int r = make_tmap(&tb, W, 2, dB, sB, bB, estr2)) return r;
   CUtensorMap tc = ta;
   p.c_box = c_box_for(bn, epi->glu, epi->out_fp32, ldo, out);
+  if (g_epilogue_mode == 1 && p.c_box > 0 && epi->glu == VB_GLU_NONE && bn >= 32) {
+    p.c_warp = 1;
+    p.c_box = 0;
+    uint64_t dC[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    uint64_t sC[1] = {static_cast<uint64_t>(ldo) * 2};
+    uint32_t bC[2] = {32, 32};
+    if (int r = make_tmap(&tc, out, 2, dC, sC, bC, estr2, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+  }
   if (p.c_box > 0) {
     const long long n_out = epi->glu != VB_GLU_NONE ? N / 2 : N;
     uint64_t dC[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
