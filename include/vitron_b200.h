@@ -66,15 +66,6 @@ int vb200_set_pdl(int enable);
  * 64/128 with >= 96 query rows, mma.sync otherwise), 1 = mma.sync only, 2 = tcgen05 whenever supported.
  * Both kernels compute the same function; the switch exists so the parity tests can pin each of them. */
 int vb200_set_attention_impl(int impl);
-/* Small-K GEMM mode of vb200_gemm_bf16: when all k-blocks of a CTA's n-block of the weight matrix fit in shared memory
- * next to an A ring, the CTA loads them ONCE and streams only A tiles (instead of re-fetching B from L2 for every
- * 128-row tile). 0 = off, 1 = automatic (enough m-blocks per CTA to pay off), 2 = whenever structurally possible (lets
- * the parity tests pin the mode on small shapes). Same function, same accumulation order. Returns the previous mode. */
-int vb200_set_gemm_b_resident(int mode);
-/* Epilogue variant of the plain bf16 GEMM (no GLU): 0 = the 8 epilogue warps fill one 128-row x 64-column staging box,
- * one thread stores it (two CTA-level barriers per box); 1 = every warp stages and TMA-stores its own 32 x 32 chunk, no
- * CTA-level barrier. Same values. Returns the previous mode. */
-int vb200_set_gemm_epilogue(int mode);
 /* Diagnostics for the tcgen05 attention kernel: every mbarrier wait in it is bounded (~0.5 s); if one expires
  * the CTA drains instead of hanging the GPU and records where. out3 = {site id (0 = never fired), packed block
  * index, thread}; reading clears the record. Synchronises the device. */

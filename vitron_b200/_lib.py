@@ -33,8 +33,6 @@ SIGNATURES = {
     "vb200_device_ok": (_i32, []),
     "vb200_set_pdl": (_i32, [_i32]),
     "vb200_set_attention_impl": (_i32, [_i32]),
-    "vb200_set_gemm_b_resident": (_i32, [_i32]),
-    "vb200_set_gemm_epilogue": (_i32, [_i32]),
     "vb200_attention_watchdog": (_i32, [_p]),
     "vb200_attention_tc_occupancy": (_i32, [_i32]),
     "vb200_gemm_bf16_workspace_size": (_sz, [_i64, _i64, _i64]),
@@ -98,12 +96,6 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
-    mode = os.environ.get("VB200_GEMM_B_RESIDENT")  # tuning / test knob for the small-K GEMM mode (see the header)
-    if mode is not None:
-        lib.vb200_set_gemm_b_resident(int(mode))
-    mode = os.environ.get("VB200_GEMM_EPILOGUE")     # 0 = CTA-staged boxes, 1 = per-warp boxes
-    if mode is not None:
-        lib.vb200_set_gemm_epilogue(int(mode))
     return lib
 
 

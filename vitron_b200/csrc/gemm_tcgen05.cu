@@ -67,15 +67,11 @@ struct GemmParams {
   int act;            // VB_ACT_*
   int glu;            // VB_GLU_*
   int out_fp32;
-  int b_resident;     // > 0: small-K mode — the CTA keeps its n-block of B (all k-blocks) in shared memory for its whole
-                      // life and streams only A through a ring of `b_resident` stages (plain GEMM, no split-K)
   int swap;           // accumulator rows are output columns (decode / tiny-M path) -> workspace
   float* ws;          // split-K / swap workspace [splits, rows_c, cols_c] fp32
   long long ws_split_stride;
   long long ws_ld;
   int c_box;          // > 0: bf16 output leaves through smem + TMA store in boxes of c_box (64 | 32) columns
-  int c_warp;         // 1: per-warp staging — every epilogue warp stores its own 32 x 32 chunk with its own TMA store,
-                      // no CTA-level barrier in the epilogue (plain GEMM, bf16 out, no GLU); tmap_c box = {32, 32}, 64B swizzle
   int* counters;      // one arrival counter per output tile (zero on entry, zero again on exit)
   int rows_c, cols_c; // extent of the output in C orientation (rows = tokens, cols = features)
 };
@@ -180,12 +176,6 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int unit) {
   TileCoord t;
-  if (p.b_resident) {  // n-block fixed per CTA (gridDim.x is a multiple of n_blocks): unit % n_blocks == blockIdx.x % n_blocks
-    t.split = 0;
-    t.n_blk = unit % p.n_blocks;
-    t.m_blk = unit / p.n_blocks;
-    return t;
-  }
   int tile = unit / p.splits;
   t.split = unit - tile * p.splits;
   // grouped rasterisation: 16 m-blocks wide so a wave of CTAs re-uses A and B tiles through L2
@@ -231,7 +221,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
   volatile int* fin_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
-  uint64_t* b_full = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // resident-B mode: B of this CTA's n-block has landed
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // BLOCK_N floats
 
   const int warp = threadIdx.x >> 5;
@@ -249,7 +238,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
     }
-    mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -265,27 +253,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0 && p.b_resident) {
-      // ---- small-K mode: B[n-block] once, then only A tiles through a ring of p.b_resident 16 KB slots
-      uint8_t* a_ring = smem + p.num_k_blocks * B_BYTES;
-      if (static_cast<int>(blockIdx.x) < total_units) {
-        const int n_blk = static_cast<int>(blockIdx.x) % p.n_blocks;
-        mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(p.num_k_blocks) * B_BYTES);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb)
-          tma_load_2d(smem + kb * B_BYTES, &tmap_b, b_full, kb * BLOCK_K, n_blk * BLOCK_N);
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        TileCoord t = decode_work(p, unit);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes);
-          tma_load_2d(a_ring + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, t.m_blk * BLOCK_M);
-          if (++stage == p.b_resident) { stage = 0; phase ^= 1; }
-        }
-      }
-    } else if (lane == 0) {
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -327,12 +295,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int ring_stages = p.b_resident ? p.b_resident : STAGES;
-    const uint32_t a_ring = smem_u32(smem) + (p.b_resident ? p.num_k_blocks * B_BYTES : 0);
-    if (p.b_resident && static_cast<int>(blockIdx.x) < total_units) {
-      mbar_wait(b_full, 0);
-      tc_fence_after();
-    }
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       TileCoord t = decode_work(p, unit);
       int k0, k1;
@@ -344,8 +306,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = p.b_resident ? a_ring + stage * A_BYTES : smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = p.b_resident ? smem_u32(smem) + kb * B_BYTES : sa + A_BYTES;
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sb);
 #pragma unroll
@@ -357,7 +319,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (kb == k1 - 1) tc_commit(&tmem_full[acc]);
         }
         __syncwarp();
-        if (++stage == ring_stages) { stage = 0; phase ^= 1; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (k1 <= k0 && lane == 0) tc_commit(&tmem_full[acc]);  // degenerate (never for K>0)
       __syncwarp();
@@ -432,131 +394,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       } else {
         if constexpr (BLOCK_N >= 32) {
-          if (p.c_warp) {
-            // -------- per-warp epilogue: TMEM chunk -> registers -> this warp's own 2 x 2 KB staging -> TMA store of a
-            // 32-row x 32-column box. No CTA-level barrier: with 3-12 k-steps per tile (K = 192-768) the tile time is
-            // the epilogue's latency chain, and the eight block-wide barriers per tile of the box path are part of it.
-            uint8_t* wbuf = cstage + (warp - 2) * 4096;
-            constexpr int NCHUNKS = BLOCK_N / 32;
-            const bf16* rb = nullptr;
-            if (p.rowbias != nullptr && orow >= 0) rb = p.rowbias + (orow / p.rowbias_rows) * static_cast<long long>(p.N);
-            const float rs = (p.rowscale != nullptr && orow >= 0) ? p.rowscale[orow] : 1.f;
-            const bf16* rrow = (p.residual != nullptr && orow >= 0) ? p.residual + orow * p.ldr + col0 : nullptr;
-            const bool res_vec = rrow != nullptr && (p.ldr & 7) == 0;
-            uint32_t v[32];
-            uint4 rnext[4];
-            auto issue = [&](int c) {
-              tmem_ld_32x32(taddr + c * 32, v);
-              if (res_vec && col0 + (c + 1) * 32 <= p.N) {
-                const uint4* rp = reinterpret_cast<const uint4*>(rrow + c * 32);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) rnext[q] = __ldg(rp + q);
-              }
-            };
-            if (ehalf < NCHUNKS) issue(ehalf);
-            int wb = 0;
-#pragma unroll 1
-            for (int ci = ehalf; ci < NCHUNKS; ci += 2) {
-              const int gc = col0 + ci * 32;
-              tmem_ld_wait();
-              float f[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * rs;
-              uint4 rcur[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
-              if (ci + 2 < NCHUNKS) issue(ci + 2);
-              const bool full = gc + 32 <= p.N && (p.N & 7) == 0;
-              if (p.bias != nullptr) {   // same address in every lane -> broadcast loads
-                if (full) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.bias + gc) + q);
-                    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                      const float2 b2 = unpack_bf16(uu[w]);
-                      f[q * 8 + 2 * w] += b2.x;
-                      f[q * 8 + 2 * w + 1] += b2.y;
-                    }
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (gc + j < p.N) f[j] += __bfloat162float(p.bias[gc + j]);
-                }
-              }
-              if (rb != nullptr) {
-                if (full) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(rb + gc) + q);
-                    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                      const float2 r2 = unpack_bf16(uu[w]);
-                      f[q * 8 + 2 * w] += r2.x;
-                      f[q * 8 + 2 * w + 1] += r2.y;
-                    }
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (gc + j < p.N) f[j] += __bfloat162float(rb[gc + j]);
-                }
-              }
-              if (p.act == VB_ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
-              } else if (p.act == VB_ACT_SILU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = silu(f[j]);
-              } else if (p.act != VB_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-              }
-              if (rrow != nullptr) {
-                if (res_vec && gc + 32 <= p.N) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const uint32_t uu[4] = {rcur[q].x, rcur[q].y, rcur[q].z, rcur[q].w};
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                      const float2 r2 = unpack_bf16(uu[w]);
-                      f[q * 8 + 2 * w] = fmaf(p.alpha, f[q * 8 + 2 * w], r2.x);
-                      f[q * 8 + 2 * w + 1] = fmaf(p.alpha, f[q * 8 + 2 * w + 1], r2.y);
-                    }
-                  }
-                } else {
-                  const bf16* rp = rrow + ci * 32;
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (gc + j < p.N) f[j] = __bfloat162float(rp[j]) + p.alpha * f[j];
-                }
-              } else if (p.alpha != 1.0f) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
-              }
-              if (lane == 0) bulk_wait_read<1>();        // the store that last used this buffer has read it
-              __syncwarp();
-              uint8_t* buf = wbuf + (wb & 1) * 2048;
-              ++wb;
-              uint8_t* rowp = buf + lane * 64;            // row = lane, 64 bytes, 64B swizzle: piece ^= (row >> 1) & 3
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const int piece = (j >> 3) ^ ((lane >> 1) & 3);
-                *reinterpret_cast<uint4*>(rowp + piece * 16) =
-                    make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]), pack_bf16(f[j + 4], f[j + 5]),
-                               pack_bf16(f[j + 6], f[j + 7]));
-              }
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                if (gc < p.N) tma_store_2d(&tmap_c, buf, gc, t.m_blk * BLOCK_M + quad * 32);
-                bulk_commit();
-              }
-            }
-          } else if (p.c_box > 0) {
+          if (p.c_box > 0) {
             // -------- fused epilogue -> 128B/64B-swizzled smem tile -> TMA store (coalesced, clipped by the
             // tensor map at the ragged edges; conv: one 4-D box per pixel tile, mirroring the A load).
             // The two warps of a TMEM lane quadrant take alternate 32-column accumulator chunks; each keeps
@@ -711,7 +549,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         }
-        if (BLOCK_N < 32 || (p.c_box == 0 && !p.c_warp)) {
+        if (BLOCK_N < 32 || p.c_box == 0) {
         // -------- fused epilogue straight to the output tensor
         const bf16* rb = nullptr;
         if (p.rowbias != nullptr && orow >= 0)
@@ -846,7 +684,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   if (threadIdx.x == 64 && p.c_box > 0) bulk_wait<0>();  // staged tiles must be read out before smem goes away
-  if (p.c_warp && warp >= 2 && lane == 0) bulk_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -900,20 +737,6 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* 
   return r == CUDA_SUCCESS ? VB_OK : VB_ERR_DRIVER;
 }
 
-static int g_epilogue_mode = 0;  // 0 = CTA-staged 64-column boxes, 1 = per-warp 32 x 32 boxes (plain bf16 GEMM)
-extern "C" int vb200_set_gemm_epilogue(int mode) {
-  const int prev = g_epilogue_mode;
-  if (mode == 0 || mode == 1) g_epilogue_mode = mode;
-  return prev;
-}
-
-static int g_b_resident_mode = 0;  // 0 off, 1 automatic, 2 whenever structurally possible (parity tests)
-extern "C" int vb200_set_gemm_b_resident(int mode) {
-  const int prev = g_b_resident_mode;
-  if (mode >= 0 && mode <= 2) g_b_resident_mode = mode;
-  return prev;
-}
-
 template <int BN, int STAGES>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                       cudaStream_t stream) {
@@ -928,22 +751,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   }
   int units = p.m_blocks * p.n_blocks * p.splits;
   int grid = units < vb_num_sms() ? units : vb_num_sms();
-  GemmParams q = p;
-  q.b_resident = 0;
-  if (g_b_resident_mode != 0 && p.a_mode == 0 && p.splits == 1 && p.ws == nullptr && !p.swap && p.n_blocks <= vb_num_sms()) {
-    constexpr int A_B = BLOCK_M * BLOCK_K * 2, B_B = BN * BLOCK_K * 2, RING = STAGES * (A_B + B_B);
-    const long long left = static_cast<long long>(RING) - static_cast<long long>(p.num_k_blocks) * B_B;
-    int a_stages = left >= 2 * A_B ? static_cast<int>(left / A_B) : 0;
-    if (a_stages > STAGES) a_stages = STAGES;   // the barrier arrays hold STAGES entries
-    const int rgrid = (vb_num_sms() / p.n_blocks) * p.n_blocks;
-    // worth it when every CTA re-uses its B block over several m-blocks (mode 2 = whenever structurally possible: tests)
-    const bool pays = p.m_blocks * p.n_blocks >= 3 * rgrid;
-    if (a_stages >= 2 && (pays || g_b_resident_mode == 2)) {
-      q.b_resident = a_stages;
-      grid = units < rgrid ? ((units + p.n_blocks - 1) / p.n_blocks) * p.n_blocks : rgrid;
-    }
-  }
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, tc, q);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, tc, p);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
@@ -1122,14 +930,6 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   if (int r = make_tmap(&tb, W, 2, dB, sB, bB, estr2)) return r;
   CUtensorMap tc = ta;
   p.c_box = c_box_for(bn, epi->glu, epi->out_fp32, ldo, out);
-  if (g_epilogue_mode == 1 && p.c_box > 0 && epi->glu == VB_GLU_NONE && bn >= 32) {
-    p.c_warp = 1;
-    p.c_box = 0;
-    uint64_t dC[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
-    uint64_t sC[1] = {static_cast<uint64_t>(ldo) * 2};
-    uint32_t bC[2] = {32, 32};
-    if (int r = make_tmap(&tc, out, 2, dC, sC, bC, estr2, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
-  }
   if (p.c_box > 0) {
     const long long n_out = epi->glu != VB_GLU_NONE ? N / 2 : N;
     uint64_t dC[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};

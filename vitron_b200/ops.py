@@ -251,11 +251,6 @@ def attention(q, k, v, scale=None, causal=False, kv_len=None, mask=None, out=Non
     return out
 
 
-def set_gemm_b_resident(mode):
-    """Small-K GEMM mode (weights of a CTA's n-block resident in shared memory): 0 off, 1 automatic, 2 whenever possible."""
-    return _lib.load().vb200_set_gemm_b_resident(int(mode))
-
-
 def set_attention_impl(impl):
     """0 = automatic, 1 = mma.sync kernel only, 2 = tcgen05 kernel whenever the shape is supported."""
     check(_lib.load().vb200_set_attention_impl(int(impl)), "vb200_set_attention_impl")
