@@ -273,11 +273,36 @@ def vit_embed_ln(patch_out, cls, pos, ln_w, ln_b, nb, npatch, eps):
     return F.layer_norm(x, (d,), ln_w.float(), ln_b.float(), eps).to(BF16)
 
 
+def seem_attn_mask(mask_logits, h2, w2):
+    """fp32 [Q, H, W] -> uint8 [Q, h2*w2]: bilinear resize, masked where sigmoid < 0.5 (logit < 0), fully masked rows reset."""
+    r = F.interpolate(mask_logits[None].float(), size=(h2, w2), mode="bilinear", align_corners=False)[0].flatten(1)
+    m = r < 0
+    m[m.all(dim=1)] = False
+    return m.to(torch.uint8)
+
+
+def attention_short(q, k, v, scale=None, out=None):
+    """q/k/v [nseq, S, H, D] or [outer, inner, S, H, D] strided views; attention over S per (sequence, head)."""
+    D = q.shape[-1]
+    scale = D ** -0.5 if scale is None else scale
+    s = torch.einsum("...qhd,...khd->...hqk", q.float(), k.float()) * scale
+    o = torch.einsum("...hqk,...khd->...qhd", s.softmax(-1), v.float()).to(BF16)
+    if out is not None:
+        out.copy_(o)
+        return out
+    return o.contiguous()
+
+
+def cfg_combine(y, u, scale):
+    return (u + scale * (y - u)).contiguous()
+
+
 def install(monkeypatch):
     """Replace the kernel-launching entry points of vitron_b200.ops with the statements above."""
     from vitron_b200 import ops
     for name in ("gemm", "layernorm", "layernorm_add", "pack_dwconv_weight", "dwconv_nhwc", "colmean", "focal_modulate",
                  "mul_rows", "im2col_nchw", "pack_conv_weight", "conv_nhwc", "groupnorm_nhwc", "conv_nhwc_direct",
                  "upsample2x_nhwc", "softmax_rows", "preprocess_frames", "pack_glu_weight", "attention",
-                 "splice_multimodal", "add", "patchify", "vit_embed_ln"):
+                 "splice_multimodal", "add", "patchify", "vit_embed_ln", "seem_attn_mask", "attention_short",
+                 "cfg_combine"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -247,3 +247,75 @@ def test_clip_embedder_host_logic_against_oracle(monkeypatch):
     import pytest
     with pytest.raises(ValueError):
         emb("a caption")
+
+
+def test_seem_host_logic_against_reference_golden(monkeypatch):
+    """Host side of vitron_b200.seem (grouped K/V projections per feature level, FPN order, mask-head GEMM layout, mask
+    reset rule, output dict) with the kernels replaced by torch statements, against the golden outputs of the UNMODIFIED
+    reference pixel decoder + mask decoder (tests/golden/seem_tiny.pt)."""
+    import os
+    import torch
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200.seem import MultiScaleMaskedTransformerDecoder, TransformerEncoderPixelDecoder, XDecoderHead
+    cpu_ops_emulator.install(monkeypatch)
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "seem_tiny.pt"), weights_only=False)
+    t = fx["cfg"]
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    pd = TransformerEncoderPixelDecoder(t["in_channels"], t["C"], t["C"], t["heads"], t["ffn"], t["enc_layers"], device="cpu")
+    pr = MultiScaleMaskedTransformerDecoder(t["C"], t["dim_proj"], t["Q"], t["heads"], t["ffn"], t["dec_layers"], t["C"], device="cpu")
+    head = XDecoderHead(pd, pr).load_state_dict(sd)
+    head.predictor.set_text_embeddings(fx["t_emb"], t["logit_scale"])
+    mf, enc, multi = head.pixel_decoder.forward_features(fx["features"])
+    pairs = [(mf, fx["mask_features"], "mask_features"), (enc, fx["enc_features"], "encoder features")]
+    pairs += [(a, b, "multi-scale") for a, b in zip(multi, fx["multi_scale"])]
+    for got, ref, what in pairs:
+        e_inf, e_l2 = _rel(got, ref)
+        assert tuple(got.shape) == tuple(ref.shape) and e_inf < 0.05 and e_l2 < 0.04, (what, e_inf, e_l2)
+    out = head.predictor(fx["multi_scale"], fx["mask_features"])
+    assert sorted(k for k in out if k.startswith("pred_") or k == "aux_outputs") == ["aux_outputs", "pred_logits", "pred_maskembs", "pred_masks"]
+    a0, r0 = out["aux_outputs"][0], fx["out"]["aux_outputs"][0]
+    for k in ("pred_masks", "pred_logits"):
+        e_inf, e_l2 = _rel(a0[k], r0[k])
+        assert e_inf < 0.03 and e_l2 < 0.03, (k, e_inf, e_l2)
+    e_inf, e_l2 = _rel(out["pred_masks"], fx["out"]["pred_masks"])
+    assert e_l2 < 0.08, (e_inf, e_l2)
+
+
+def test_unet_i2vgen_host_logic_against_reference_golden(monkeypatch):
+    """Host side of vitron_b200.unet_i2vgen.UNetSD_I2VGen (block plan, batched time-embedding projection, NHWC skip concats,
+    strided temporal attention views, context assembly, cached local-image adapter) with the kernels replaced by torch
+    statements, against the golden output of the UNMODIFIED reference class (tests/golden/unet_tiny.pt)."""
+    import os
+    import torch
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200.unet_i2vgen import UNetSD_I2VGen
+    cpu_ops_emulator.install(monkeypatch)
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "unet_tiny.pt"), weights_only=False)
+    m = UNetSD_I2VGen(**fx["cfg"], device="cpu")
+    m.load_state_dict(seeded_state_dict(fx["shapes"], fx["seed"], fx["gain"]))
+    out = m(**fx["inputs"])
+    e_inf, e_l2 = _rel(out, fx["out"])
+    assert out.shape == fx["out"].shape and e_inf < 0.05 and e_l2 < 0.04, (e_inf, e_l2)
+
+
+def test_gligen_block_host_logic_against_reference_golden(monkeypatch):
+    """Host side of vitron_b200.gligen (concat-free gated self-attention over [visual ; grounding] rows, packed GEGLU
+    weights, tanh-gated residual epilogues) with the kernels replaced by torch statements, against the golden outputs of
+    the UNMODIFIED reference attention.py (tests/golden/gligen_tiny.pt)."""
+    import os
+    import torch
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200.gligen import BasicTransformerBlock
+    cpu_ops_emulator.install(monkeypatch)
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "gligen_tiny.pt"), weights_only=False)
+    for case in fx["cases"]:
+        C, heads = case["C"], case["heads"]
+        blk = BasicTransformerBlock(C, 768, 768, heads, C // heads, "gatedSA", device="cpu").load_state_dict(
+            seeded_state_dict(case["shapes"], fx["seed"]))
+        for got, ref, what in ((blk.fuser(case["x"], fx["objs"]), case["fuser_out"], "fuser"),
+                               (blk(case["x"], fx["context"], fx["objs"]), case["block_out"], "block")):
+            e_inf, e_l2 = _rel(got, ref)
+            assert got.shape == ref.shape and e_inf < 0.04 and e_l2 < 0.03, (C, what, e_inf, e_l2)
