@@ -24,9 +24,13 @@ def _unglu(v):
 
 def gemm(a, w, bias=None, act=ACT_NONE, glu=0, residual=None, alpha=1.0, rowbias=None, rowbias_rows=0, out=None,
          out_fp32=False, rowscale=None, rms_eps=0.0):
-    assert rowscale is None and not rms_eps
     assert a.dtype == BF16 and w.dtype == BF16 and a.shape[-1] == w.shape[1]
-    v = a.float().reshape(-1, a.shape[-1]) @ w.float().t()
+    a2 = a.float().reshape(-1, a.shape[-1])
+    v = a2 @ w.float().t()
+    if rowscale is not None:
+        v = v * rowscale.float().reshape(-1, 1)
+    elif rms_eps:                                   # folded RMSNorm: rows scaled by rsqrt(mean(a^2) + eps)
+        v = v * torch.rsqrt(a2.pow(2).mean(-1, keepdim=True) + rms_eps)
     if bias is not None:
         v = v + bias.float()
     if rowbias is not None:
@@ -53,7 +57,6 @@ def pack_glu_weight(w_a, w_b):
 
 
 def attention(q, k, v, scale=None, causal=False, kv_len=None, mask=None, out=None):
-    assert kv_len is None
     B, Sq, H, D = q.shape
     scale = D ** -0.5 if scale is None else scale
     s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale
@@ -62,6 +65,9 @@ def attention(q, k, v, scale=None, causal=False, kv_len=None, mask=None, out=Non
         s = s.masked_fill(torch.ones(Sq, Skv, dtype=torch.bool).triu(Skv - Sq + 1), float("-inf"))
     if mask is not None:
         s = s.masked_fill(mask.bool(), float("-inf"))
+    if kv_len is not None:
+        dead = torch.arange(k.shape[1])[None, :] >= kv_len.long().reshape(-1, 1)
+        s = s.masked_fill(dead[:, None, None, :], float("-inf"))
     o = torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1).nan_to_num(), v.float()).to(BF16).contiguous()
     if out is not None:
         out.copy_(o)
@@ -242,9 +248,14 @@ def preprocess_frames(frames, rh, rw, top, left, oh, ow, mean, std, mode, flip=F
 
 
 def splice_multimodal(embed, feats, srcmap, out=None):
-    src = srcmap.long()
-    assert feats is None and bool((src >= 0).all())
-    v = embed[src.reshape(-1)].reshape(*srcmap.shape, embed.shape[1])
+    src = srcmap.long().reshape(-1)
+    v = torch.zeros((src.numel(), embed.shape[1]), dtype=BF16)
+    tok = (src >= 0) & (src < embed.shape[0])
+    v[tok] = embed[src[tok]]
+    if feats is not None:                          # src = -(row + 1) selects feature row `row`; INT_MIN = padding (zeros)
+        fr = (src < 0) & (src > -(2 ** 31)) & ((-(src + 1)) < feats.shape[0])
+        v[fr] = feats[(-(src[fr] + 1))]
+    v = v.reshape(*srcmap.shape, embed.shape[1])
     if out is not None:
         out.copy_(v.reshape(out.shape))
         return out
@@ -297,6 +308,47 @@ def cfg_combine(y, u, scale):
     return (u + scale * (y - u)).contiguous()
 
 
+def rope_kv_append(qkv, positions, n_heads, head_dim, theta, k_pages=None, v_pages=None, block_table=None,
+                   batch_of_token=None, slot_of_token=None, page_size=0):
+    """rotate_half RoPE on the q | k thirds of every row in place (the K/V page scatter only matters for decode)."""
+    T = qkv.shape[0]
+    x = qkv.float().view(T, 3, n_heads, head_dim)
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    fr = positions.float()[:, None] * inv
+    emb = torch.cat([fr, fr], -1)
+    cos, sin = emb.cos()[:, None, :], emb.sin()[:, None, :]
+    rot = lambda t: torch.cat([-t[..., head_dim // 2:], t[..., :head_dim // 2]], -1)
+    for j in (0, 1):
+        x[:, j] = x[:, j] * cos + rot(x[:, j]) * sin
+    qkv.copy_(x.view(T, -1).to(BF16))
+    return qkv
+
+
+def region_mask_pool(feats, boxes, image_size):
+    """feats [B, g*g, C], boxes fp32 [B, 4] -> [B, C]: the reference's MaskPooling incl. the x-indexes-rows quirk
+    (region_extractor/layer.py:27-43, 77-112)."""
+    B, n, c = feats.shape
+    g = int(n ** 0.5)
+    m = torch.zeros((B, 1, image_size, image_size))
+    for b in range(B):
+        x1, y1, x2, y2 = [float(v) for v in boxes[b]]
+        m[b, 0, int(x1):int(x2), int(y1):int(y2)] = 1
+    m = (F.interpolate(m, size=(g, g), mode="bilinear", align_corners=False) > 0).float()
+    den = m.sum(dim=(-1, -2), keepdim=True) + 1e-8
+    f = feats.float().reshape(B, g, g, c).permute(0, 3, 1, 2)
+    return torch.einsum("bchw,bqhw->bqc", f, m / den).reshape(B, c).to(BF16)
+
+
+def add_rowgroup(x, table, group_rows, period, out=None):
+    rows = x.reshape(-1, x.shape[-1])
+    idx = (torch.arange(rows.shape[0]) // group_rows) % period
+    v = (rows.float() + table.float()[idx]).to(BF16).reshape(x.shape)
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v
+
+
 def install(monkeypatch):
     """Replace the kernel-launching entry points of vitron_b200.ops with the statements above."""
     from vitron_b200 import ops
@@ -304,5 +356,5 @@ def install(monkeypatch):
                  "mul_rows", "im2col_nchw", "pack_conv_weight", "conv_nhwc", "groupnorm_nhwc", "conv_nhwc_direct",
                  "upsample2x_nhwc", "softmax_rows", "preprocess_frames", "pack_glu_weight", "attention",
                  "splice_multimodal", "add", "patchify", "vit_embed_ln", "seem_attn_mask", "attention_short",
-                 "cfg_combine"):
+                 "cfg_combine", "rope_kv_append", "region_mask_pool", "add_rowgroup"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -319,3 +319,32 @@ def test_gligen_block_host_logic_against_reference_golden(monkeypatch):
                                (blk(case["x"], fx["context"], fx["objs"]), case["block_out"], "block")):
             e_inf, e_l2 = _rel(got, ref)
             assert got.shape == ref.shape and e_inf < 0.04 and e_l2 < 0.03, (C, what, e_inf, e_l2)
+
+
+def test_vitron_forward_host_logic_against_reference_golden(monkeypatch):
+    """Host side of the vision-LLM path (rows a1-a7): LanguageBind tower, projector, region extractor, multimodal splice
+    map, folded RMSNorm gains, packed SwiGLU weights, prefill bookkeeping — `VitronLlamaForCausalLM.forward` with the kernels
+    replaced by torch statements must reproduce the UNMODIFIED reference's golden logits (tests/golden/vitron_llm_tiny.pt)."""
+    import os
+    import torch
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200.vision_tower import VisionConfig
+    from vitron_b200.vitron_model import VitronConfig, VitronLlamaForCausalLM
+    cpu_ops_emulator.install(monkeypatch)
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vitron_llm_tiny.pt"), weights_only=False)
+    vit = dict(fx["vit"], hidden_act="gelu")
+    cfg = VitronConfig(llm=fx["llm"], vision=VisionConfig(**vit),
+                       video=VisionConfig(**vit, add_time_attn=True, num_frames=fx["num_frames"]), tokenizer_model_max_length=4096)
+    model = VitronLlamaForCausalLM(cfg, "cpu", max_batch=2, max_seq_len=256)
+    model.load_state_dict(seeded_state_dict(fx["shapes"], fx["seed"]))
+    g = fx["img"]
+    out = model.forward(input_ids=g["input_ids"], attention_mask=g["attention_mask"], images=g["images"], regions=g["regions"])
+    ref = g["logits"]
+    for b, n in enumerate(model._last_lens):
+        e_inf, e_l2 = _rel(out.logits[b, :n], ref[b, :n])
+        assert e_inf < 0.05 and e_l2 < 0.04, (b, e_inf, e_l2)
+    v = fx["vid"]                                   # video tower (temporal attention over the frames) + 8-sentinel splice
+    out = model.forward(input_ids=v["input_ids"], images=[v["images"][0]])
+    e_inf, e_l2 = _rel(out.logits, v["logits"])
+    assert e_inf < 0.05 and e_l2 < 0.04, ("video", e_inf, e_l2)
