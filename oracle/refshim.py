@@ -262,6 +262,17 @@ def gligen_unet_class():
     return importlib.import_module("modules.GLIGEN.demo.gligen.ldm.modules.diffusionmodules.openaimodel").UNetModel
 
 
+def gligen_plms_classes():
+    """Unmodified (PLMSSampler, DDPM) of gligen/ldm/models/diffusion/{plms,ddpm}.py (same package stubs as the UNet)."""
+    gligen_unet_class()
+    for name in ("modules.GLIGEN.demo.gligen.ldm.models", "modules.GLIGEN.demo.gligen.ldm.models.diffusion"):
+        if name not in sys.modules:
+            _pkg(name, os.path.join(REF, *name.split(".")))
+    plms = importlib.import_module("modules.GLIGEN.demo.gligen.ldm.models.diffusion.plms")
+    ddpm = importlib.import_module("modules.GLIGEN.demo.gligen.ldm.models.diffusion.ddpm")
+    return plms.PLMSSampler, ddpm.DDPM
+
+
 def seem_pieces():
     """The importable SEEM pieces (torch/einops only)."""
     ns = types.SimpleNamespace()

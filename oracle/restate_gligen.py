@@ -41,12 +41,12 @@ def gated_self_attention_dense(sd, prefix, x, objs, heads, scale=1.0):
     return x + scale * torch.tanh(sd[p + "alpha_dense"].float()) * _ff(_ln(x, sd, p + "norm2."), sd, p + "ff.")
 
 
-def basic_transformer_block(sd, prefix, x, context, objs, heads):
+def basic_transformer_block(sd, prefix, x, context, objs, heads, scale=1.0):
     p = prefix if (prefix == "" or prefix.endswith(".")) else prefix + "."
     x = x.float()
     h = _ln(x, sd, p + "norm1.")
     x = _mha(h, h, h, sd, p + "attn1.", heads) + x
-    x = gated_self_attention_dense(sd, p + "fuser.", x, objs, heads)
+    x = gated_self_attention_dense(sd, p + "fuser.", x, objs, heads, scale)   # `scale` = evaluator.py set_alpha_scale
     c = context.float()
     x = _mha(_ln(x, sd, p + "norm2."), c, c, sd, p + "attn2.", heads) + x
     return _ff(_ln(x, sd, p + "norm3."), sd, p + "ff.") + x

@@ -66,18 +66,19 @@ def res_block(x, emb, sd, p):
     return x + h
 
 
-def spatial_transformer(x, context, objs, sd, p, heads, depth):
+def spatial_transformer(x, context, objs, sd, p, heads, depth, scale=1.0):
     b, c, h, w = x.shape
     t = _conv(_gn(x, sd, p + "norm.", 1e-6), sd, p + "proj_in.", padding=0)
     t = t.flatten(2).transpose(1, 2)
     for d in range(depth):
-        t = basic_transformer_block(sd, p + f"transformer_blocks.{d}.", t, context, objs, heads)
+        t = basic_transformer_block(sd, p + f"transformer_blocks.{d}.", t, context, objs, heads, scale)
     t = t.transpose(1, 2).reshape(b, -1, h, w)
     return _conv(t, sd, p + "proj_out.", padding=0) + x
 
 
-def unet_forward(sd, cfg, inp):
-    """cfg: UNetModel constructor kwargs; inp: the reference's input dict -> [B, out_channels, H, W]."""
+def unet_forward(sd, cfg, inp, alpha_scale=1.0):
+    """cfg: UNetModel constructor kwargs; inp: the reference's input dict -> [B, out_channels, H, W].
+    alpha_scale = the `scale` evaluator.py::set_alpha_scale puts on every gated fuser (the sampler's gate schedule)."""
     mc, mult, nrb = cfg["model_channels"], tuple(cfg["channel_mult"]), cfg["num_res_blocks"]
     att, heads, depth = list(cfg["attention_resolutions"]), cfg.get("num_heads", 8), cfg.get("transformer_depth", 1)
     x = inp["x"].float()
@@ -92,7 +93,7 @@ def unet_forward(sd, cfg, inp):
     if cfg.get("is_inpaint", False):
         x = torch.cat([x, inp["inpainting_extra_input"].float()], dim=1)
     context = inp["context"].float()
-    st = lambda t, p: spatial_transformer(t, context, objs, sd, p, heads, depth)
+    st = lambda t, p: spatial_transformer(t, context, objs, sd, p, heads, depth, alpha_scale)
     hs = []
     h = _conv(x, sd, "input_blocks.0.0.")
     hs.append(h)

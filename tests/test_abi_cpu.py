@@ -348,3 +348,49 @@ def test_vitron_forward_host_logic_against_reference_golden(monkeypatch):
     out = model.forward(input_ids=v["input_ids"], images=[v["images"][0]])
     e_inf, e_l2 = _rel(out.logits, v["logits"])
     assert e_inf < 0.05 and e_l2 < 0.04, ("video", e_inf, e_l2)
+
+
+def test_gligen_grounded_sample_host_logic(monkeypatch):
+    """vitron_b200.gligen_sampler.grounded_sample (PLMS + scheduled gate + VAE decode) over the B200 UNetModel / AutoencoderKL
+    with the kernels replaced by torch statements, against the same chain built from the pinned oracles; also checks that
+    set_alpha_scale reaches every gated fuser."""
+    import os
+    from functools import partial
+    import torch
+    from oracle import restate_gligen_unet as G, restate_vae as V
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200 import gligen_sampler as GS
+    from vitron_b200.autoencoder import AutoencoderKL
+    from vitron_b200.gligen_unet import UNetModel
+    cpu_ops_emulator.install(monkeypatch)
+    ufx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "gligen_unet_tiny.pt"), weights_only=False)
+    vfx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vae_tiny.pt"), weights_only=False)
+    usd = seeded_state_dict(ufx["shapes"], ufx["seed"], ufx["gain"])
+    vsd = seeded_state_dict(vfx["shapes"], vfx["seed"], 0.8)
+    cfg = dict(ufx["cfg"], image_size=8)
+    unet = UNetModel(**cfg, device="cpu").load_state_dict(usd)
+    vae = AutoencoderKL(vfx["ddconfig"], 4, device="cpu").load_state_dict(vsd)
+    GS.set_alpha_scale(unet, 0.25)
+    fusers = [b.fuser for e in unet.w.values() if isinstance(e, dict) and "blocks" in e for b in e["blocks"]]
+    assert len(fusers) >= 3 and all(f.scale == 0.25 for f in fusers)
+    inp = {k: v for k, v in ufx["inputs"].items() if k not in ("x", "timesteps")}
+    g = torch.Generator().manual_seed(1)
+    start = torch.randn((2, 4, 8, 8), generator=g)
+    uc = torch.randn(inp["context"].shape, generator=g)
+    steps, guide, atype = 5, 2.0, (0.4, 0.2, 0.4)
+    img = GS.grounded_sample(unet, vae, GS.DDPM(), dict(inp, x=start.clone(), timesteps=None), uc, guidance_scale=guide, steps=steps,
+                             alpha_type=atype)
+
+    class OracleModel:          # the oracle UNet with the gate the sampler schedules
+        scale = 1.0
+
+        def __call__(self, d):
+            return G.unet_forward(usd, cfg, d, alpha_scale=self.scale)
+    om = OracleModel()
+    sampler = GS.PLMSSampler(GS.DDPM(), om, alpha_generator_func=partial(GS.alpha_generator, type=list(atype)),
+                             set_alpha_scale=lambda m, a: setattr(m, "scale", float(a)))
+    lat = sampler.sample(S=steps, shape=(2, 4, 8, 8), input=dict(inp, x=start.clone(), timesteps=None), uc=uc, guidance_scale=guide)
+    ref = V.decode(vsd, lat, vfx["ddconfig"])
+    e_inf, e_l2 = _rel(img, ref)
+    assert img.shape == ref.shape and e_inf < 0.08 and e_l2 < 0.06, (e_inf, e_l2)

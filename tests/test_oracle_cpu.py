@@ -399,6 +399,13 @@ def test_gligen_unet_restatement_matches_live_reference():
     out = G.unet_forward(sd, cfg, inp)
     assert torch.allclose(out, ref, atol=2e-5, rtol=2e-4), (out - ref).abs().max()
     assert torch.allclose(G.unet_forward(sd, cfg, inp2), ref2, atol=2e-5, rtol=2e-4)
+    for mod in net.modules():                      # evaluator.py::set_alpha_scale (:35-39): the sampler's gate schedule
+        if type(mod).__name__ == "GatedSelfAttentionDense":
+            mod.scale = 0.3
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        ref3 = net(dict(inp))
+    assert torch.allclose(G.unet_forward(sd, cfg, inp, alpha_scale=0.3), ref3, atol=2e-5, rtol=2e-4)
+    assert not torch.allclose(ref3, ref, atol=1e-4)
 
 
 OPENCLIP_TINY = dict(embed_dim=96, text=dict(width=128, layers=3, heads=2, context_length=16, vocab_size=300),
@@ -471,3 +478,51 @@ def test_openclip_restatement_matches_transformers_clip():
     with torch.no_grad():
         iref = vm(pixel_values=img).image_embeds
     assert torch.allclose(OC.encode_image(sd, img, cfg), iref, atol=2e-4, rtol=1e-4)
+
+
+def test_gligen_plms_sampler_matches_reference_sampler():
+    """§8(f2) GLIGEN sampling loop: vitron_b200.gligen_sampler.{DDPM, PLMSSampler, alpha_generator} against the UNMODIFIED
+    reference PLMSSampler / DDPM driven by the same analytic eps-model (CFG, gate schedule callback, inpainting blend).
+    Pure fp32 host arithmetic: tight tolerance, no GPU involved."""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    from functools import partial
+    from vitron_b200 import gligen_sampler as GS
+    RefPLMS, RefDDPM = refshim.gligen_plms_classes()
+    rd, md = RefDDPM(), GS.DDPM()
+    assert torch.allclose(rd.alphas_cumprod, md.alphas_cumprod, atol=0, rtol=1e-6)
+    # the vendored DDPM (ddpm.py) carries the schedule only; plms.py:98 calls `diffusion.q_sample`, which upstream GLIGEN
+    # defines on its LatentDiffusion subclass (standard sqrt(ac) x0 + sqrt(1 - ac) eps): supply that to the reference object
+    rd.q_sample = lambda x_start, t: (rd.sqrt_alphas_cumprod[t].view(-1, 1, 1, 1) * x_start
+                                      + rd.sqrt_one_minus_alphas_cumprod[t].view(-1, 1, 1, 1) * torch.randn_like(x_start))
+    g = torch.Generator().manual_seed(5)
+    ctx, uc = torch.randn((2, 3, 4), generator=g), torch.randn((2, 3, 4), generator=g)
+    bias = torch.randn((2, 4, 8, 8), generator=g) * 0.2
+
+    class Model:
+        scale = 1.0
+
+        def __call__(self, inp):
+            t = inp["timesteps"].view(-1, 1, 1, 1).float() / 1000.0
+            return torch.tanh(inp["x"]) * 0.4 + bias * t * self.scale + inp["context"].mean(dim=(1, 2)).view(-1, 1, 1, 1) * 0.1
+
+    calls_r, calls_m = [], []
+    setter = lambda log: (lambda model, a: (log.append(float(a)), setattr(model, "scale", float(a)))[0])
+    x_start = torch.randn((2, 4, 8, 8), generator=g)
+    for kind in ("plain", "inpaint"):
+        mask = (torch.rand((2, 1, 8, 8), generator=g) > 0.5).float() if kind == "inpaint" else None
+        x0 = torch.randn((2, 4, 8, 8), generator=g) if kind == "inpaint" else None
+        mr, mm = Model(), Model()
+        ref_s = RefPLMS(rd, mr, alpha_generator_func=partial(GS.alpha_generator, type=[0.3, 0.2, 0.5]), set_alpha_scale=setter(calls_r))
+        my_s = GS.PLMSSampler(md, mm, alpha_generator_func=partial(GS.alpha_generator, type=[0.3, 0.2, 0.5]), set_alpha_scale=setter(calls_m))
+        torch.manual_seed(0)   # q_sample noise of the inpainting blend: both sides draw the same stream
+        ref = ref_s.sample(S=10, shape=(2, 4, 8, 8), input=dict(x=x_start.clone(), timesteps=None, context=ctx), uc=uc,
+                           guidance_scale=5.0, mask=mask, x0=x0)
+        torch.manual_seed(0)
+        got = my_s.sample(S=10, shape=(2, 4, 8, 8), input=dict(x=x_start.clone(), timesteps=None, context=ctx), uc=uc,
+                          guidance_scale=5.0, mask=mask, x0=x0)
+        assert torch.allclose(got, ref, atol=2e-5, rtol=1e-4), (kind, (got - ref).abs().max())
+    assert calls_r == calls_m and len(calls_m) == 20
+    ra = importlib_alpha = GS.alpha_generator(50, [0.3, 0.0, 0.7])
+    assert ra[:15] == [1] * 15 and ra[15:] == [0] * 35
