@@ -394,3 +394,30 @@ def test_gligen_grounded_sample_host_logic(monkeypatch):
     ref = V.decode(vsd, lat, vfx["ddconfig"])
     e_inf, e_l2 = _rel(img, ref)
     assert img.shape == ref.shape and e_inf < 0.08 and e_l2 < 0.06, (e_inf, e_l2)
+
+
+def test_argument_validation_of_the_widened_entry_points(lib):
+    """Error behaviour of the §8(f) entry points without a device: null pointers, misaligned strides, unsupported kernel
+    sizes and short workspaces are rejected with VB_ERR_* before any launch."""
+    import ctypes as C
+    ERR_ARG, ERR_WS, ERR_UNSUP = -1, -3, -4
+    buf = (C.c_uint8 * 4096)()
+    p = C.addressof(buf)                                   # 16-byte aligned host memory stands in for device pointers:
+    p += (-p) % 16                                         # every check below fails before the pointer is dereferenced
+    assert lib.vb200_dwconv_nhwc(None, 64, None, None, 1, 8, 8, 64, 3, 1, None) == ERR_ARG
+    assert lib.vb200_dwconv_nhwc(p, 60, p, p, 1, 8, 8, 64, 3, 1, None) == ERR_ARG          # ld_in < c / not a multiple of 8
+    assert lib.vb200_dwconv_nhwc(p, 64, p, p, 1, 8, 8, 64, 3, 2, None) == ERR_ARG          # act: only NONE / GELU
+    assert lib.vb200_dwconv_nhwc(p, 64, p, p, 1, 8, 8, 64, 4, 1, None) == ERR_UNSUP        # even kernel size
+    assert lib.vb200_set_dwconv_impl(7) in (0, 1, 2, 3) and lib.vb200_set_dwconv_impl(0) in (0, 1, 2, 3)
+    assert lib.vb200_colmean_workspace_size(2, 1000, 192) > 0
+    assert lib.vb200_colmean(p, p, 1, 1000, 192, 1, p, 16, None) == ERR_WS                 # workspace too small
+    assert lib.vb200_colmean(p, p, 1, 1000, 4096, 1, p, 1 << 30, None) == ERR_ARG          # c > 2048
+    ptrs = (C.c_void_p * 7)(*([p] * 7))
+    assert lib.vb200_focal_modulate(ptrs, 7, p, 400, p, p, 1, 64, 64, 1.0, None) == ERR_ARG  # > VB_FOCAL_MAX_LEVELS
+    assert lib.vb200_mul_rows(p, 60, p, 64, p, 4, 64, None) == ERR_ARG
+    assert lib.vb200_layernorm_add(p, 64, p, None, None, 0, p, 64, 4, 4096, 1e-5, None) == ERR_ARG  # d > 2048
+    assert lib.vb200_im2col_nchw(p, 1, p, 1, 3, 32, 32, 7, 4, 2, 8, 8, 100, None) == ERR_ARG        # kpad < c*k*k / not % 8
+    assert lib.vb200_softmax_rows(None, 8, p, 8, 1, 8, None) == ERR_ARG
+    m3 = (C.c_float * 3)(0.5, 0.5, 0.5)
+    assert lib.vb200_preprocess_frames(p, p, 1, 32, 32, 224, 224, 10, 0, 224, 224, 1, 1, m3, m3, 1, 0, 0, None) == ERR_ARG  # crop outside
+    assert lib.vb200_preprocess_frames(p, p, 1, 32, 32, 224, 224, 0, 0, 224, 224, 1, 1, m3, m3, 5, 0, 0, None) == ERR_ARG   # unknown mode
