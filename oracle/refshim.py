@@ -262,6 +262,16 @@ def gligen_unet_class():
     return importlib.import_module("modules.GLIGEN.demo.gligen.ldm.modules.diffusionmodules.openaimodel").UNetModel
 
 
+def gligen_autoencoder_class():
+    """Unmodified gligen/ldm/models/autoencoder.py::AutoencoderKL (encode = posterior.sample() * scale_factor,
+    decode(z) = decoder(post_quant_conv(z / scale_factor)))."""
+    gligen_unet_class()
+    name = "modules.GLIGEN.demo.gligen.ldm.models"
+    if name not in sys.modules:
+        _pkg(name, os.path.join(REF, *name.split(".")))
+    return importlib.import_module("modules.GLIGEN.demo.gligen.ldm.models.autoencoder").AutoencoderKL
+
+
 def gligen_plms_classes():
     """Unmodified (PLMSSampler, DDPM) of gligen/ldm/models/diffusion/{plms,ddpm}.py (same package stubs as the UNet)."""
     gligen_unet_class()

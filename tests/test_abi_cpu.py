@@ -391,7 +391,7 @@ def test_gligen_grounded_sample_host_logic(monkeypatch):
     sampler = GS.PLMSSampler(GS.DDPM(), om, alpha_generator_func=partial(GS.alpha_generator, type=list(atype)),
                              set_alpha_scale=lambda m, a: setattr(m, "scale", float(a)))
     lat = sampler.sample(S=steps, shape=(2, 4, 8, 8), input=dict(inp, x=start.clone(), timesteps=None), uc=uc, guidance_scale=guide)
-    ref = V.decode(vsd, lat, vfx["ddconfig"])
+    ref = V.decode(vsd, lat / 0.18215, vfx["ddconfig"])  # GLIGEN decode(z) = decoder(z / scale_factor) (autoencoder.py:40-45)
     e_inf, e_l2 = _rel(img, ref)
     assert img.shape == ref.shape and e_inf < 0.08 and e_l2 < 0.06, (e_inf, e_l2)
 

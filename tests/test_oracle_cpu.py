@@ -327,6 +327,44 @@ def test_vae_restatement_matches_live_reference():
     assert zz.shape == mean.shape  # encode_firsr_stage = scale_factor * posterior.sample(): stochastic, shape only
 
 
+def test_gligen_autoencoder_scale_factor_matches_live_reference():
+    """GLIGEN's AutoencoderKL folds scale_factor into encode / decode (ldm/models/autoencoder.py:34-45).
+    The product wrapper `gligen_sampler.GligenAutoencoder` over an unscaled VAE must reproduce the UNMODIFIED GLIGEN class
+    with scale_factor = 0.18215 (decode exactly; encode with the posterior noise supplied)."""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    from oracle import gen_golden as G, restate_vae as V
+    from vitron_b200.autoencoder import DiagonalGaussianDistribution
+    from vitron_b200.gligen_sampler import GligenAutoencoder
+    dd = dict(G.VAE_TINY, ch=32, ch_mult=(1, 2), num_res_blocks=1)
+    _, sd, _ = G.build_reference_vae(dd, seed=5)
+    ref = refshim.gligen_autoencoder_class()(dict(dd, dropout=0.0), 4, scale_factor=0.18215).eval()
+    missing = ref.load_state_dict(sd, strict=False)
+    assert not missing.missing_keys, missing.missing_keys
+
+    class OracleVAE:  # the unscaled i2vgen-style interface the wrapper sits on (CPU stand-in for the B200 AutoencoderKL)
+        def encode(self, x):
+            mean, logvar, _ = V.encode_moments(sd, x, dd)
+            return DiagonalGaussianDistribution(torch.cat([mean, logvar], 1))
+
+        def decode(self, z):
+            return V.decode(sd, z, dd)
+
+    wrap = GligenAutoencoder(OracleVAE(), 0.18215)
+    g = torch.Generator().manual_seed(3)
+    x, z = torch.randn((1, 3, 16, 16), generator=g), torch.randn((1, 4, 8, 8), generator=g)
+    with torch.no_grad():
+        want_dec = ref.decode(z)
+        torch.manual_seed(11)
+        want_enc = ref.encode(x)
+        torch.manual_seed(11)
+        noise = torch.randn(want_enc.shape)
+    assert torch.allclose(wrap.decode(z), want_dec, atol=2e-4, rtol=1e-4)
+    assert not torch.allclose(V.decode(sd, z, dd), want_dec, atol=1e-2)  # the unscaled decode is NOT the GLIGEN decode
+    assert torch.allclose(wrap.encode(x, noise=noise), want_enc, atol=2e-4, rtol=1e-4)
+
+
 def _rand_u8(shape, seed):
     return torch.randint(0, 256, shape, generator=torch.Generator().manual_seed(seed), dtype=torch.uint8)
 

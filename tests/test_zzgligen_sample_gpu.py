@@ -43,7 +43,7 @@ def test_grounded_sample_vs_oracle_chain(cuda):
     sampler = GS.PLMSSampler(GS.DDPM(), OracleModel(), alpha_generator_func=partial(GS.alpha_generator, type=list(atype)),
                              set_alpha_scale=lambda m, a: setattr(m, "scale", float(a)))
     lat = sampler.sample(S=steps, shape=(2, 4, 16, 16), input=dict(inp, x=start.clone(), timesteps=None), uc=uc, guidance_scale=guide)
-    ref = V.decode(vsd, lat, vfx["ddconfig"])
+    ref = V.decode(vsd, lat / 0.18215, vfx["ddconfig"])  # GLIGEN decode = decoder(z / scale_factor), autoencoder.py:40-45
     got = img.float().cpu()
     assert got.shape == ref.shape and bool(torch.isfinite(got).all())
     e_inf = ((got - ref).abs().max() / (ref.abs().max() + 1e-6)).item()

@@ -34,9 +34,10 @@ struct TcAttnParams {
   const int32_t* kv_len;
 };
 
-// Bounded mbarrier wait: a protocol or descriptor bug must never hang the GPU. After ~0.5 s without progress the
-// waiter records (site id, block) in g_tc_watchdog, raises the CTA-wide abort flag and every later wait in the
-// CTA returns at once, so the kernel drains (with garbage output) and the host can report the site.
+// Bounded mbarrier wait: a protocol or descriptor bug must never hang the GPU. After 4 s without progress the
+// waiter records (site id, block) in g_tc_watchdog and TRAPS: the launch fails with a sticky CUDA error that the
+// next vb200_* call / stream synchronisation reports (VB_ERR_CUDA) — a timed-out attention never returns garbage
+// as if it were a result. The abort flag only short-cuts the other waiters of the CTA until the trap lands.
 __device__ unsigned int g_tc_watchdog[4];
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -49,13 +50,14 @@ __device__ __noinline__ void tc_wait_slow(uint64_t* bar, uint32_t parity, volati
   const unsigned long long t0 = gtime_ns();
   while (!mbar_try_wait(bar, parity)) {
     if (*abort_flag) return;
-    if (gtime_ns() - t0 > 500000000ull) {
+    if (gtime_ns() - t0 > 4000000000ull) {
       *abort_flag = 1;
       if (atomicCAS(&g_tc_watchdog[0], 0u, static_cast<unsigned int>(site)) == 0u) {
         g_tc_watchdog[1] = blockIdx.x | (blockIdx.y << 12) | (blockIdx.z << 22);
         g_tc_watchdog[2] = threadIdx.x;
       }
-      return;
+      __threadfence_system();
+      __trap();
     }
   }
 }

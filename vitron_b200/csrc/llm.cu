@@ -26,7 +26,7 @@ __global__ void rope_kv_append_kernel(bf16* __restrict__ qkv, long long ld, cons
   const int b = batch_of_token ? batch_of_token[tok] : 0;
   bf16* row = qkv + tok * ld;
   long long cache_off = -1;
-  if (slot >= 0 && k_pages != nullptr) {
+  if (slot >= 0 && k_pages != nullptr && slot / page_size < max_pages) {  // a slot beyond the table is never written
     const int page = block_table[static_cast<long long>(b) * max_pages + slot / page_size];
     cache_off = (static_cast<long long>(page) * H) * page_size * hd + static_cast<long long>(slot % page_size) * hd;
   }

@@ -12,7 +12,7 @@ All arithmetic here is fp32 torch on the device (elementwise on a [B, 4, 64, 64]
 UNet evaluations); the model is any callable with the reference's `model(input_dict) -> eps` contract —
 `vitron_b200.gligen_unet.UNetModel` on the GPU. The gate schedule takes 2-3 distinct values over a run (alpha_type
 [0.3, 0.0, 0.7] -> 1 ... 0), it is a Python float folded into GEMM epilogues, so a CUDA graph of the UNet evaluation has to be
-captured per distinct value; `GraphedGligenEval` does that lazily.
+captured per distinct value (not done here: the sampler calls the UNet eagerly).
 """
 import numpy as np
 import torch
@@ -168,15 +168,38 @@ class PLMSSampler:
         return x_prev, pred_x0, e_t
 
 
+class GligenAutoencoder:
+    """GLIGEN's first stage (ldm/models/autoencoder.py:14-52): the SD AutoencoderKL with the latent scale folded into
+    its interface — `encode` returns `posterior.sample() * scale_factor`, `decode` computes `decode(z / scale_factor)`
+    (every GLIGEN config sets scale_factor 0.18215). Wraps the i2vgen-style `vitron_b200.autoencoder.AutoencoderKL`,
+    whose encode / decode are unscaled."""
+
+    def __init__(self, vae, scale_factor=0.18215):
+        self.vae, self.scale_factor = vae, float(scale_factor)
+
+    @torch.no_grad()
+    def encode(self, x, generator=None, noise=None):
+        return self.vae.encode(x).sample(generator=generator, noise=noise) * self.scale_factor
+
+    @torch.no_grad()
+    def decode(self, z):
+        return self.vae.decode(z * (1.0 / self.scale_factor))
+
+
 @torch.no_grad()
 def grounded_sample(model, autoencoder, diffusion, input, uc, guidance_scale=7.5, steps=50, alpha_type=(0.3, 0.0, 0.7),
-                    mask=None, x0=None, batch_size=None):
+                    mask=None, x0=None, batch_size=None, scale_factor=0.18215):
     """The sampling part of `grounded_generation_box` (task_grounded_generation.py:241-263): PLMS over the grounded UNet with the
-    scheduled gate, then VAE decode. `input` is the reference's dict (x=None draws the start noise), `uc` the unconditional context."""
+    scheduled gate, then VAE decode. `input` is the reference's dict (x=None draws the start noise), `uc` the unconditional context.
+    `autoencoder` is either a `GligenAutoencoder` (scale already in its interface) or a bare `AutoencoderKL`, which is wrapped
+    with `scale_factor` here: the reference decodes `1/scale_factor * z` (ldm/models/autoencoder.py:41) and its inpainting `x0`
+    is `encode(image) = posterior.sample() * scale_factor` (:34-38) — pass x0 from `GligenAutoencoder.encode`."""
     from functools import partial
     b = batch_size or input["context"].shape[0]
     sampler = PLMSSampler(diffusion, model, alpha_generator_func=partial(alpha_generator, type=list(alpha_type)),
                           set_alpha_scale=set_alpha_scale)
     shape = (b, model.in_channels, model.image_size, model.image_size)
     latents = sampler.sample(S=steps, shape=shape, input=input, uc=uc, guidance_scale=guidance_scale, mask=mask, x0=x0)
+    if not isinstance(autoencoder, GligenAutoencoder):
+        autoencoder = GligenAutoencoder(autoencoder, scale_factor)
     return autoencoder.decode(latents)

@@ -127,6 +127,10 @@ class LlamaEngine:
         self._graphs = {}
         self.launches_per_step = 0
         self.use_pdl = True
+        # the split-KV workspace address is baked into the decode graphs: size it for max_batch once, so a later
+        # generate() at a larger batch can never move it under a captured graph
+        if self.device.type == "cuda":
+            ops.reserve_decode_workspace(max_batch, c.num_attention_heads, c.head_dim, self.device)
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, sd, prefix=""):
@@ -215,10 +219,14 @@ class LlamaEngine:
         if B > self.max_batch:
             raise ValueError(f"batch {B} > engine max_batch {self.max_batch}")
         lens = [S] * B if seq_lens is None else [int(x) for x in seq_lens]
+        if max(lens) > cache.max_seq_len or S > cache.max_seq_len:
+            # the K/V scatter indexes block_table[b, slot // page_size]: a prompt longer than the table must never launch
+            raise ValueError(f"prompt of {max(max(lens), S)} tokens exceeds the KV cache capacity {cache.max_seq_len} "
+                             f"(construct the model with a larger max_seq_len)")
         for b in range(self.max_batch):
             cache.release(b)
         for b in range(B):
-            cache.reserve(b, min(cache.max_seq_len, lens[b]))
+            cache.reserve(b, lens[b])
         cache.sync_table()
         ar = torch.arange(S, dtype=torch.int32)
         lens_t = torch.tensor(lens, dtype=torch.int32)

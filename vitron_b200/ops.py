@@ -34,15 +34,28 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+_ws_retired = []
+
+
 def workspace(nbytes, device, tag="main"):
     """Grow-only per-(device, tag) scratch buffer, zero-filled at allocation (the split-K / split-KV
-    arrival counters at its head must start at zero; the kernels leave them zeroed)."""
+    arrival counters at its head must start at zero; the kernels leave them zeroed). A buffer that is outgrown is
+    RETIRED, never freed: captured CUDA graphs keep the address they were captured with, and every buffer is
+    self-consistent (its own counters), so an old graph replaying against its old buffer stays correct."""
     key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
     buf = _ws.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)
         buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _ws[key] = buf
     return buf
+
+
+def reserve_decode_workspace(max_batch, n_heads, head_dim, device):
+    """Pre-size the split-KV decode workspace for the largest batch an engine will ever run."""
+    need = _lib.load().vb200_attn_decode_workspace_size(max_batch, n_heads, head_dim, 32)
+    return workspace(need, torch.device(device), "dec")
 
 
 def _req(cond, msg):

@@ -498,10 +498,11 @@ class DiffusionDDIM:
         alphas_prev = self._i(self.alphas_cumprod, (t - stride).clamp(0), xt)
         sigmas = eta * torch.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
         direction = torch.sqrt(1 - alphas_prev - sigmas ** 2) * eps
-        xt_1 = torch.sqrt(alphas_prev) * x0 + direction
-        if eta != 0.0:
-            mask = t.ne(0).float().view(-1, *((1,) * (xt.ndim - 1)))
-            xt_1 = xt_1 + mask * sigmas * torch.randn_like(xt)
+        # the reference draws the noise unconditionally (diffusion_ddim.py:233), also at eta = 0 where it is multiplied
+        # by sigma = 0: the draw is kept so that a shared torch RNG stream stays aligned with the reference's
+        noise = torch.randn_like(xt)
+        mask = t.ne(0).float().view(-1, *((1,) * (xt.ndim - 1)))
+        xt_1 = torch.sqrt(alphas_prev) * x0 + direction + mask * sigmas * noise
         return xt_1, x0
 
     @torch.no_grad()
