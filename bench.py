@@ -86,36 +86,32 @@ def synth_inputs(seed_px=1, seed_ids=2, batch=BATCH):
 
 
 # =============================================================================== CPU (reference arm)
-def cpu_sample(threads=None):
-    """Bounded CPU sample of the same workload with the oracle port of the reference
-    (oracle/restate_llm.py): ViT-L/14 2 of 23 needed layers on 1 image, LLaMA-7B-shaped 2 of 32
-    layers — prefill S=768 at B=1, 4 cached decode steps at B=8 — fp32, all host threads; the
-    per-layer times are scaled to the full depth and batch. Returns (tokens_per_s, info)."""
-    from oracle import restate_llm as R
-    threads = _pick_threads()
-    torch.set_num_threads(threads)
+CPU_LLM_LAYERS, CPU_VIT_LAYERS, CPU_DECODE_STEPS = 8, 6, 3
+
+
+def _cpu_weights():
+    """fp32 random-init weights of the timed slice: CPU_LLM_LAYERS LLaMA-7B layers + embeddings + lm_head,
+    CPU_VIT_LAYERS ViT-L/14 layers (built once per process)."""
+    if "w" in _CPU_CACHE:
+        return _CPU_CACHE["w"]
     g = torch.Generator().manual_seed(0)
     rn = lambda *s: torch.randn(s, generator=g) * 0.02
-    LL = 2
     d, f, V = 4096, 11008, 32000
-    if "w" in _CPU_CACHE:
-        sd, cfg, vsd, vcfg, vp = _CPU_CACHE["w"]
-        return _cpu_time(R, sd, cfg, vsd, vcfg, vp, rn, g, LL, d)
     sd = {"model.embed_tokens.weight": rn(V, d), "lm_head.weight": rn(V, d), "model.norm.weight": torch.ones(d)}
-    for i in range(LL):
+    for i in range(CPU_LLM_LAYERS):
         p = f"model.layers.{i}."
         for n in "qkvo":
             sd[p + f"self_attn.{n}_proj.weight"] = rn(d, d)
         sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"], sd[p + "mlp.down_proj.weight"] = rn(f, d), rn(f, d), rn(d, f)
         sd[p + "input_layernorm.weight"] = torch.ones(d)
         sd[p + "post_attention_layernorm.weight"] = torch.ones(d)
-    cfg = dict(VICUNA_7B, num_hidden_layers=LL)
+    cfg = dict(VICUNA_7B, num_hidden_layers=CPU_LLM_LAYERS)
     vd, vf = 1024, 4096
     vp = "v."
     vsd = {vp + "embeddings.class_embedding": rn(vd), vp + "embeddings.patch_embedding.weight": rn(vd, 3, 14, 14),
            vp + "embeddings.position_embedding.weight": rn(257, vd), vp + "pre_layrnorm.weight": torch.ones(vd),
            vp + "pre_layrnorm.bias": torch.zeros(vd)}
-    for i in range(LL):
+    for i in range(CPU_VIT_LAYERS):
         p = vp + f"encoder.layers.{i}."
         for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
             vsd[p + f"self_attn.{n}.weight"], vsd[p + f"self_attn.{n}.bias"] = rn(vd, vd), torch.zeros(vd)
@@ -123,10 +119,60 @@ def cpu_sample(threads=None):
             vsd[p + n + ".weight"], vsd[p + n + ".bias"] = torch.ones(vd), torch.zeros(vd)
         vsd[p + "mlp.fc1.weight"], vsd[p + "mlp.fc1.bias"] = rn(vf, vd), torch.zeros(vf)
         vsd[p + "mlp.fc2.weight"], vsd[p + "mlp.fc2.bias"] = rn(vd, vf), torch.zeros(vd)
-    vcfg = dict(VIT_L14, num_hidden_layers=LL, layer_norm_eps=1e-5)
-    _CPU_CACHE["w"] = (sd, cfg, vsd, vcfg, vp)
-    return _cpu_time(R, sd, cfg, vsd, vcfg, vp, rn, g, LL, d)
+    vcfg = dict(VIT_L14, num_hidden_layers=CPU_VIT_LAYERS, layer_norm_eps=1e-5)
+    _CPU_CACHE["w"] = (sd, cfg, vsd, vcfg, vp, rn, g)
+    return _CPU_CACHE["w"]
 
+
+def cpu_sample(batch=BATCH):
+    """One BOUNDED sample of the workload on the host cores with the oracle port of the reference (oracle/restate_llm.py,
+    fp32, KV cache grown by torch.cat like HF 4.31): every stage at its REAL shape and context —
+      * ViT-L/14 encode of 1 image, CPU_VIT_LAYERS of the 23 layers the path needs,
+      * LLaMA-7B prefill of ONE sequence at the full S = 768, CPU_LLM_LAYERS of 32 layers,
+      * CPU_DECODE_STEPS cached decode steps at batch `batch` on the real 768+ token context (the prefill KV replicated
+        over the batch), same layer count, + the full-size final norm / lm_head.
+    The layers of both stacks are identical, so the full-depth time is the per-layer time x depth; per-sequence stages
+    scale with the batch (they are compute-bound on a CPU). Returns (tokens_per_s_of_the_full_workload, info) where
+    info['sample_s'] is the wall time this sample actually took."""
+    import torch.nn.functional as F
+    from oracle import restate_llm as R
+    threads = _pick_threads()
+    torch.set_num_threads(threads)
+    sd, cfg, vsd, vcfg, vp, rn, g = _cpu_weights()
+    d = 4096
+    with torch.no_grad():
+        t_all = time.perf_counter()
+        t0 = time.perf_counter()
+        R.clip_vit_hidden(vsd, vp, vcfg, torch.randn((1, 3, 224, 224), generator=g), select_layer=-1)
+        t_vit = time.perf_counter() - t0
+        m = R.LlamaCPU(sd, cfg)
+        t0 = time.perf_counter()
+        m.prefill(rn(1, VISION + TEXT, d))
+        t_pre = time.perf_counter() - t0
+        m.kv = [(k.expand(batch, -1, -1, -1).contiguous(), v.expand(batch, -1, -1, -1).contiguous()) for k, v in m.kv]
+        h = rn(batch, 1, d)
+        t0 = time.perf_counter()
+        for _ in range(CPU_DECODE_STEPS):
+            m._layers(h, m.pos)
+            m.pos += 1
+        t_lay = (time.perf_counter() - t0) / CPU_DECODE_STEPS
+        t0 = time.perf_counter()
+        F.linear(R.rms_norm(h, sd["model.norm.weight"], 1e-5), sd["lm_head.weight"])
+        t_head = time.perf_counter() - t0
+        sample_s = time.perf_counter() - t_all
+    t_dec_full = (32 / CPU_LLM_LAYERS) * t_lay + t_head
+    full = batch * (23 / CPU_VIT_LAYERS) * t_vit + batch * (32 / CPU_LLM_LAYERS) * t_pre + NEW * t_dec_full
+    info = {"sample_s": round(sample_s, 3), f"t_vit_{CPU_VIT_LAYERS}of23_layers_1img_s": round(t_vit, 3),
+            f"t_prefill_{CPU_LLM_LAYERS}of32_layers_b1_s768_s": round(t_pre, 3),
+            f"t_decode_{CPU_LLM_LAYERS}of32_layers_b{batch}_ctx{VISION + TEXT}_s": round(t_lay, 4), f"t_lm_head_b{batch}_s": round(t_head, 4),
+            "threads": threads, "batch": batch, "full_depth_decode_step_s": round(t_dec_full, 3), "full_workload_step_s": round(full, 2)}
+    return batch * NEW / full, info
+
+
+CPU_SAMPLE_TEXT = (f"oracle port (fp32 torch restatement of the reference path, KV cache by torch.cat): per step ViT-L/14 "
+                   f"{CPU_VIT_LAYERS}/23 layers on 1 image + LLaMA-7B {CPU_LLM_LAYERS}/32 layers: prefill of ONE sequence at S=768 and "
+                   f"{CPU_DECODE_STEPS} cached decode steps at the full batch on the real 768-token context + full lm_head; value = "
+                   "batch x 128 tokens / (per-layer times x depth, per-sequence stages x batch); ms_per_step = wall time of the sample itself")
 
 _CPU_CACHE = {}
 
@@ -159,66 +205,25 @@ def _pick_threads():
     return best
 
 
-def _cpu_time(R, sd, cfg, vsd, vcfg, vp, rn, g, LL, d):
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        R.clip_vit_hidden(vsd, vp, vcfg, torch.randn((1, 3, 224, 224), generator=g), select_layer=-1)
-        t_vit = time.perf_counter() - t0
-        m = R.LlamaCPU(sd, cfg)
-        t0 = time.perf_counter()
-        m.prefill(rn(1, VISION + TEXT, d))
-        t_pre = time.perf_counter() - t0
-        m8 = R.LlamaCPU(sd, cfg)
-        m8.prefill(rn(BATCH, 64, d))  # short context is enough for the weight-bound decode step
-        # decoder layers and the (single) norm + lm_head are timed separately, so that only the layers are
-        # scaled to the full depth; small-M GEMVs do not always profit from every host thread, so the
-        # decode part is timed at two thread counts and the faster one is reported
-        import torch.nn.functional as F
-        best = None
-        base_threads = torch.get_num_threads()
-        for th in sorted({base_threads, max(1, base_threads // 2), min(base_threads, 16)}, reverse=True):
-            torch.set_num_threads(th)
-            h = rn(BATCH, 1, d)
-            m8._layers(h, m8.pos)  # warm
-            m8.pos += 1
-            t0 = time.perf_counter()
-            for _ in range(3):
-                m8._layers(h, m8.pos)
-                m8.pos += 1
-            t_lay = (time.perf_counter() - t0) / 3
-            t0 = time.perf_counter()
-            for _ in range(3):
-                F.linear(R.rms_norm(h, sd["model.norm.weight"], 1e-5), sd["lm_head.weight"])
-            t_head = (time.perf_counter() - t0) / 3
-            if best is None or t_lay + t_head < best[0] + best[1]:
-                best = (t_lay, t_head, th)
-        t_lay, t_head, dec_threads = best
-        torch.set_num_threads(base_threads)
-    t_dec_full = (32 / LL) * t_lay + t_head
-    full = BATCH * (23 / LL) * t_vit + BATCH * (32 / LL) * t_pre + NEW * t_dec_full
-    info = {"t_vit_2layers_1img_s": round(t_vit, 3), "t_prefill_2layers_b1_s": round(t_pre, 3),
-            "t_decode_2layers_b8_s": round(t_lay, 4), "t_lm_head_b8_s": round(t_head, 4), "threads": base_threads, "decode_threads": dec_threads,
-            "extrapolated_decode_step_s": round(t_dec_full, 3), "extrapolated_step_s": round(full, 2)}
-    return BATCH * NEW / full, info
-
-
 def run_reference(args, rank):
+    """`--impl reference`: the reference's CPU path (oracle port) on this box's host cores, K bounded samples after W
+    warm-up samples; the batch follows the GPU arm's global batch (8 x N)."""
     if rank != 0:
         return
-    vals, info = [], {}
+    batch = BATCH * max(1, args.gpus)
+    vals, secs, info = [], [], {}
     for i in range(args.warmup + args.steps):
-        v, info = cpu_sample()
+        v, info = cpu_sample(batch)
         if i >= args.warmup:
             vals.append(v)
+            secs.append(info["sample_s"])
     v = sum(vals) / len(vals)
-    sample = ("oracle port (fp32 torch CPU restatement of the reference path): ViT-L/14 2/23 layers on 1 image, "
-              "LLaMA-7B 2/32 layers prefill S=768 B=1 + 3 cached decode steps B=8 (layers scaled to full depth, lm_head timed once); batch 8")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * BATCH * NEW / v,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(secs) / len(secs),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus),
             "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": info.get("threads"), "host_cores": _host_cores(), "kind": "port",
-                             "sample": sample, **info},
+                             "sample": CPU_SAMPLE_TEXT, **info},
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -318,48 +323,198 @@ def run_profile():
 UNET_CFG = dict(in_dim=4, concat_dim=4, dim=320, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
                 head_dim=64, num_res_blocks=2, attn_scales=[1.0, 0.5, 0.25], num_tokens=4)
 UNET_TFLOP_PER_FORWARD = 12.67  # algorithmic FLOPs of the reference class at f=16, 40x64 latent
+UNET_METRIC = "i2vgen-xl UNet3D DDIM steps/s (2 UNet forwards + CFG per step), latent [1,4,16,40,64] = 16 frames of 320x512 px"
+UNET_LATENT = (1, 4, 16, 40, 64)
 
 
-def bench_unet(device, tf_peak, steps=3):
-    """Second half of BASELINE.json's metric: i2vgen-xl UNet3D denoise steps/s (config 5: 16 x (40x64) latent
-    = 320x512 px, DDIM step = 2 UNet forwards with classifier-free guidance 9.0), bf16, random-init 1.42 B
-    parameter UNetSD_I2VGen, one request on one GPU, CUDA-graphed step."""
+def _unet_inputs(device, seed=4):
+    g = torch.Generator(device=device).manual_seed(seed)
+    rn = lambda *s: torch.randn(s, generator=g, device=device)
+    noise, local = rn(*UNET_LATENT), rn(*UNET_LATENT)
+    cond = dict(y=rn(1, 77, 1024), image=rn(1, 1, 1024), local_image=local, fps=torch.tensor([16], device=device))
+    unc = dict(y=rn(1, 77, 1024), image=torch.zeros((1, 1, 1024), device=device), local_image=local,
+               fps=torch.tensor([16], device=device))
+    return noise, cond, unc
+
+
+def unet_gemm_roofline(unet, noise, cond, tf_peak, peak_kind):
+    """Dominant kernel family of a UNet forward = the tcgen05 GEMM / implicit-GEMM conv kernel (gemm_v2_kernel<BN,...>,
+    ~70 % of the forward). Every ops.gemm / ops.conv_nhwc call of ONE forward is recorded with its live operands, then
+    exactly those calls are replayed back to back from a CUDA graph and timed with CUDA events: achieved = their
+    algorithmic FLOPs (2*M*N*K, conv 2*pixels*cout*cin*taps) / that time."""
+    from vitron_b200 import ops
+    calls = []
+    real_gemm, real_conv = ops.gemm, ops.conv_nhwc
+
+    def rec_gemm(a, w, *args, **kw):
+        out = real_gemm(a, w, *args, **kw)
+        if a.numel() // a.shape[-1] > 16:
+            kw2 = dict(kw)
+            kw2["out"] = out if kw.get("out") is None else kw["out"]
+            if kw2.get("residual") is not None and kw2["residual"].data_ptr() == kw2["out"].data_ptr():
+                kw2["residual"] = kw2["residual"].clone()  # replay must not accumulate in place
+                kw2["out"] = torch.empty_like(kw2["residual"])
+            calls.append((real_gemm, (a, w) + args, kw2, 2.0 * (a.numel() // a.shape[-1]) * a.shape[-1] * w.shape[0]))
+        return out
+
+    def rec_conv(x, wt, kh, kw_, *args, **kw):
+        out = real_conv(x, wt, kh, kw_, *args, **kw)
+        calls.append((real_conv, (x, wt, kh, kw_) + args, dict(kw, out=out),
+                      2.0 * out.shape[0] * out.shape[1] * out.shape[2] * wt.shape[0] * wt.shape[1] * x.shape[-1]))
+        return out
+    ops.gemm, ops.conv_nhwc = rec_gemm, rec_conv
+    import vitron_b200.unet_i2vgen as U
+    try:
+        unet(noise, torch.tensor([981], device=noise.device), **cond)
+    finally:
+        ops.gemm, ops.conv_nhwc = real_gemm, real_conv
+    torch.cuda.synchronize()
+    flops = sum(c[3] for c in calls)
+
+    def replay():
+        for fn, a, kw, _ in calls:
+            fn(*a, **kw)
+    s = torch.cuda.Stream(device=noise.device)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        replay()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        replay()
+    for _ in range(2):
+        g.replay()
+    ms = timed(g.replay, 5)
+    traffic = None
+    pj = os.path.join(ROOT, "profiles", "dominant_kernel_unet.json")
+    if os.path.exists(pj):
+        with open(pj) as fh:
+            traffic = json.load(fh).get("traffic_bytes_per_launch")
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "gemm_v2_kernel<BN,STAGES,EPI> (tcgen05 GEMM + implicit-GEMM conv: every Linear / Conv2d / Conv3d of the forward)",
+            "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_kind}, burst)", "traffic": traffic,
+            "launches": len(calls), "algorithmic_tflop": flops / 1e12, "avg_launch_us": ms * 1e3 / len(calls), "replay_ms": ms}
+
+
+def unet_cpu_baseline():
+    """CPU baseline of the UNet half: the oracle port (oracle/restate_unet.py, fp32, the reference class's arithmetic) with
+    the full 1.42 B-parameter weights on a REDUCED latent [1,4,4,24,32] (3/40 of the frames x pixels), one forward timed;
+    steps/s = 1 / (2 forwards x 13.3 x t): convolutions / linears scale with frames x pixels (BASELINE.md §3 prescribes the
+    FLOP-ratio scaling; the quadratic attention terms shrink faster, so this slightly FAVOURS the CPU)."""
+    from oracle import restate_unet as RU
+    from vitron_b200 import param_shapes as PS
+    threads = _pick_threads()
+    torch.set_num_threads(threads)
+    sd = {k: v.float() for k, v in PS.random_state_dict(PS.unet_shapes(UNET_CFG), torch.device("cpu"), seed=4).items()}
+    g = torch.Generator().manual_seed(4)
+    rn = lambda *sh: torch.randn(sh, generator=g)
+    f, h, w = 4, 24, 32  # h, w divisible by 8 (three stride-2 levels)
+    x, local = rn(1, 4, f, h, w), rn(1, 4, f, h, w)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        RU.unet_forward(sd, UNET_CFG, x, torch.tensor([981]), y=rn(1, 77, 1024), image=rn(1, 1, 1024), local_image=local,
+                        fps=torch.tensor([16]))
+        t = time.perf_counter() - t0
+    scale = (16 * 40 * 64) / (f * h * w)
+    return {"value": 1.0 / (2 * scale * t), "unit": "steps/s", "cores": threads, "host_cores": _host_cores(), "kind": "port",
+            "sample": f"oracle port fp32, full weights, ONE forward at latent [1,4,{f},{h},{w}] ({t:.2f} s), scaled x{scale:.0f} "
+                      "(frames x pixels) to the [1,4,16,40,64] latent, 2 forwards per step"}
+
+
+def bench_unet(device, tf_peak, peak_kind, steps=10, rank=0, world=1, with_cpu=True):
+    """Second half of BASELINE.json's metric: i2vgen-xl UNet3D denoise steps/s (configs[4] at the primary latent reading
+    16 x (40x64) = 320x512 px; DDIM step = 2 UNet forwards with classifier-free guidance 9.0 + the v-prediction update),
+    bf16, random-init 1.42 B-parameter UNetSD_I2VGen, CUDA-graphed.
+    N = 1: one request. N > 1: `value` = N independent requests (replicas, no collective); `cfg_split` =
+    the cond / uncond branches of ONE request on a GPU pair, one NCCL all_gather of the two [1,4,16,40,64] fp32 branch
+    outputs per step (N/2 requests in flight, each step ~2x faster)."""
     from vitron_b200 import ops
     from vitron_b200 import param_shapes as PS
-    from vitron_b200.unet_i2vgen import DiffusionDDIM, GraphedCFGDenoiser, UNetSD_I2VGen
+    from vitron_b200.unet_i2vgen import CFGSplitDenoiser, DiffusionDDIM, GraphedBranch, GraphedCFGDenoiser, UNetSD_I2VGen
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
     unet = UNetSD_I2VGen(**UNET_CFG, device=device)
     sd = PS.random_state_dict(PS.unet_shapes(UNET_CFG), device, seed=4)
     unet.load_state_dict(sd)
     del sd
-    g = torch.Generator(device=device).manual_seed(4)
-    rn = lambda *s: torch.randn(s, generator=g, device=device)
-    noise, local = rn(1, 4, 16, 40, 64), rn(1, 4, 16, 40, 64)
-    cond = dict(y=rn(1, 77, 1024), image=rn(1, 1, 1024), local_image=local, fps=torch.tensor([16], device=device))
-    unc = dict(y=rn(1, 77, 1024), image=torch.zeros((1, 1, 1024), device=device), local_image=local,
-               fps=torch.tensor([16], device=device))
-    den = GraphedCFGDenoiser(unet, cond, unc, 9.0, noise, torch.zeros((1,), dtype=torch.long, device=device))
+    noise, cond, unc = _unet_inputs(device)
     diff = DiffusionDDIM()
-    xt = noise
-    ts = [981, 961, 941, 921, 901, 881, 861, 841]
-    for tv in ts[:2]:  # warm-up + capture
-        xt, _ = diff.ddim_sample(xt, torch.tensor([tv], device=device), den, None, 9.0, 50)
+    tz = torch.zeros((1,), dtype=torch.long, device=device)
+    den = GraphedCFGDenoiser(unet, cond, unc, 9.0, noise, tz)
+    ts = [int(v) for v in (1 + torch.arange(0, 1000, 20)).clamp(0, 999).flip(0)]  # the DDIM-50 schedule
+
+    def run_steps(model, xt, tvals):
+        for tv in tvals:
+            xt, _ = diff.ddim_sample(xt, torch.full((1,), tv, dtype=torch.long, device=device), model, None, 9.0, 50)
+        return xt
+
+    def time_steps(model, x0, n):
+        xt = run_steps(model, x0, ts[:3])  # warm-up + capture
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        xt = run_steps(model, xt, ts[3:3 + n])
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t), xt
+
     l0 = ops.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for tv in ts[2:2 + steps]:
-        xt, _ = diff.ddim_sample(xt, torch.tensor([tv], device=device), den, None, 9.0, 50)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    tfs = 2 * UNET_TFLOP_PER_FORWARD / (ms * 1e-3)
+    ms, xt = time_steps(den, noise, steps)
+    launches = (ops.launch_count() - l0) // (steps + 3)
     finite = bool(torch.isfinite(xt).all())
+    tfs = 2 * UNET_TFLOP_PER_FORWARD / (ms * 1e-3)
+    out = {"metric": UNET_METRIC, "value": world * 1000.0 / ms, "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": 3,
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "BASELINE.json configs[4], primary latent reading [1,4,16,40,64]; DDIM-50 schedule, guide 9.0",
+                      "parallelism": f"{world} request replica(s)", "requests_in_flight": world,
+                      "l2": "2.8 GB of weights + ~0.6 GB of activations streamed per forward (> 126 MB L2)"},
+           "latent": list(UNET_LATENT), "guide_scale": 9.0, "gpu_launches": launches,
+           "achieved_tflops_per_gpu": tfs, "frac_of_bf16_peak": tfs / tf_peak, "finite": finite,
+           "algorithmic_tflop_per_step": 2 * UNET_TFLOP_PER_FORWARD}
+
+    if world == 1:
+        # ---- e2e: the latent of each step arrives from / returns to pinned host memory
+        x_pin = noise.cpu().pin_memory()
+        out_pin = torch.empty_like(x_pin).pin_memory()
+
+        def e2e_step(i=[0]):
+            xt = x_pin.to(device, non_blocking=True)
+            xt = run_steps(den, xt, [ts[3 + i[0] % 40]])
+            out_pin.copy_(xt, non_blocking=True)
+            torch.cuda.synchronize()
+            i[0] += 1
+        e2e_step()
+        ms_e2e = timed(e2e_step, steps)
+        nb = x_pin.numel() * 4
+        out["e2e"] = {"value": 1000.0 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": nb,
+                      "d2h_bytes_per_step": nb, "input": "x_t fp32 [1,4,16,40,64] from pinned host memory, x_{t-1} read back"}
+        out["roofline"] = unet_gemm_roofline(unet, noise, cond, tf_peak, peak_kind)
+        if with_cpu:
+            out["cpu_baseline"] = unet_cpu_baseline()
+    elif world % 2 == 0:
+        # ---- CFG-branch split over GPU pairs
+        groups = [dist.new_group([2 * i, 2 * i + 1]) for i in range(world // 2)]
+        role = rank % 2
+        branch = GraphedBranch(unet, cond if role == 0 else unc, noise, tz)
+        split = CFGSplitDenoiser(branch, role, 9.0, group=groups[rank // 2])
+        ms2, xt2 = time_steps(split, noise, steps)
+        ref = run_steps(den, noise, ts[:3 + steps])
+        out["cfg_split"] = {"value": (world // 2) * 1000.0 / ms2, "unit": "steps/s", "ms_per_step": ms2, "requests_in_flight": world // 2,
+                            "speedup_per_request_vs_1gpu": ms / ms2, "collective": "NCCL all_gather of 2 x 655 KB per step inside each pair",
+                            "max_abs_diff_vs_single_gpu_cfg": float((xt2 - ref).abs().max()), "finite": bool(torch.isfinite(xt2).all())}
     del unet, den
     torch.cuda.empty_cache()
-    return {"metric": "i2vgen-xl UNet3D DDIM steps/s (2 UNet forwards + CFG per step)", "value": 1000.0 / ms, "unit": "steps/s",
-            "ms_per_step": ms, "latent": [1, 4, 16, 40, 64], "guide_scale": 9.0, "launches_per_step": (ops.launch_count() - l0) // steps,
-            "achieved_tflops": tfs, "frac_of_bf16_peak": tfs / tf_peak, "finite": finite,
-            "algorithmic_tflop_per_step": 2 * UNET_TFLOP_PER_FORWARD}
+    return out
 
 
 def run_ours(args, rank, world):
@@ -425,6 +580,12 @@ def run_ours(args, rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
+    # guard on what was timed: the generated ids must be valid vocabulary entries, identical from run to run (greedy,
+    # deterministic kernels) and identical between the HBM-resident and the host-input arms' code path
+    tok_a, tok_b = step_resident()[:BATCH], step_resident()[:BATCH]
+    tokens_check = {"in_vocab": bool(((tok_a >= 0) & (tok_a < VICUNA_7B["vocab_size"])).all()),
+                    "deterministic": bool((tok_a == tok_b).all()), "distinct_ids": int(tok_a.unique().numel()),
+                    "shape": list(tok_a.shape)}
 
     line = None
     if rank == 0:
@@ -434,7 +595,9 @@ def run_ours(args, rank, world):
         t_vit = timed(lambda: model.encode_images(pixels_d), 3)
         _, _, _, _, emb, _ = model.prepare_inputs_labels_for_multimodal(ids_d, None, torch.ones_like(ids_d), None, None, pixels_d)
         t_pre = timed(lambda: eng.prefill(emb), 3)
-        first = ops.argmax_rows(eng.prefill(emb))
+        logits0 = eng.prefill(emb)
+        tokens_check["prefill_logits_finite"] = bool(torch.isfinite(logits0).all())
+        first = ops.argmax_rows(logits0)
         eng.start_decode(first, NEW)
         eng.decode_steps(BATCH, 2)
         t_dec = timed(lambda: eng.decode_steps(BATCH, 1), 64)
@@ -459,20 +622,24 @@ def run_ours(args, rank, world):
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
                         "input": ("uint8 336x336 images, device-side LanguageBind transform" if args.e2e_input == "raw"
                                   else "pre-processed fp32 224x224 pixels")},
-                "gpu_launches": launches, "clocks": sampler.result(), "roofline": roof,
+                "gpu_launches": launches, "clocks": sampler.result(), "roofline": roof, "tokens_check": tokens_check,
                 "phases": {"vit_projector_ms": t_vit, "prefill_ms": t_pre, "decode_ms_per_token": t_dec,
                            "prefill_tokens_per_s": BATCH * S / (t_pre * 1e-3),
                            "decode_tokens_per_s": BATCH / (t_dec * 1e-3)}}
-        if world == 1 and not args.no_unet:
-            del model
-            torch.cuda.empty_cache()
-            line["unet"] = bench_unet(device, tf_peak)
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": "tokens/s", "cores": cpu_info.get("threads"),
-                                    "host_cores": _host_cores(), "kind": "port",
-                                    "sample": "oracle port, fp32, ViT 2/23 + LLaMA 2/32 layers (prefill B=1 S=768, 3 decode "
-                                              "steps B=8; layers scaled to full depth, lm_head timed once), batch 8",
-                                    **cpu_info}
+                                    "host_cores": _host_cores(), "kind": "port", "sample": CPU_SAMPLE_TEXT, **cpu_info}
+    # ---- the UNet half of the metric (every rank takes part when N > 1)
+    unet_line = None
+    if not args.no_unet:
+        del model
+        torch.cuda.empty_cache()
+        _, tf_peak_all, kind_all = measured_peaks()
+        unet_line = bench_unet(device, tf_peak_all, kind_all, steps=max(10, args.steps), rank=rank, world=world,
+                               with_cpu=(rank == 0))
+    if rank == 0:
+        if unet_line is not None:
+            line["unet"] = unet_line
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -90,10 +90,19 @@ int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
  * X [nb,h,w,cin]; Wt [cout, kh*kw, ceil64(cin)] (zero padded); out [nb,ho,wo,cout].
  * Replaces nn.Conv2d 3x3/1x1 (i2vgen util.py:651,677; Upsample/Downsample util.py:579-607,
  * 732-756), Conv3d (3,1,1) as kh=3,kw=1 over [b, f, h*w, c] (util.py:1360-1375), SEEM FPN convs
- * (transformer_encoder_fpn.py:54-107). stride in {1,2}. */
+ * (transformer_encoder_fpn.py:54-107). stride in {1,2}. Convolutions whose output-pixel tiles cannot fill the SMs
+ * (the 1280-channel UNet levels) run split-K over (tap, channel-chunk) steps: fp32 partials + tile counters in the
+ * workspace reported by vb200_conv_nhwc_workspace_size (0 for every other shape), zero-filled ONCE by the caller
+ * and left zeroed; with workspace == NULL the call runs unsplit. */
+size_t vb200_conv_nhwc_workspace_size(int64_t nb, int64_t h, int64_t w, int64_t cin, int64_t cout, int kh, int kw,
+                                      int stride, int pad_h, int pad_w);
 int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int64_t nb, int64_t h,
                          int64_t w, int64_t cin, int64_t cout, int kh, int kw, int stride,
-                         int pad_h, int pad_w, const vb_epilogue* epi, cudaStream_t stream);
+                         int pad_h, int pad_w, const vb_epilogue* epi, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream);
+/* 0 = the compile-time-specialised kernel (gemm_v2) whenever the operands allow its 256-bit epilogue accesses
+ * (default), 1 = the generic kernel only. Returns the previous setting. For A/B measurements and parity tests. */
+int vb200_set_gemm_impl(int impl);
 
 /* direct (SIMT) convolution for the two odd-shaped layers (cin < 8-aligned or tiny cout) */
 int vb200_conv_nhwc_direct(const void* X, const void* Wt, const void* bias, void* out, int64_t nb,
@@ -110,7 +119,8 @@ int vb200_row_rstd(const void* x, int64_t ldx, float* out, int64_t rows, int64_t
                    cudaStream_t stream);
 int vb200_layernorm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out,
                     int64_t ldo, int64_t rows, int64_t d, float eps, cudaStream_t stream);
-size_t vb200_groupnorm_workspace_size(int64_t n, int64_t groups);
+/* workspace: zero-filled ONCE by the caller before first use; the kernels leave its counters zeroed (no per-call memset) */
+size_t vb200_groupnorm_workspace_size(int64_t n, int64_t groups, int64_t c);
 int vb200_groupnorm_nhwc(const void* x, const void* weight, const void* bias, void* out, int64_t n,
                          int64_t spatial, int64_t c, int64_t groups, float eps, int act,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -3,6 +3,8 @@ modules, so that their HOST LOGIC (weight folding / packing, view slicing, call 
 without a GPU (`-m "not gpu"`). Never imported by the product: tests install it with monkeypatch over
 `vitron_b200.ops`; the kernels themselves are checked on the GPU against the oracle (tests/*_gpu.py).
 Each function mirrors the contract in vitron_b200/ops.py: bf16 storage, fp32 arithmetic."""
+import math
+
 import torch
 import torch.nn.functional as F
 
@@ -321,7 +323,89 @@ def rope_kv_append(qkv, positions, n_heads, head_dim, theta, k_pages=None, v_pag
     for j in (0, 1):
         x[:, j] = x[:, j] * cos + rot(x[:, j]) * sin
     qkv.copy_(x.view(T, -1).to(BF16))
+    if k_pages is not None and block_table is not None:   # K/V scatter into the paged cache [pages, H, page_size, D]
+        xb = qkv.view(T, 3, n_heads, head_dim)
+        for t in range(T):
+            slot = int(slot_of_token[t]) if slot_of_token is not None else int(positions[t])
+            if slot < 0:
+                continue
+            b = int(batch_of_token[t]) if batch_of_token is not None else 0
+            page = int(block_table[b, slot // page_size])
+            k_pages[page, :, slot % page_size] = xb[t, 1]
+            v_pages[page, :, slot % page_size] = xb[t, 2]
     return qkv
+
+
+def row_rstd(x, eps):
+    x2 = x.float().reshape(-1, x.shape[-1])
+    return torch.rsqrt(x2.pow(2).mean(-1) + eps)
+
+
+def rope_table(positions, head_dim, theta, out=None):
+    """fp32 [B, head_dim] = cos | sin of inv_freq_i * position (vb200_rope_table)."""
+    half = head_dim // 2
+    inv = torch.exp2(-(torch.arange(half, dtype=torch.float32) / half) * math.log2(theta))
+    ang = positions.float()[:, None] * inv[None]
+    tab = torch.cat([ang.cos(), ang.sin()], -1)
+    if out is not None:
+        out.copy_(tab)
+        return out
+    return tab
+
+
+def attn_decode_rope(qkv, table, k_pages, v_pages, block_table, kv_len, n_heads, head_dim, page_size, max_kv_len, scale=None,
+                     out=None):
+    """One decode token per sequence: RoPE on q / k from the cos|sin table, K/V of the new token appended at slot
+    kv_len - 1 of the paged cache, softmax attention over the kv_len keys (vb200_attn_decode_rope)."""
+    B = qkv.shape[0]
+    half = head_dim // 2
+    scale = head_dim ** -0.5 if scale is None else scale
+    x = qkv[:, :3 * n_heads * head_dim].float().view(B, 3, n_heads, head_dim)
+    cos = torch.cat([table[:, :half], table[:, :half]], -1)[:, None]
+    sin = torch.cat([table[:, half:], table[:, half:]], -1)[:, None]
+    rot = lambda t: torch.cat([-t[..., half:], t[..., :half]], -1)
+    q = (x[:, 0] * cos + rot(x[:, 0]) * sin).to(BF16).float()
+    k = (x[:, 1] * cos + rot(x[:, 1]) * sin).to(BF16)
+    v = x[:, 2].to(BF16)
+    res = torch.empty((B, n_heads * head_dim), dtype=BF16) if out is None else out
+    for b in range(B):
+        n = int(kv_len[b])
+        slot = n - 1
+        page = int(block_table[b, slot // page_size])
+        k_pages[page, :, slot % page_size] = k[b]
+        v_pages[page, :, slot % page_size] = v[b]
+        pages = block_table[b, :(n + page_size - 1) // page_size].long()
+        kk = k_pages[pages].permute(1, 0, 2, 3).reshape(n_heads, -1, head_dim)[:, :n].float()
+        vv = v_pages[pages].permute(1, 0, 2, 3).reshape(n_heads, -1, head_dim)[:, :n].float()
+        p = torch.softmax(torch.einsum("hd,hnd->hn", q[b], kk) * scale, -1)
+        res[b] = torch.einsum("hn,hnd->hd", p, vv).reshape(-1).to(BF16)
+    return res
+
+
+def argmax_rows(logits, out=None):
+    idx = logits.float().reshape(-1, logits.shape[-1]).argmax(-1)
+    if out is not None:
+        out.copy_(idx)
+        return out
+    return idx
+
+
+def argmax_advance(logits, out_idx, next_src=None, positions=None, kv_len=None, token_log=None, prompt_len=None):
+    """vb200_argmax_advance: arg-max + the device-side decode bookkeeping."""
+    idx = logits.float().argmax(-1)
+    out_idx.copy_(idx)
+    if next_src is not None:
+        next_src.copy_(idx.to(next_src.dtype))
+    if token_log is not None:
+        for b in range(idx.shape[0]):
+            step = int(kv_len[b]) - int(prompt_len[b])
+            if 0 <= step < token_log.shape[1]:
+                token_log[b, step] = idx[b]
+    if positions is not None:
+        positions.add_(1)
+    if kv_len is not None:
+        kv_len.add_(1)
+    return out_idx
 
 
 def region_mask_pool(feats, boxes, image_size):
@@ -356,5 +440,6 @@ def install(monkeypatch):
                  "mul_rows", "im2col_nchw", "pack_conv_weight", "conv_nhwc", "groupnorm_nhwc", "conv_nhwc_direct",
                  "upsample2x_nhwc", "softmax_rows", "preprocess_frames", "pack_glu_weight", "attention",
                  "splice_multimodal", "add", "patchify", "vit_embed_ln", "seem_attn_mask", "attention_short",
-                 "cfg_combine", "rope_kv_append", "region_mask_pool", "add_rowgroup"):
+                 "cfg_combine", "rope_kv_append", "region_mask_pool", "add_rowgroup", "row_rstd", "rope_table", "attn_decode_rope",
+                 "argmax_rows", "argmax_advance"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -54,3 +54,54 @@ def test_two_rank_gather_restores_request_order():
             assert full == want
             seen += mine
         assert sorted(seen) == list(range(n_total))
+
+
+def _cfg_worker(rank, world, port, q):
+    """CFG-branch split on 2 gloo ranks with an analytic eps-model standing in for the UNet: each rank evaluates ONE branch,
+    one all_gather per DDIM step; both ranks must end with the latent the serial two-branch sampler produces."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vitron_b200.unet_i2vgen import CFGSplitDenoiser, DiffusionDDIM
+    g = torch.Generator().manual_seed(3)
+    noise = torch.randn((1, 4, 4, 6, 8), generator=g)
+    wy, wu = torch.randn((4, 4), generator=g) * 0.3, torch.randn((4, 4), generator=g) * 0.3
+
+    def model(xt, t, w=None):
+        return torch.einsum("oc,bcfhw->bofhw", w, xt) * (1.0 + t.float().view(-1, 1, 1, 1, 1) / 1000.0)
+    combine = lambda y, u, s: u + s * (y - u)
+    diff = DiffusionDDIM()
+    # serial reference: both branches on this rank (guide_scale path of ddim_sample with a torch combine)
+    xt = noise.clone()
+    steps = (1 + torch.arange(0, 1000, 1000 // 5)).clamp(0, 999).flip(0)
+    for step in steps:
+        t = torch.full((1,), int(step), dtype=torch.long)
+        out = combine(model(xt, t, wy), model(xt, t, wu), 7.5)
+        xt = _ddim_update(diff, xt, t, out, 5)
+    branch = (lambda x, t: model(x, t, wy)) if rank == 0 else (lambda x, t: model(x, t, wu))
+    den = CFGSplitDenoiser(branch, role=rank, guide_scale=7.5, combine=combine)
+    got = diff.ddim_sample_loop(noise.clone(), den, model_kwargs=None, guide_scale=7.5, ddim_timesteps=5)
+    q.put((rank, float((got - xt).abs().max()), float(xt.abs().max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _ddim_update(diff, xt, t, out, ddim_timesteps):
+    """x_{t-1} from a given model output (the algebra of DiffusionDDIM.ddim_sample after the model call)."""
+    class Fixed:
+        pass
+    return diff.ddim_sample(xt, t, lambda x, tt: out, {}, None, ddim_timesteps)[0]
+
+
+def test_cfg_branch_split_two_ranks_equals_serial_cfg():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cfg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, scale in res:
+        assert err <= 1e-5 * max(scale, 1.0), (rank, err, scale)

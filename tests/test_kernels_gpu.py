@@ -30,15 +30,27 @@ def act_ref(x, act):
             ops.ACT_RELU: F.relu, ops.ACT_SILU: F.silu}[act](x)
 
 
+@pytest.fixture(params=[0, 1], ids=["v2", "generic"])
+def gemm_impl(request, cuda):
+    """Every GEMM / convolution test runs on both tcgen05 kernels: the compile-time-specialised v2 (default whenever
+    the operands allow its 256-bit epilogue accesses) and the generic kernel."""
+    from vitron_b200 import ops
+    prev = ops.set_gemm_impl(request.param)
+    yield request.param
+    ops.set_gemm_impl(prev)
+
+
 GEMM_SHAPES = [
     (128, 128, 64), (128, 256, 128), (256, 512, 256), (200, 136, 72), (2056, 1024, 1024),
     (257, 3072, 1024), (1000, 4096, 1024), (6144, 1024, 4096), (101, 512, 512), (77, 1024, 1024),
-    (4096, 32000, 128), (130, 8, 64),
+    (4096, 32000, 128), (130, 8, 64), (300, 48, 128), (1000, 80, 320), (129, 2560, 64), (40960, 320, 320),
+    # few tiles, long K: split-K on the v2 kernel
+    (640, 1280, 3840), (200, 1280, 5120), (2560, 1280, 11520), (128, 256, 4096), (640, 336, 2048),
 ]
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-def test_gemm_plain(cuda, M, N, K):
+def test_gemm_plain(cuda, gemm_impl, M, N, K):
     from vitron_b200 import ops
     a, w = rnd((M, K), cuda, 1), rnd((N, K), cuda, 2, 0.05)
     out = ops.gemm(a, w)
@@ -59,7 +71,7 @@ def test_gemm_swap_small_m(cuda, M, N, K):
 
 
 @pytest.mark.parametrize("act", [1, 2, 3, 4])
-def test_gemm_bias_act_residual(cuda, act):
+def test_gemm_bias_act_residual(cuda, gemm_impl, act):
     from vitron_b200 import ops
     M, N, K = 777, 1024, 512
     a, w, bias, res = rnd((M, K), cuda, 1), rnd((N, K), cuda, 2, 0.05), rnd((N,), cuda, 3), rnd((M, N), cuda, 4)
@@ -79,7 +91,7 @@ def test_gemm_bias_act_residual(cuda, act):
 
 @pytest.mark.parametrize("M", [8, 300, 2048])
 @pytest.mark.parametrize("glu", [1, 2])
-def test_gemm_glu(cuda, M, glu):
+def test_gemm_glu(cuda, gemm_impl, M, glu):
     from vitron_b200 import ops
     K, Fd = 512, 1376
     a = rnd((M, K), cuda, 1)
@@ -94,7 +106,42 @@ def test_gemm_glu(cuda, M, glu):
     close(out, ref, 4e-2, 2e-2, f"glu {glu} M={M}")
 
 
-def test_gemm_rowbias_strided(cuda):
+def test_gemm_v2_feature_matrix(cuda, gemm_impl):
+    """rowscale (folded RMSNorm), rowscale + SwiGLU, residual / alpha through the split-K finaliser, fp32 output, bias-free
+    residual, all on shapes that take the specialised variants (and the same calls on the generic kernel)."""
+    from vitron_b200 import ops
+    M, N, K = 6144, 512, 256
+    a, w = rnd((M, K), cuda, 1), rnd((N, K), cuda, 2, 0.05)
+    rsc = (torch.rand((M,), device=cuda) + 0.5).float()
+    ref = (a.float() @ w.float().t()) * rsc[:, None]
+    close(ops.gemm(a, w, rowscale=rsc), ref, 3e-2, 1.6e-2, "rowscale")
+    wa, wb = rnd((N, K), cuda, 3, 0.05), rnd((N, K), cuda, 4, 0.05)
+    out = ops.gemm(a, ops.pack_glu_weight(wa, wb), glu=1, rowscale=rsc)
+    xa, xb = (a.float() @ wa.float().t()) * rsc[:, None], (a.float() @ wb.float().t()) * rsc[:, None]
+    close(out, F.silu(xa) * xb, 4e-2, 2e-2, "rowscale + swiglu")
+    close(ops.gemm(a, w, rowscale=rsc, out_fp32=True), ref, 2e-3, 2e-3, "rowscale fp32 out")
+    # split-K shapes with the whole epilogue in the finaliser
+    M, N, K = 640, 1280, 3840
+    a, w = rnd((M, K), cuda, 5), rnd((N, K), cuda, 6, 0.02)
+    bias, res = rnd((N,), cuda, 7), rnd((M, N), cuda, 8)
+    rb = rnd((M // 40, N), cuda, 9)
+    ref = a.float() @ w.float().t() + bias.float()
+    close(ops.gemm(a, w, bias=bias, residual=res, alpha=0.5), res.float() + 0.5 * ref, 5e-2, 2e-2, "split residual")
+    close(ops.gemm(a, w, bias=bias, act=4, rowbias=rb, rowbias_rows=40),
+          F.silu(ref + rb.float().repeat_interleave(40, 0)), 5e-2, 2e-2, "split act rowbias")
+    wa, wb = rnd((N // 2, K), cuda, 10, 0.02), rnd((N // 2, K), cuda, 11, 0.02)
+    out = ops.gemm(a, ops.pack_glu_weight(wa, wb), glu=2)
+    close(out, (a.float() @ wa.float().t()) * F.gelu(a.float() @ wb.float().t()), 5e-2, 2e-2, "split geglu")
+    close(ops.gemm(a, w, bias=bias, out_fp32=True), ref, 5e-3, 3e-3, "split fp32 out")
+    r2 = res.clone()
+    ops.gemm(a, w, residual=r2, out=r2)
+    close(r2, res.float() + a.float() @ w.float().t(), 5e-2, 2e-2, "split in-place residual")
+    # repeated split launches reuse the self-zeroing counters
+    for _ in range(3):
+        close(ops.gemm(a, w, bias=bias), ref, 5e-2, 2e-2, "split repeat")
+
+
+def test_gemm_rowbias_strided(cuda, gemm_impl):
     from vitron_b200 import ops
     M, N, K = 640, 320, 256
     big = rnd((M, K + 64), cuda, 1)
@@ -112,11 +159,14 @@ CONVS = [
     (16, 5, 8, 1280, 1280, 3, 3, 1), (3, 10, 16, 320, 640, 1, 1, 1), (16, 40, 64, 320, 320, 3, 3, 2),
     (4, 9, 13, 128, 96, 3, 3, 2), (2, 16, 2560 // 16, 320, 320, 3, 1, 1), (1, 64, 64, 512, 512, 3, 3, 1),
     (1, 33, 200, 192, 512, 1, 1, 1), (2, 12, 12, 8, 320, 3, 3, 1), (2, 12, 12, 320, 8, 3, 3, 1),
+    # few pixel tiles, long K (UNet 1280-channel levels, temporal Conv3d (3,1,1) as kh=3 kw=1): split-K on v2
+    (16, 10, 16, 1280, 1280, 3, 3, 1), (1, 16, 40, 1280, 1280, 3, 1, 1), (1, 16, 160, 1280, 1280, 3, 1, 1),
+    (16, 5, 8, 2560, 1280, 3, 3, 1), (2, 5, 8, 640, 48, 3, 3, 1),
 ]
 
 
 @pytest.mark.parametrize("nb,h,w,cin,cout,kh,kw,stride", CONVS)
-def test_conv_nhwc(cuda, nb, h, w, cin, cout, kh, kw, stride):
+def test_conv_nhwc(cuda, gemm_impl, nb, h, w, cin, cout, kh, kw, stride):
     from vitron_b200 import ops
     x = rnd((nb, h, w, cin), cuda, 1)
     wt = rnd((cout, cin, kh, kw), cuda, 2, 0.03)
@@ -126,7 +176,7 @@ def test_conv_nhwc(cuda, nb, h, w, cin, cout, kh, kw, stride):
     close(out, ref.permute(0, 2, 3, 1), 4e-2 * math.sqrt(cin * kh * kw / 576), 2e-2, "conv")
 
 
-def test_conv_epilogue(cuda):
+def test_conv_epilogue(cuda, gemm_impl):
     from vitron_b200 import ops
     nb, h, w, cin, cout = 4, 20, 32, 128, 256
     x, wt = rnd((nb, h, w, cin), cuda, 1), rnd((cout, cin, 3, 3), cuda, 2, 0.03)
@@ -138,6 +188,13 @@ def test_conv_epilogue(cuda):
     d = ops.conv_nhwc_direct(x, wt.permute(0, 2, 3, 1).reshape(cout, 9, cin).contiguous(), bias, 3, 3)
     ref2 = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
     close(d, ref2, 5e-2, 2e-2, "direct conv")
+    # few-tile convolution (split-K on v2) with the ResBlock epilogue: bias + time-embedding rowbias + residual
+    nb, h, w, cin, cout = 16, 5, 8, 1280, 1280
+    x, wt = rnd((nb, h, w, cin), cuda, 6), rnd((cout, cin, 3, 3), cuda, 7, 0.01)
+    bias, rb, res = rnd((cout,), cuda, 8), rnd((1, cout), cuda, 9), rnd((nb, h, w, cout), cuda, 10)
+    out = ops.conv_nhwc(x, ops.pack_conv_weight(wt), 3, 3, bias=bias, rowbias=rb, rowbias_rows=nb * h * w, residual=res)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
+    close(out, res.float() + ref + rb.float()[0], 8e-2, 2e-2, "split conv epilogue")
 
 
 @pytest.mark.parametrize("rows,d", [(7, 4096), (300, 1024), (33, 320), (5, 1280), (3, 11008), (9, 512),
@@ -153,16 +210,22 @@ def test_norms(cuda, rows, d):
 
 @pytest.mark.parametrize("n,sp,c,act", [(16, 40 * 64, 320, 4), (2, 16 * 100, 640, 0), (3, 77, 1280, 4), (1, 64 * 64, 512, 3),
                                         (2, 50, 2560, 4), (2, 33, 960, 4),
-                                        # slabs too large for the single-pass kernel -> stats + apply
                                         (1, 16 * 2560, 320, 4), (1, 16 * 640, 640, 4), (2, 5000, 1920, 0),
-                                        # UNet temporal layouts on the single-pass kernel
-                                        (1, 16 * 160, 1280, 4), (1, 16 * 40, 1280, 0), (16, 20 * 32, 640, 4)])
+                                        # UNet temporal layouts
+                                        (1, 16 * 160, 1280, 4), (1, 16 * 40, 1280, 0), (16, 20 * 32, 640, 4),
+                                        # narrow groups (VAE: 4 channels per group), fewer rows than a CTA pass, one row
+                                        (2, 300, 128, 4), (3, 3, 320, 0), (4, 1, 64, 3), (16, 5 * 8, 2560, 4)])
 def test_groupnorm(cuda, n, sp, c, act):
     from vitron_b200 import ops
     x, w, b = rnd((n, sp, c), cuda, 1, 1.5), rnd((c,), cuda, 2), rnd((c,), cuda, 3)
     ref = F.group_norm(x.float().permute(0, 2, 1), 32, w.float(), b.float(), 1e-5).permute(0, 2, 1)
     ref = act_ref(ref, act)
     close(ops.groupnorm_nhwc(x, w, b, 32, 1e-5, act=act), ref, 3e-2, 2e-2, "groupnorm")
+    # the workspace hands itself back zeroed: a second call (and an in-place one) must give the same result
+    y2 = ops.groupnorm_nhwc(x, w, b, 32, 1e-5, act=act)
+    close(y2, ref, 3e-2, 2e-2, "groupnorm (second call)")
+    xi = x.clone()
+    close(ops.groupnorm_nhwc(xi, w, b, 32, 1e-5, act=act, out=xi), ref, 3e-2, 2e-2, "groupnorm (in place)")
 
 
 def sdpa_ref(q, k, v, scale, causal=False, kv_len=None, mask=None):

@@ -37,13 +37,15 @@ SIGNATURES = {
     "vb200_attention_tc_occupancy": (_i32, [_i32]),
     "vb200_gemm_bf16_workspace_size": (_sz, [_i64, _i64, _i64]),
     "vb200_gemm_bf16": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, C.POINTER(Epilogue), _p, _sz, _p]),
+    "vb200_conv_nhwc_workspace_size": (_sz, [_i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32]),
     "vb200_conv_nhwc_bf16": (_i32, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
-                                    C.POINTER(Epilogue), _p]),
+                                    C.POINTER(Epilogue), _p, _sz, _p]),
+    "vb200_set_gemm_impl": (_i32, [_i32]),
     "vb200_conv_nhwc_direct": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
     "vb200_rmsnorm": (_i32, [_p, _i64, _p, _p, _i64, _i64, _i64, _f, _p]),
     "vb200_row_rstd": (_i32, [_p, _i64, _p, _i64, _i64, _f, _p]),
     "vb200_layernorm": (_i32, [_p, _i64, _p, _p, _p, _i64, _i64, _i64, _f, _p]),
-    "vb200_groupnorm_workspace_size": (_sz, [_i64, _i64]),
+    "vb200_groupnorm_workspace_size": (_sz, [_i64, _i64, _i64]),
     "vb200_groupnorm_nhwc": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _i32, _p, _sz, _p]),
     "vb200_attention": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64] + [_i64] * 12 +
                         [_f, _i32, _p, _p, _i64, _i64, _i64, _p]),

@@ -39,6 +39,19 @@ class VisionProjector:
             self.linears = [(get(f"{2 * i}.weight"), get(f"{2 * i}.bias")) for i in range(self.depth)]
         return self
 
+    def state_dict(self, prefix=""):
+        if self.projector_type == "linear":
+            return {prefix + "weight": self.linears[0][0], prefix + "bias": self.linears[0][1]}
+        out = {}
+        for i, (w, b) in enumerate(self.linears):
+            out[f"{prefix}{2 * i}.weight"], out[f"{prefix}{2 * i}.bias"] = w, b
+        return out
+
+    def parameters(self):
+        for w, b in self.linears:
+            yield w
+            yield b
+
     def __call__(self, x):
         if self.depth == 0:
             return x
@@ -80,6 +93,20 @@ class RegionExtractor:
         self.loc = [(w0p, get("loc_encoder.loc_encoder.0.bias")),
                     (get("loc_encoder.loc_encoder.2.weight"), get("loc_encoder.loc_encoder.2.bias"))]
         return self
+
+    def state_dict(self, prefix=""):
+        out = {}
+        for i, (w, b) in enumerate(self.mlp):
+            out[f"{prefix}region_linear.layers.{i}.weight"], out[f"{prefix}region_linear.layers.{i}.bias"] = w, b
+        out[prefix + "loc_encoder.loc_encoder.0.weight"] = self.loc[0][0][:, :4].contiguous()
+        out[prefix + "loc_encoder.loc_encoder.0.bias"] = self.loc[0][1]
+        out[prefix + "loc_encoder.loc_encoder.2.weight"], out[prefix + "loc_encoder.loc_encoder.2.bias"] = self.loc[1]
+        return out
+
+    def parameters(self):
+        for w, b in self.mlp + self.loc:
+            yield w
+            yield b
 
     def forward(self, feats, regions):
         """feats [B, S, C] patch features, regions: list of B [x1, y1, x2, y2] -> [B, 1, out_dim]."""

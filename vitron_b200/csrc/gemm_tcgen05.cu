@@ -17,184 +17,9 @@
 // q/k/v/out/fc1/fc2, mm_projector, region MLP, every Linear / Conv2d(3x3,1x1) / Conv3d(3,1,1) of
 // UNetSD_I2VGen, SEEM FPN convs + mask einsum, GLIGEN fuser linears.
 #include <cstdlib>
-#include "common.cuh"
-#include "vitron_b200.h"
+#include "gemm_v2.cuh"
 
 namespace vb {
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quadrant
-constexpr int EPI_THREADS = 32 * NUM_EPI_WARPS;
-constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
-
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the epilogue warps only
-  asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-}
-constexpr int SMEM_LIMIT = 227 * 1024;
-
-struct GemmParams {
-  int M, N;           // logical output extent (rows of A-space, rows of B)
-  int num_k_blocks;   // k-steps of BLOCK_K (conv: taps * cin_chunks)
-  int splits;         // split-K factor (>=1)
-  int m_blocks, n_blocks;
-  // ---- A addressing
-  int a_mode;         // 0: 2-D matrix, 1: NHWC conv
-  int cin_chunks;     // conv: BLOCK_K chunks per tap
-  int kw;             // conv: kernel width (tap -> dy = tap / kw, dx = tap % kw)
-  int stride, pad_h, pad_w;
-  int tw, th, tn;     // conv: output-pixel tile (tw*th*tn <= 128)
-  int wo, ho, nb;     // conv: output width / height / images
-  int tiles_w, tiles_h;
-  uint32_t a_box_bytes;
-  // ---- epilogue
-  void* out;          // bf16 or fp32 [rows, ldo]
-  long long ldo;
-  const bf16* bias;      // [N] or null
-  const bf16* rowbias;   // [groups, N] or null; group = out_row / rowbias_rows
-  int rowbias_rows;
-  const bf16* residual;  // [rows, ldr] or null; out = residual + alpha * v
-  long long ldr;
-  float alpha;
-  const float* rowscale;  // fp32 per output row (C orientation) or null
-  int act;            // VB_ACT_*
-  int glu;            // VB_GLU_*
-  int out_fp32;
-  int swap;           // accumulator rows are output columns (decode / tiny-M path) -> workspace
-  float* ws;          // split-K / swap workspace [splits, rows_c, cols_c] fp32
-  long long ws_split_stride;
-  long long ws_ld;
-  int c_box;          // > 0: bf16 output leaves through smem + TMA store in boxes of c_box (64 | 32) columns
-  int* counters;      // one arrival counter per output tile (zero on entry, zero again on exit)
-  int rows_c, cols_c; // extent of the output in C orientation (rows = tokens, cols = features)
-};
-
-__device__ __forceinline__ float apply_act(float x, int act) {
-  switch (act) {
-    case VB_ACT_GELU: return gelu_erf_fast(x);  // exact-erf GELU, |erf error| <= 1.5e-7, straight-line (erff's branches
-                                                // made an M = 65536, N = 768 GELU epilogue ALU-bound: 274 us vs ~40)
-    case VB_ACT_QUICK_GELU: return quick_gelu(x);
-    case VB_ACT_RELU: return fmaxf(x, 0.f);
-    case VB_ACT_SILU: return silu(x);
-    default: return x;
-  }
-}
-
-// One 8-wide output item of the split-K finalisation: out[row, oc..oc+8) = epi(sum_s ws[s, row, cols]).
-// Partials are read with ld.global.cg (L2) because they were written by other CTAs.
-__device__ __forceinline__ void reduce_item(const float* __restrict__ ws, int splits, long long split_stride,
-                                            long long ws_ld, int row, int oc, int ncols, void* out, long long ldo,
-                                            const bf16* __restrict__ bias, const bf16* __restrict__ rowbias,
-                                            int rowbias_rows, const bf16* __restrict__ residual, long long ldr,
-                                            float alpha, int act, int glu, int out_fp32,
-                                            const float* __restrict__ rowscale = nullptr) {
-  const int n_out_total = glu != VB_GLU_NONE ? ncols / 2 : ncols;
-  int ca = oc, cb = -1;
-  if (glu != VB_GLU_NONE) {
-    ca = (oc / 16) * 32 + (oc % 16);
-    cb = ca + 16;
-  }
-  float a[8], b[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
-  const bool vec = (oc + 8 <= n_out_total) && ((ws_ld & 3) == 0);
-  for (int s = 0; s < splits; ++s) {
-    const float* src = ws + s * split_stride + row * ws_ld;
-    if (vec) {
-      const float4 x0 = __ldcg(reinterpret_cast<const float4*>(src + ca));
-      const float4 x1 = __ldcg(reinterpret_cast<const float4*>(src + ca + 4));
-      a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w;
-      a[4] += x1.x; a[5] += x1.y; a[6] += x1.z; a[7] += x1.w;
-      if (cb >= 0) {
-        const float4 y0 = __ldcg(reinterpret_cast<const float4*>(src + cb));
-        const float4 y1 = __ldcg(reinterpret_cast<const float4*>(src + cb + 4));
-        b[0] += y0.x; b[1] += y0.y; b[2] += y0.z; b[3] += y0.w;
-        b[4] += y1.x; b[5] += y1.y; b[6] += y1.z; b[7] += y1.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (oc + j < n_out_total) {
-          a[j] += __ldcg(src + ca + j);
-          if (cb >= 0) b[j] += __ldcg(src + cb + j);
-        }
-      }
-    }
-  }
-  const bf16* rb = rowbias ? rowbias + (row / rowbias_rows) * static_cast<long long>(ncols) : nullptr;
-  float v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    v[j] = 0.f;
-    if (oc + j >= n_out_total) continue;
-    float va = a[j], vb_ = b[j];
-    if (rowscale) { const float rs = rowscale[row]; va *= rs; vb_ *= rs; }
-    if (bias) {
-      va += __bfloat162float(bias[ca + j]);
-      if (cb >= 0) vb_ += __bfloat162float(bias[cb + j]);
-    }
-    if (rb) {
-      va += __bfloat162float(rb[ca + j]);
-      if (cb >= 0) vb_ += __bfloat162float(rb[cb + j]);
-    }
-    float r;
-    if (glu == VB_GLU_SWIGLU) r = silu(va) * vb_;
-    else if (glu == VB_GLU_GEGLU) r = va * gelu_erf(vb_);
-    else r = apply_act(va, act);
-    if (residual) r = __bfloat162float(residual[row * ldr + oc + j]) + alpha * r;
-    else r *= alpha;
-    v[j] = r;
-  }
-  if (out_fp32) {
-    float* dst = reinterpret_cast<float*>(out) + row * ldo + oc;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (oc + j < n_out_total) dst[j] = v[j];
-  } else {
-    bf16* dst = reinterpret_cast<bf16*>(out) + row * ldo + oc;
-    if (oc + 8 <= n_out_total && (ldo & 7) == 0) {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                                  pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (oc + j < n_out_total) dst[j] = __float2bfloat16(v[j]);
-    }
-  }
-}
-
-struct TileCoord {
-  int m_blk, n_blk, split;
-};
-
-__device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int unit) {
-  TileCoord t;
-  int tile = unit / p.splits;
-  t.split = unit - tile * p.splits;
-  // grouped rasterisation: 16 m-blocks wide so a wave of CTAs re-uses A and B tiles through L2
-  const int GROUP_M = 16;
-  int per_group = GROUP_M * p.n_blocks;
-  int group = tile / per_group;
-  int first_m = group * GROUP_M;
-  int gsize = min(p.m_blocks - first_m, GROUP_M);
-  int in_group = tile - group * per_group;
-  t.m_blk = first_m + in_group % gsize;
-  t.n_blk = in_group / gsize;
-  return t;
-}
-
-__device__ __forceinline__ void split_range(const GemmParams& p, int split, int& k0, int& k1) {
-  int base = p.num_k_blocks / p.splits, rem = p.num_k_blocks % p.splits;
-  k0 = split * base + min(split, rem);
-  k1 = k0 + base + (split < rem ? 1 : 0);
-}
 
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -699,13 +524,13 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits,
                                      void* out, long long ldo, const bf16* __restrict__ bias,
                                      const bf16* __restrict__ rowbias, int rowbias_rows,
                                      const bf16* __restrict__ residual, long long ldr, float alpha,
-                                     int act, int glu, int out_fp32) {
+                                     int act, int glu, int out_fp32, const float* __restrict__ rowscale) {
   const int n_out_total = glu != VB_GLU_NONE ? ncols / 2 : ncols;
   const int groups = (n_out_total + 7) / 8;
   long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * groups) return;
   reduce_item(ws, splits, split_stride, ws_ld, static_cast<int>(idx / groups), static_cast<int>(idx % groups) * 8,
-              ncols, out, ldo, bias, rowbias, rowbias_rows, residual, ldr, alpha, act, glu, out_fp32);
+              ncols, out, ldo, bias, rowbias, rowbias_rows, residual, ldr, alpha, act, glu, out_fp32, rowscale);
 }
 
 // ------------------------------------------------------------------ host side
@@ -836,19 +661,140 @@ static int validate_epi(const vb_epilogue* e, long long N) {
   return VB_OK;
 }
 
+
+// ------------------------------------------------------------------ v2 planning
+static int g_gemm_impl = 0;  // 0: v2 whenever eligible, 1: generic kernel only (A/B measurements, parity tests of both)
+
+struct TilePlan {
+  int bn, splits;
+};
+
+// Tile width and split-K factor for `mb` 128-row m-blocks x N columns x `kblocks` k-steps. Time model in units of one
+// 128x256x64 k-step: per-unit main loop = k-steps x tk[bn] (narrow tiles are L2->smem bound: measured in round 1,
+// profiles/r01_tile_width_sweep.jsonl), waves = ceil(units / SMs); a split costs its partial write + the finaliser.
+static TilePlan plan_tiles(long long mb, long long N, int kblocks, bool allow_split, long long out_rows) {
+  const int sms = vb_num_sms();
+  const int cands[5] = {256, 160, 128, 64, 32};
+  const float tk[5] = {1.0f, 0.78f, 0.76f, 0.625f, 0.57f};
+  TilePlan best = {256, 1};
+  float best_t = 1e30f;
+  if (const char* force = getenv("VB200_FORCE_BN")) {
+    const int v = atoi(force);
+    if (v == 256 || v == 160 || v == 128 || v == 64 || v == 32) return {v, 1};
+  }
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i];
+    const long long nbk = (N + bn - 1) / bn;
+    const long long tiles = mb * nbk;
+    if (tiles > 4096 && allow_split) { /* counters cover 4096 tiles: no split for such grids (they fill the GPU anyway) */ }
+    for (int sp = 1; sp <= 8; ++sp) {
+      if (sp > 1) {
+        if (!allow_split || tiles > 4096 || tiles * 10 >= static_cast<long long>(sms) * 7) break;
+        if (kblocks / sp < 4) break;
+        if (static_cast<unsigned long long>(sp) * out_rows * N * sizeof(float) > (64ull << 20)) break;
+      }
+      const long long units = tiles * sp;
+      const long long waves = (units + sms - 1) / sms;
+      const int kpu = (kblocks + sp - 1) / sp;
+      float t = static_cast<float>(waves) * (kpu * tk[i] + (sp > 1 ? 1.5f : 0.f));
+      t += 2.0f * bn / 256.f;
+      // a split writes and re-reads sp fp32 copies of the output (~5 TB/s through L2; one unit = 0.27 us) and pays one
+      // more launch (~2.5 us)
+      if (sp > 1) t += static_cast<float>(sp) * out_rows * N * 8.0f / 5.0e6f / 0.27f + 9.0f;
+      if (t < best_t - 1e-4f) { best_t = t; best = {bn, sp}; }
+    }
+  }
+  return best;
+}
+
+static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
+// can the v2 kernel (256-bit epilogue accesses) serve this call?
+static bool v2_eligible(const vb_epilogue* e, const void* out, long long ldo, long long N) {
+  if (g_gemm_impl == 1) return false;
+  if (!aligned32(out)) return false;
+  if (e->out_fp32 ? (ldo % 8) != 0 : (ldo % 16) != 0) return false;
+  if (e->bias && !aligned32(e->bias)) return false;
+  if (e->rowbias && (!aligned32(e->rowbias) || (N % 16) != 0)) return false;
+  if (e->residual && (!aligned32(e->residual) || (e->ldr % 16) != 0)) return false;
+  if ((N % 32) != 0 && (N % 16) != 0) return false;  // ragged tail handled per element, rows must stay 32-byte aligned
+  return true;
+}
+
+static int v2_need(const vb_epilogue* e, int splits) {
+  if (splits > 1) return F_WS;
+  int need = 0;
+  if (e->rowscale) need |= F_RS;
+  if (e->rowbias) need |= F_RB;
+  if (e->residual || e->alpha != 1.0f) need |= F_RES;
+  if (e->act != VB_ACT_NONE) need |= F_ACT;
+  if (e->glu != VB_GLU_NONE) need |= F_GLU;
+  if (e->out_fp32) need |= F_F32;
+  return need;
+}
+
+static int launch_gemm_v2(int bn, int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                          cudaStream_t stream) {
+  int r;
+  switch (bn) {
+    case 256: r = launch_gemm_v2_256(need, ta, tb, p, stream); break;
+    case 160: r = launch_gemm_v2_160(need, ta, tb, p, stream); break;
+    case 128: r = launch_gemm_v2_128(need, ta, tb, p, stream); break;
+    case 64: r = launch_gemm_v2_64(need, ta, tb, p, stream); break;
+    case 32: r = launch_gemm_v2_32(need, ta, tb, p, stream); break;
+    default: return VB_ERR_ARG;
+  }
+  if (r != VB_OK || !(need & F_WS)) return r;
+  // split-K: sum the partials in split order + the fused epilogue, one thread per 8 outputs of a row
+  const int n_out = p.glu != VB_GLU_NONE ? p.N / 2 : p.N;
+  const long long items = static_cast<long long>(p.M) * ((n_out + 7) / 8);
+  splitk_reduce_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, stream>>>(
+      p.ws, p.splits, p.ws_split_stride, p.ws_ld, p.M, p.N, p.out, p.ldo, p.bias, p.rowbias, p.rowbias_rows, p.residual,
+      p.ldr, p.alpha, p.act, p.glu, p.out_fp32, p.rowscale);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+// conv output-pixel tile tw x th x tn (<= 128 accumulator rows): the shape that covers the output with the fewest
+// tiles; ties go to the widest tile (longest contiguous runs for the TMA boxes)
+static void conv_pixel_tile(int wo, int ho, long long nb, int& tw, int& th, int& tn) {
+  tw = th = tn = 1;
+  long long best = -1;
+  for (int cw = wo < 128 ? wo : 128; cw >= 1; --cw) {
+    const int hmax = 128 / cw < ho ? 128 / cw : ho;
+    for (int ch = hmax; ch >= 1; --ch) {
+      int cn = 128 / (cw * ch);
+      if (cn > nb) cn = static_cast<int>(nb);
+      const long long blocks = static_cast<long long>((wo + cw - 1) / cw) * ((ho + ch - 1) / ch) * ((nb + cn - 1) / cn);
+      if (best < 0 || blocks < best) { best = blocks; tw = cw; th = ch; tn = cn; }
+    }
+  }
+}
+
 }  // namespace vb
 
 using namespace vb;
+
+extern "C" int vb200_set_gemm_impl(int impl) {
+  const int prev = g_gemm_impl;
+  if (impl == 0 || impl == 1) g_gemm_impl = impl;
+  return prev;
+}
 
 int vb_launch_gemv(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int64_t M,
                    int64_t N, int64_t K, const vb_epilogue* e, cudaStream_t stream);  // gemv.cu
 
 extern "C" size_t vb200_gemm_bf16_workspace_size(int64_t M, int64_t N, int64_t K) {
   // M <= 16: weight-streaming kernel (gemv.cu), no workspace; 16 < M <= 64: swap-AB + split-K
-  if (M <= 16 || N <= 0 || K <= 0 || M > 64) return 0;
+  if (M <= 16 || N <= 0 || K <= 0) return 0;
   // [tile counters | fp32 partials]; the caller zero-fills it ONCE, the kernels leave the counters zeroed
-  return GEMM_COUNTER_BYTES + static_cast<size_t>(swap_splits(M, N, K)) * static_cast<size_t>(M) *
-                                  static_cast<size_t>(N) * sizeof(float);
+  if (M <= 64)
+    return GEMM_COUNTER_BYTES + static_cast<size_t>(swap_splits(M, N, K)) * static_cast<size_t>(M) *
+                                    static_cast<size_t>(N) * sizeof(float);
+  // M > 64: split-K only when the tile set cannot fill the SMs (plan_tiles)
+  const TilePlan pl = plan_tiles((M + BLOCK_M - 1) / BLOCK_M, N, static_cast<int>((K + BLOCK_K - 1) / BLOCK_K), true, M);
+  if (pl.splits <= 1) return 0;
+  return GEMM_COUNTER_BYTES + static_cast<size_t>(pl.splits) * static_cast<size_t>(M) * static_cast<size_t>(N) * sizeof(float);
 }
 
 extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
@@ -914,10 +860,35 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
     return launch_gemm(bn, ta, tb, ta, p, stream);  // the last CTA of every tile finalises it (no TMA store)
   }
 
-  int bn = pick_block_n(M, N, epi->glu);
   p.M = static_cast<int>(M);
   p.N = static_cast<int>(N);
   p.m_blocks = static_cast<int>((M + BLOCK_M - 1) / BLOCK_M);
+  if (v2_eligible(epi, out, ldo, N)) {
+    TilePlan pl = plan_tiles(p.m_blocks, N, p.num_k_blocks, true, M);
+    if (pl.splits > 1) {
+      const size_t need_ws = GEMM_COUNTER_BYTES + static_cast<size_t>(pl.splits) * M * N * sizeof(float);
+      if (workspace == nullptr || workspace_bytes < need_ws || !aligned32(workspace)) pl = plan_tiles(p.m_blocks, N, p.num_k_blocks, false, M);
+    }
+    p.n_blocks = static_cast<int>((N + pl.bn - 1) / pl.bn);
+    p.splits = pl.splits;
+    if (pl.splits > 1) {
+      p.counters = reinterpret_cast<int*>(workspace);
+      p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + GEMM_COUNTER_BYTES);
+      p.ws_ld = N;
+      p.ws_split_stride = M * N;
+      p.vec_ok = (N % 8) == 0;
+    }
+    uint64_t dA[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t sA[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t bA[2] = {BLOCK_K, BLOCK_M};
+    if (int r = make_tmap(&ta, A, 2, dA, sA, bA, estr2)) return r;
+    uint64_t dB[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t sB[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(pl.bn)};
+    if (int r = make_tmap(&tb, W, 2, dB, sB, bB, estr2)) return r;
+    return launch_gemm_v2(pl.bn, v2_need(epi, pl.splits), ta, tb, p, stream);
+  }
+  int bn = pick_block_n(M, N, epi->glu);
   p.n_blocks = static_cast<int>((N + bn - 1) / bn);
   p.splits = 1;
   uint64_t dA[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
@@ -942,10 +913,34 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   return launch_gemm(bn, ta, tb, tc, p, stream);
 }
 
+static void conv_out_dims(int64_t h, int64_t w, int kh, int kw, int stride, int pad_h, int pad_w, int& ho, int& wo) {
+  ho = static_cast<int>((h + 2 * pad_h - kh) / stride + 1);
+  wo = static_cast<int>((w + 2 * pad_w - kw) / stride + 1);
+}
+
+extern "C" size_t vb200_conv_nhwc_workspace_size(int64_t nb, int64_t h, int64_t w, int64_t cin, int64_t cout, int kh,
+                                                 int kw, int stride, int pad_h, int pad_w) {
+  // split-K partials for convolutions whose pixel tiles cannot fill the SMs (0 for every other shape);
+  // [tile counters | fp32 partials], zero-filled ONCE by the caller, left zeroed by the kernel
+  if (nb <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || kh <= 0 || kw <= 0 || (stride != 1 && stride != 2)) return 0;
+  int ho, wo;
+  conv_out_dims(h, w, kh, kw, stride, pad_h, pad_w, ho, wo);
+  if (ho <= 0 || wo <= 0) return 0;
+  int tw, th, tn;
+  conv_pixel_tile(wo, ho, nb, tw, th, tn);
+  const long long mb = static_cast<long long>((wo + tw - 1) / tw) * ((ho + th - 1) / th) * ((nb + tn - 1) / tn);
+  const int kblocks = kh * kw * static_cast<int>((cin + BLOCK_K - 1) / BLOCK_K);
+  const long long rows = nb * ho * wo;
+  const TilePlan pl = plan_tiles(mb, cout, kblocks, true, rows);
+  if (pl.splits <= 1) return 0;
+  return GEMM_COUNTER_BYTES + static_cast<size_t>(pl.splits) * rows * cout * sizeof(float);
+}
+
 extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int64_t nb,
                                     int64_t h, int64_t w, int64_t cin, int64_t cout, int kh,
                                     int kw, int stride, int pad_h, int pad_w,
-                                    const vb_epilogue* epi, cudaStream_t stream) {
+                                    const vb_epilogue* epi, void* workspace, size_t workspace_bytes,
+                                    cudaStream_t stream) {
   // X [nb, h, w, cin] bf16 NHWC; Wt [cout, kh*kw, cin_pad] bf16 with cin_pad = ceil64(cin)
   // (zero padded); out [nb, ho, wo, cout(/2 if GLU)].
   VB_CHECK_ARG(X && Wt && out && epi);
@@ -953,29 +948,16 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
   VB_CHECK_ARG(stride == 1 || stride == 2);
   VB_CHECK_ARG((cin % 8) == 0);
   if (int r = validate_epi(epi, cout)) return r;
-  const int ho = static_cast<int>((h + 2 * pad_h - kh) / stride + 1);
-  const int wo = static_cast<int>((w + 2 * pad_w - kw) / stride + 1);
+  int ho, wo;
+  conv_out_dims(h, w, kh, kw, stride, pad_h, pad_w, ho, wo);
   VB_CHECK_ARG(ho > 0 && wo > 0);
   const int cin_chunks = static_cast<int>((cin + BLOCK_K - 1) / BLOCK_K);
   const int cin_pad = cin_chunks * BLOCK_K;
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  // pixel tile tw x th x tn (<= 128 accumulator rows): the shape that covers the output with the fewest tiles;
-  // ties go to the widest tile (longest contiguous runs for the TMA boxes)
-  int tw = 1, th = 1, tn = 1;
-  {
-    long long best = -1;
-    for (int cw = wo < 128 ? wo : 128; cw >= 1; --cw) {
-      const int hmax = 128 / cw < ho ? 128 / cw : ho;
-      for (int ch = hmax; ch >= 1; --ch) {
-        int cn = 128 / (cw * ch);
-        if (cn > nb) cn = static_cast<int>(nb);
-        const long long blocks = static_cast<long long>((wo + cw - 1) / cw) * ((ho + ch - 1) / ch) * ((nb + cn - 1) / cn);
-        if (best < 0 || blocks < best) { best = blocks; tw = cw; th = ch; tn = cn; }
-      }
-    }
-  }
+  int tw, th, tn;
+  conv_pixel_tile(wo, ho, nb, tw, th, tn);
   p.a_mode = 1;
   p.cin_chunks = cin_chunks;
   p.kw = kw;
@@ -1005,7 +987,26 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
   p.out = out;
   p.ldo = epi->glu != VB_GLU_NONE ? cout / 2 : cout;
 
-  int bn = pick_block_n(static_cast<long long>(p.m_blocks) * BLOCK_M, cout, epi->glu);
+  const bool v2 = v2_eligible(epi, out, p.ldo, cout);
+  int bn;
+  if (v2) {
+    TilePlan pl = plan_tiles(p.m_blocks, cout, p.num_k_blocks, true, p.M);
+    if (pl.splits > 1) {
+      const size_t need_ws = GEMM_COUNTER_BYTES + static_cast<size_t>(pl.splits) * p.M * cout * sizeof(float);
+      if (workspace == nullptr || workspace_bytes < need_ws || !aligned32(workspace)) pl = plan_tiles(p.m_blocks, cout, p.num_k_blocks, false, p.M);
+    }
+    bn = pl.bn;
+    p.splits = pl.splits;
+    if (pl.splits > 1) {
+      p.counters = reinterpret_cast<int*>(workspace);
+      p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + GEMM_COUNTER_BYTES);
+      p.ws_ld = cout;
+      p.ws_split_stride = static_cast<long long>(p.M) * cout;
+      p.vec_ok = (cout % 8) == 0;
+    }
+  } else {
+    bn = pick_block_n(static_cast<long long>(p.m_blocks) * BLOCK_M, cout, epi->glu);
+  }
   p.n_blocks = static_cast<int>((cout + bn - 1) / bn);
 
   CUtensorMap ta, tb;
@@ -1023,6 +1024,7 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
   uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
   const uint32_t estr2[2] = {1, 1};
   if (int r = make_tmap(&tb, Wt, 2, dB, sB, bB, estr2)) return r;
+  if (v2) return launch_gemm_v2(bn, v2_need(epi, p.splits), ta, tb, p, stream);
   CUtensorMap tc = tb;
   p.c_box = c_box_for(bn, epi->glu, epi->out_fp32, p.ldo, out);
   if (p.c_box > 0) {

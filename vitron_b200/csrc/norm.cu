@@ -295,8 +295,22 @@ static int launch_rownorm(const void* x, long long ldx, const void* w, const voi
 }
 
 // ------------------------------------------------------------------ GroupNorm NHWC
-// pass 1: per (image, spatial slab) partial sums per group -> atomics into [n, groups, 2] fp32
-// pass 2: normalise + affine (+ activation).  x: [n, spatial, c], group = channel / (c / groups).
+// x: [n, spatial, c] bf16, group = channel / (c / groups). ONE launch, x read from global ONCE:
+//
+//   The grid is at most one CTA per SM and every CTA owns a contiguous slab of rows of ONE sample. Phase 1 streams
+//   the slab with fully coalesced 16-byte loads (a thread owns one fixed 8-channel vector) INTO SHARED MEMORY
+//   (up to ~190 KB per SM: the 26 MB level-0 UNet tensor is 177 KB per SM) while accumulating per-channel sums in
+//   registers; the CTA folds them into per-group sums (smem, warp shuffles) and adds them to sums[n][groups][2] with
+//   fp32 atomics. The CTAs of a sample then meet at a counter barrier (all CTAs are co-resident: grid <= SMs), every
+//   CTA derives the per-channel affine (rstd*gamma, beta - mean*rstd*gamma) into smem, and phase 2 normalises its
+//   slab OUT OF SHARED MEMORY with 16-byte stores. The last CTA to have read the sums zeroes the workspace again
+//   (zero at allocation, left zero: no memset, stateless). Slabs beyond the smem budget (78 MB decoder concats) are
+//   re-read from global (L2) in phase 2 by the same kernel.
+//
+//   History: round 1 = single-pass kernel over [spatial x 40-channel] slabs (80-byte row fragments) or stats + apply
+//   kernels, 3.5 ms of a 25 ms UNet forward; a coalesced stats / apply pair with a last-CTA finaliser measured 15.7 +
+//   16.6 us per GroupNorm — both launches are latency chains (launch, L2 round trips, atomics, fence) longer than
+//   the data movement, so the fix is one launch and one read, not faster loops.
 __device__ __forceinline__ void gn_accumulate(const uint4 u, float (&s)[8], float (&q)[8]) {
   float2 f;
   f = unpack_bf16(u.x); s[0] += f.x; q[0] += f.x * f.x; s[1] += f.y; q[1] += f.y * f.y;
@@ -305,66 +319,14 @@ __device__ __forceinline__ void gn_accumulate(const uint4 u, float (&s)[8], floa
   f = unpack_bf16(u.w); s[6] += f.x; q[6] += f.x * f.x; s[7] += f.y; q[7] += f.y * f.y;
 }
 
-// fold the 8 per-channel partials of a thread into per-group shared accumulators
-__device__ __forceinline__ void gn_fold(const float (&s)[8], const float (&q)[8], int ch0, int cpg, float* sacc) {
-  int g_prev = ch0 / cpg;
-  float as = 0.f, aq = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (ch0 + j) / cpg;
-    if (g != g_prev) {
-      atomicAdd(&sacc[g_prev * 2], as);
-      atomicAdd(&sacc[g_prev * 2 + 1], aq);
-      as = aq = 0.f;
-      g_prev = g;
-    }
-    as += s[j];
-    aq += q[j];
-  }
-  atomicAdd(&sacc[g_prev * 2], as);
-  atomicAdd(&sacc[g_prev * 2 + 1], aq);
-}
+struct GnWs {
+  float* sums;      // [n][groups][2]
+  int* arrived;     // [n]  CTAs of the sample that published their sums
+  int* readers;     // [n]  CTAs of the sample that consumed the sums (the last one cleans up)
+};
 
-// Shared-memory float atomics are CAS loops on this architecture (ATOMS.CAST.SPIN): hundreds of threads folding
-// into a handful of group accumulators serialise for tens of microseconds. For cpg >= 8 an 8-channel vector
-// touches at most two groups, so every thread publishes (sum, sq) for "its first group" and "the next one", and
-// one warp per group then reduces the matching slots with shuffles: no atomics, deterministic order.
-// part: [threads][4]; sacc: [ngroups][2]. All threads of the CTA must call this (contains __syncthreads()).
-__device__ __forceinline__ void gn_block_group_sums(const float (&s)[8], const float (&q)[8], int my_vec, int vec_per_row,
-                                                    int nthreads_active, int cpg, int ngroups, float* part, float* sacc) {
-  const int tid = threadIdx.x;
-  if (tid < nthreads_active) {
-    const int ga = (my_vec * 8) / cpg;
-    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if ((my_vec * 8 + j) / cpg == ga) { sa += s[j]; qa += q[j]; }
-      else { sb += s[j]; qb += q[j]; }
-    }
-    *reinterpret_cast<float4*>(part + tid * 4) = make_float4(sa, qa, sb, qb);
-  }
-  __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  const int rows_per_pass = nthreads_active / vec_per_row;
-  for (int g = warp; g < ngroups && warp < nwarps; g += nwarps) {  // full warps only (blockDim need not be a multiple of 32)
-    const int v_lo = (g * cpg) / 8, v_hi = ((g + 1) * cpg - 1) / 8;  // vectors overlapping group g
-    const int nv = v_hi - v_lo + 1;
-    float as = 0.f, aq = 0.f;
-    for (int e = lane; e < rows_per_pass * nv; e += 32) {
-      const int row = e / nv, v = v_lo + e % nv;
-      const float4 pv = *reinterpret_cast<const float4*>(part + (row * vec_per_row + v) * 4);
-      const int ga = (v * 8) / cpg;
-      if (ga == g) { as += pv.x; aq += pv.y; }
-      else if (ga == g - 1) { as += pv.z; aq += pv.w; }
-    }
-    as = warp_sum(as);
-    aq = warp_sum(aq);
-    if (lane == 0) { sacc[g * 2] = as; sacc[g * 2 + 1] = aq; }
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ uint4 gn_affine(const uint4 u, const float* sc, const float* sh, int act) {
+template <int ACT>
+__device__ __forceinline__ uint4 gn_affine(const uint4 u, const float (&sc)[8], const float (&sh)[8]) {
   const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
   uint32_t oo[4];
 #pragma unroll
@@ -372,153 +334,144 @@ __device__ __forceinline__ uint4 gn_affine(const uint4 u, const float* sc, const
     const float2 f = unpack_bf16(uu[j]);
     float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]);
     float y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
-    if (act == VB_ACT_SILU) { y0 = silu(y0); y1 = silu(y1); }
-    else if (act == VB_ACT_RELU) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+    if (ACT == VB_ACT_SILU) { y0 = silu(y0); y1 = silu(y1); }
+    else if (ACT == VB_ACT_RELU) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
     oo[j] = pack_bf16(y0, y1);
   }
   return make_uint4(oo[0], oo[1], oo[2], oo[3]);
 }
 
-// Single-pass GroupNorm for slabs that fit in shared memory: CTA (part, image) owns `cpart` channels (whole
-// groups) of one image, pulls its [spatial x cpart] slab into smem while accumulating the group sums, then
-// normalises out of smem: x is read from HBM once instead of twice and there is one launch instead of three.
-__global__ void gn_fused_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
-                                bf16* __restrict__ out, int spatial, int c, int groups, float eps, int act, int cpart) {
-  extern __shared__ __align__(16) uint8_t gsm[];
-  const int cpg = c / groups;
-  const int gpart = cpart / cpg;
-  bf16* slab = reinterpret_cast<bf16*>(gsm);                                   // [spatial][cpart]
-  float* ss = reinterpret_cast<float*>(gsm + static_cast<size_t>(spatial) * cpart * 2);  // scale[cpart], shift[cpart]
-  float* sacc = ss + 2 * cpart;                                                // [gpart * 2]
-  const int n = blockIdx.y, c0 = blockIdx.x * cpart;
-  __shared__ __align__(16) float part[512 * 4];
-  const int vec_per_row = cpart / 8;
-  const int rows_per_pass = blockDim.x / vec_per_row;
-  const int my_vec = threadIdx.x % vec_per_row, my_row = threadIdx.x / vec_per_row;
-  const bf16* base = x + (static_cast<long long>(n) * spatial) * c + c0 + my_vec * 8;
-  float s[8], q[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  if (my_row < rows_per_pass) {  // threads beyond vec_per_row * rows_per_pass idle (blockDim is exact: none)
-    int r = my_row;
-    for (; r + 7 * rows_per_pass < spatial; r += 8 * rows_per_pass) {  // eight independent 16-byte loads in flight
-      uint4 u[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r + k * rows_per_pass) * c));
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        *reinterpret_cast<uint4*>(slab + static_cast<size_t>(r + k * rows_per_pass) * cpart + my_vec * 8) = u[k];
-        gn_accumulate(u[k], s, q);
-      }
-    }
-    for (; r < spatial; r += rows_per_pass) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * c));
-      *reinterpret_cast<uint4*>(slab + static_cast<size_t>(r) * cpart + my_vec * 8) = u;
-      gn_accumulate(u, s, q);
-    }
-  }
-  gn_block_group_sums(s, q, my_vec, vec_per_row, vec_per_row * rows_per_pass, cpg, gpart, part, sacc);
-  const float cnt = static_cast<float>(cpg) * static_cast<float>(spatial);
-  for (int ch = threadIdx.x; ch < cpart; ch += blockDim.x) {
-    const int g = ch / cpg;
-    const float mean = sacc[g * 2] / cnt;
-    const float rstd = rsqrtf(fmaxf(sacc[g * 2 + 1] / cnt - mean * mean, 0.f) + eps);
-    const float scl = rstd * __bfloat162float(w[c0 + ch]);
-    ss[ch] = scl;
-    ss[cpart + ch] = __bfloat162float(b[c0 + ch]) - mean * scl;
-  }
-  __syncthreads();
-  if (my_row < rows_per_pass) {
-    float scl[8], shf[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { scl[j] = ss[my_vec * 8 + j]; shf[j] = ss[cpart + my_vec * 8 + j]; }
-    bf16* obase = out + (static_cast<long long>(n) * spatial) * c + c0 + my_vec * 8;
-    for (int r = my_row; r < spatial; r += rows_per_pass) {  // each thread re-reads exactly what it staged
-      const uint4 u = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(r) * cpart + my_vec * 8);
-      *reinterpret_cast<uint4*>(obase + static_cast<long long>(r) * c) = gn_affine(u, scl, shf, act);
-    }
-  }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
-__global__ void gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, long long spatial,
-                                int c, int groups, int rows_per_cta) {
-  // blockDim.x = vec_per_row * rows_per_pass: every thread owns one fixed 8-channel vector, keeps
-  // per-channel sums in registers, and folds them into per-group shared accumulators at the end.
-  extern __shared__ float sacc[];  // [groups * 2]
+// grid = (ctas_per_sample, n); blockDim = (c / 8) * rpp; dynamic smem = [part: rpp*c*2 floats | slab: rows*c bf16 if CACHED]
+template <int ACT, bool CACHED>
+__global__ void __launch_bounds__(512)
+gn_onepass_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b, bf16* __restrict__ out,
+                  GnWs ws, int spatial, int c, int groups, int rows_per_cta, int rpp, float eps) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  __shared__ float gsum[1024];                                                        // [groups][2] when the sample is one CTA
+  float* part = reinterpret_cast<float*>(gsm);                                        // [rpp][c][2], later aff[2][c]
+  uint4* slab = reinterpret_cast<uint4*>(gsm + static_cast<size_t>(rpp) * c * 2 * sizeof(float));  // [rows][c/8]
   const int n = blockIdx.y;
-  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const int cpg = c / groups;
-  const int vec_per_row = c / 8;
-  const int rows_per_pass = blockDim.x / vec_per_row;
-  const int my_vec = threadIdx.x % vec_per_row;
-  const int my_row = threadIdx.x / vec_per_row;
-  const long long rend = min(r0 + rows_per_cta, spatial);
-  const bf16* base = x + static_cast<long long>(n) * spatial * c + my_vec * 8;
+  const int vec_per_row = c >> 3;
+  const int my_vec = threadIdx.x % vec_per_row, my_row = threadIdx.x / vec_per_row;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int rows = min(rows_per_cta, spatial - r0);
+  const size_t off = (static_cast<size_t>(n) * spatial + r0) * c + my_vec * 8;
+  const bf16* xb = x + off;
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  long long r = r0 + my_row;
-  for (; r + 3LL * rows_per_pass < rend; r += 4LL * rows_per_pass) {  // four independent 16-byte loads in flight
+  int r = my_row;
+  for (; r + 3 * rpp < rows; r += 4 * rpp) {  // four independent 16-byte loads in flight
     uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (r + static_cast<long long>(k) * rows_per_pass) * c));
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r + k * rpp) * c));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) gn_accumulate(u[k], s, q);
+    for (int k = 0; k < 4; ++k) {
+      if (CACHED) slab[(r + k * rpp) * vec_per_row + my_vec] = u[k];
+      gn_accumulate(u[k], s, q);
+    }
   }
-  for (; r < rend; r += rows_per_pass) gn_accumulate(__ldg(reinterpret_cast<const uint4*>(base + r * c)), s, q);
-  __shared__ __align__(16) float part[1024 * 4];
-  if (cpg >= 8) {
-    gn_block_group_sums(s, q, my_vec, vec_per_row, vec_per_row * rows_per_pass, cpg, groups, part, sacc);
-  } else {
-    gn_fold(s, q, my_vec * 8, cpg, sacc);  // narrow groups: shared atomics (slow, rare)
+  for (; r < rows; r += rpp) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r) * c));
+    if (CACHED) slab[r * vec_per_row + my_vec] = u;
+    gn_accumulate(u, s, q);
+  }
+  float* mine = part + (static_cast<size_t>(my_row) * c + my_vec * 8) * 2;
+#pragma unroll
+  for (int j = 0; j < 8; j += 2)
+    *reinterpret_cast<float4*>(mine + j * 2) = make_float4(s[j], q[j], s[j + 1], q[j + 1]);
+  __syncthreads();
+  const int cpg = c / groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* gs = ws.sums + static_cast<size_t>(n) * groups * 2;
+  const int ctas = gridDim.x;
+  for (int g = warp; g < groups; g += nwarps) {
+    float as = 0.f, aq = 0.f;
+    const int items = rpp * cpg;
+    for (int e = lane; e < items; e += 32) {
+      const int rr = e / cpg, ch = g * cpg + (e - rr * cpg);
+      const float2 v = *reinterpret_cast<const float2*>(part + (static_cast<size_t>(rr) * c + ch) * 2);
+      as += v.x;
+      aq += v.y;
+    }
+    as = warp_sum(as);
+    aq = warp_sum(aq);
+    if (lane == 0) {
+      if (ctas > 1) {
+        atomicAdd(gs + g * 2, as);
+        atomicAdd(gs + g * 2 + 1, aq);
+      } else {  // the whole sample is this CTA: no global round trip
+        gsum[g * 2] = as;
+        gsum[g * 2 + 1] = aq;
+      }
+    }
+  }
+  // ---- the CTAs of this sample meet: publish, then wait until all have published
+  if (ctas > 1) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(ws.arrived + n, 1);
+      while (ld_acquire_gpu(ws.arrived + n) < ctas) { }
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-    atomicAdd(&stats[static_cast<long long>(n) * groups * 2 + i], sacc[i]);
-}
-
-// y = x * scale[n][c] + shift[n][c] (+ activation): the per-channel affine of this image is computed once
-// per CTA into smem, then a slab of rows is streamed with 16-byte loads / stores.
-__global__ void __launch_bounds__(256)
-gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats, const bf16* __restrict__ w,
-                const bf16* __restrict__ b, bf16* __restrict__ out, long long spatial, int c, int groups, float eps,
-                int act, int rows_per_cta) {
-  extern __shared__ float ss[];  // [c] scale, [c] shift
-  const int n = blockIdx.y;
-  const int cpg = c / groups;
+  // ---- per-channel affine into smem (`part` is free: every warp passed the barrier above after its reads)
   const float cnt = static_cast<float>(cpg) * static_cast<float>(spatial);
+  float* aff = part;  // [2][c]
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     const int g = ch / cpg;
-    const float sum = stats[(static_cast<long long>(n) * groups + g) * 2], sq = stats[(static_cast<long long>(n) * groups + g) * 2 + 1];
+    float sum, sq;
+    if (ctas > 1) { sum = __ldcg(gs + g * 2); sq = __ldcg(gs + g * 2 + 1); }
+    else { sum = gsum[g * 2]; sq = gsum[g * 2 + 1]; }
     const float mean = sum / cnt;
     const float rstd = rsqrtf(fmaxf(sq / cnt - mean * mean, 0.f) + eps);
     const float sc = rstd * __bfloat162float(w[ch]);
-    ss[ch] = sc;
-    ss[c + ch] = __bfloat162float(b[ch]) - mean * sc;
+    aff[ch] = sc;
+    aff[c + ch] = __bfloat162float(b[ch]) - mean * sc;
   }
   __syncthreads();
-  const int vec_per_row = c / 8;
-  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
-  const long long nvec = min(static_cast<long long>(rows_per_cta), spatial - r0) * vec_per_row;
-  const long long base = (static_cast<long long>(n) * spatial + r0) * c;
-  long long i = threadIdx.x;
-  for (; i + 3LL * blockDim.x < nvec; i += 4LL * blockDim.x) {  // four independent 16-byte loads in flight
-    uint4 u[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x + base + (i + static_cast<long long>(k) * blockDim.x) * 8));
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long ii = i + static_cast<long long>(k) * blockDim.x;
-      const int cv = static_cast<int>(ii % vec_per_row) * 8;
-      *reinterpret_cast<uint4*>(out + base + ii * 8) = gn_affine(u[k], ss + cv, ss + c + cv, act);
+  if (ctas > 1 && threadIdx.x == 0) {
+    // every thread of this CTA has read the sums (the barrier above): the last CTA of the sample to get here hands the
+    // workspace back zeroed
+    __threadfence();
+    const int prev = atomicAdd(ws.readers + n, 1);
+    if (prev == ctas - 1) {
+      for (int i = 0; i < groups * 2; ++i) gs[i] = 0.f;
+      ws.arrived[n] = 0;
+      ws.readers[n] = 0;
     }
   }
-  for (; i < nvec; i += blockDim.x) {
-    const int cv = static_cast<int>(i % vec_per_row) * 8;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + base + i * 8));
-    *reinterpret_cast<uint4*>(out + base + i * 8) = gn_affine(u, ss + cv, ss + c + cv, act);
+  float sc[8], sh[8];
+  {
+    const float4 a0 = *reinterpret_cast<const float4*>(aff + my_vec * 8), a1 = *reinterpret_cast<const float4*>(aff + my_vec * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(aff + c + my_vec * 8), b1 = *reinterpret_cast<const float4*>(aff + c + my_vec * 8 + 4);
+    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+  }
+  bf16* ob = out + off;
+  if (CACHED) {
+    for (int rr = my_row; rr < rows; rr += rpp)  // each thread re-reads exactly the vectors it staged
+      *reinterpret_cast<uint4*>(ob + static_cast<size_t>(rr) * c) = gn_affine<ACT>(slab[rr * vec_per_row + my_vec], sc, sh);
+  } else {
+    int rr = my_row;
+    for (; rr + 3 * rpp < rows; rr += 4 * rpp) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(rr + k * rpp) * c));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<uint4*>(ob + static_cast<size_t>(rr + k * rpp) * c) = gn_affine<ACT>(u[k], sc, sh);
+    }
+    for (; rr < rows; rr += rpp)
+      *reinterpret_cast<uint4*>(ob + static_cast<size_t>(rr) * c) =
+          gn_affine<ACT>(__ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(rr) * c)), sc, sh);
   }
 }
 
@@ -549,8 +502,27 @@ extern "C" int vb200_layernorm(const void* x, int64_t ldx, const void* weight, c
   return launch_rownorm<true>(x, ldx, weight, bias, out, ldo, rows, d, eps, stream);
 }
 
-extern "C" size_t vb200_groupnorm_workspace_size(int64_t n, int64_t groups) {
-  return static_cast<size_t>(n) * groups * 2 * sizeof(float);
+static size_t gn_align16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
+
+extern "C" size_t vb200_groupnorm_workspace_size(int64_t n, int64_t groups, int64_t c) {
+  // [group sums | arrival counters | reader counters]; zero-fill ONCE before first use, the kernel leaves it zeroed
+  (void)c;
+  return gn_align16(static_cast<size_t>(n) * groups * 2 * sizeof(float)) + 2 * gn_align16(static_cast<size_t>(n) * sizeof(int));
+}
+
+template <int ACT, bool CACHED>
+static int gn_launch(const bf16* x, const bf16* w, const bf16* b, bf16* out, GnWs ws, int spatial, int c, int groups, int rpc,
+                     int rpp, float eps, dim3 grid, int threads, size_t smem, cudaStream_t stream) {
+  auto kern = gn_onepass_kernel<ACT, CACHED>;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
+    smem_set = 227 * 1024;
+  }
+  kern<<<grid, threads, smem, stream>>>(x, w, b, out, ws, spatial, c, groups, rpc, rpp, eps);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
 }
 
 extern "C" int vb200_groupnorm_nhwc(const void* x, const void* weight, const void* bias, void* out,
@@ -559,70 +531,45 @@ extern "C" int vb200_groupnorm_nhwc(const void* x, const void* weight, const voi
                                     cudaStream_t stream) {
   VB_CHECK_ARG(x && weight && bias && out && n > 0 && spatial > 0 && c > 0 && groups > 0);
   VB_CHECK_ARG(c % 8 == 0 && c % groups == 0);
-  VB_CHECK_ARG(c / 8 <= 1024);
-  {
-    // single-pass kernel when a CTA's [spatial x cpart] slab fits in shared memory; cpart = whole groups and
-    // whole 16-byte vectors. Prefer slabs <= 48 KB (several CTAs per SM), else the narrowest part up to 200 KB.
-    const int cpg = static_cast<int>(c / groups);
-    int unit = cpg;
-    while (unit % 8 != 0) unit += cpg;  // lcm(cpg, 8)
-    int cpart = 0;
-    if (cpg >= 8 && c % unit == 0 && spatial <= (1 << 20)) {
-      for (int cand = unit; cand <= c; cand += unit) {
-        if (c % cand != 0 || cand / 8 > 512) continue;
-        const long long slab = spatial * cand * 2;
-        if (cpart == 0 && slab <= 200 * 1024) cpart = cand;       // narrowest that fits at all
-        if (slab <= 48 * 1024) cpart = cand;                      // widest small slab
-      }
-    }
-    if (cpart > 0 && x != out) {
-      const int vec_per_row = cpart / 8;
-      const int rows_per_pass = 512 / vec_per_row;
-      const int threads = vec_per_row * rows_per_pass;
-      const size_t smem = static_cast<size_t>(spatial) * cpart * 2 + 2 * cpart * sizeof(float) + (cpart / cpg) * 2 * sizeof(float);
-      static size_t smem_set = 0;
-      if (smem > smem_set) {
-        cudaError_t ea = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-        if (ea != cudaSuccess) { vb_set_last_error(ea); return VB_ERR_CUDA; }
-        smem_set = 208 * 1024;
-      }
-      dim3 gridf(static_cast<unsigned>(c / cpart), static_cast<unsigned>(n));
-      gn_fused_kernel<<<gridf, threads, smem, stream>>>(
-          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(weight), reinterpret_cast<const bf16*>(bias),
-          reinterpret_cast<bf16*>(out), static_cast<int>(spatial), static_cast<int>(c), static_cast<int>(groups), eps, act,
-          cpart);
-      VB_LAUNCH_CHECK();
-      return VB_OK;
-    }
-  }
-  size_t need = vb200_groupnorm_workspace_size(n, groups);
-  if (!workspace || workspace_bytes < need) return VB_ERR_WORKSPACE;
-  cudaError_t e = cudaMemsetAsync(workspace, 0, need, stream);
-  if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
-  // slabs sized so that n * slabs ~ 4 CTAs per SM
-  long long want = (4LL * vb_num_sms() + n - 1) / n;
-  long long rows_per_cta = (spatial + want - 1) / want;
-  if (rows_per_cta < 8) rows_per_cta = 8;
-  long long slabs = (spatial + rows_per_cta - 1) / rows_per_cta;
-  dim3 grid(static_cast<unsigned>(slabs), static_cast<unsigned>(n));
+  VB_CHECK_ARG(c / 8 <= 512 && n <= 65535 && spatial < (1LL << 31) / 4 && groups <= 512);
+  VB_CHECK_ARG(act == VB_ACT_NONE || act == VB_ACT_SILU || act == VB_ACT_RELU);
+  VB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const size_t need = vb200_groupnorm_workspace_size(n, groups, c);
+  if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return VB_ERR_WORKSPACE;
+  GnWs ws;
+  char* wsp = reinterpret_cast<char*>(workspace);
+  ws.sums = reinterpret_cast<float*>(wsp);
+  ws.arrived = reinterpret_cast<int*>(wsp + gn_align16(static_cast<size_t>(n) * groups * 2 * sizeof(float)));
+  ws.readers = reinterpret_cast<int*>(reinterpret_cast<char*>(ws.arrived) + gn_align16(static_cast<size_t>(n) * sizeof(int)));
   const int vec_per_row = static_cast<int>(c / 8);
-  int rows_per_pass = 256 / vec_per_row;
-  if (rows_per_pass < 1) rows_per_pass = 1;
-  int threads = vec_per_row * rows_per_pass;
-  gn_stats_kernel<<<grid, threads, groups * 2 * sizeof(float), stream>>>(
-      reinterpret_cast<const bf16*>(x), reinterpret_cast<float*>(workspace), spatial,
-      static_cast<int>(c), static_cast<int>(groups), static_cast<int>(rows_per_cta));
-  VB_LAUNCH_CHECK();
-  // apply: ~8 CTAs per SM, each with its own smem copy of the per-channel affine
-  long long want2 = (8LL * vb_num_sms() + n - 1) / n;
-  long long rpc = (spatial + want2 - 1) / want2;
-  if (rpc < 4) rpc = 4;
-  dim3 grid2(static_cast<unsigned>((spatial + rpc - 1) / rpc), static_cast<unsigned>(n));
-  gn_apply_kernel<<<grid2, 256, 2 * c * sizeof(float), stream>>>(
-      reinterpret_cast<const bf16*>(x), reinterpret_cast<const float*>(workspace),
-      reinterpret_cast<const bf16*>(weight), reinterpret_cast<const bf16*>(bias),
-      reinterpret_cast<bf16*>(out), spatial, static_cast<int>(c), static_cast<int>(groups), eps, act,
-      static_cast<int>(rpc));
-  VB_LAUNCH_CHECK();
-  return VB_OK;
+  int rpp = 512 / vec_per_row;
+  if (rpp < 1) rpp = 1;
+  if (rpp > spatial) rpp = static_cast<int>(spatial);
+  const int threads = vec_per_row * rpp;
+  // CTAs per sample: the grid never exceeds the SM count (the CTAs of a sample wait for each other), a CTA gets at
+  // least 4 passes of rows
+  const int sms = vb_num_sms();
+  long long per = n >= sms ? 1 : sms / n;
+  const long long max_useful = (spatial + 4LL * rpp - 1) / (4LL * rpp);
+  if (per > max_useful) per = max_useful;
+  if (per < 1) per = 1;
+  long long rpc = (spatial + per - 1) / per;
+  per = (spatial + rpc - 1) / rpc;
+  const size_t part_bytes = static_cast<size_t>(rpp) * c * 2 * sizeof(float);
+  const size_t slab_bytes = static_cast<size_t>(rpc) * c * 2;
+  const bool cached = part_bytes + slab_bytes <= 220 * 1024;
+  const size_t smem = part_bytes + (cached ? slab_bytes : 0);
+  dim3 grid(static_cast<unsigned>(per), static_cast<unsigned>(n));
+  const bf16* xp = reinterpret_cast<const bf16*>(x);
+  const bf16* wp = reinterpret_cast<const bf16*>(weight);
+  const bf16* bp = reinterpret_cast<const bf16*>(bias);
+  bf16* op = reinterpret_cast<bf16*>(out);
+  const int sp = static_cast<int>(spatial), ci = static_cast<int>(c), gi = static_cast<int>(groups), rc = static_cast<int>(rpc);
+#define VB_GN_CASE(A)                                                                                                   \
+  return cached ? gn_launch<A, true>(xp, wp, bp, op, ws, sp, ci, gi, rc, rpp, eps, grid, threads, smem, stream)           \
+                : gn_launch<A, false>(xp, wp, bp, op, ws, sp, ci, gi, rc, rpp, eps, grid, threads, smem, stream)
+  if (act == VB_ACT_SILU) { VB_GN_CASE(VB_ACT_SILU); }
+  if (act == VB_ACT_RELU) { VB_GN_CASE(VB_ACT_RELU); }
+  VB_GN_CASE(VB_ACT_NONE);
+#undef VB_GN_CASE
 }

@@ -150,9 +150,15 @@ class LlamaEngine:
         self.embed = get("model.embed_tokens.weight").contiguous()
         self.lm_head = folded("lm_head.weight", "model.norm.weight").contiguous()
         self.layers = []
+        # the RMSNorm gains are folded into the consuming weights; the (tiny) gain vectors are kept so that state_dict()
+        # can hand back reference-named tensors
+        g32 = lambda n: sd[prefix + n].detach().to(device=dev, dtype=torch.float32).contiguous()
+        self.norm_gains = dict(norm=g32("model.norm.weight"), ln1=[], ln2=[])
         for i in range(self.cfg.num_hidden_layers):
             p = f"model.layers.{i}."
             ln1, ln2 = p + "input_layernorm.weight", p + "post_attention_layernorm.weight"
+            self.norm_gains["ln1"].append(g32(ln1))
+            self.norm_gains["ln2"].append(g32(ln2))
             wqkv = torch.cat([folded(p + "self_attn.q_proj.weight", ln1), folded(p + "self_attn.k_proj.weight", ln1),
                               folded(p + "self_attn.v_proj.weight", ln1)], 0).contiguous()
             wgu = ops.pack_glu_weight(folded(p + "mlp.gate_proj.weight", ln2), folded(p + "mlp.up_proj.weight", ln2))
@@ -179,6 +185,43 @@ class LlamaEngine:
                 wdown=w(c.hidden_size, c.intermediate_size)))
         self._graphs = {}
         return self
+
+    def state_dict(self, prefix=""):
+        """Reference-named tensors (HF LlamaForCausalLM names, bf16) rebuilt from the packed device weights: q/k/v and
+        gate/up are un-fused, the folded RMSNorm gains divided out again (exact where the gain is 1, else within one
+        bf16 rounding of the loaded value)."""
+        c, out = self.cfg, {}
+        d, f = c.hidden_size, c.intermediate_size
+        gains = getattr(self, "norm_gains", None)
+        ones = torch.ones((d,), dtype=torch.float32, device=self.device)
+
+        def unfold(w, g):
+            return (w.float() / g[None, :]).to(BF16)
+        out[prefix + "model.embed_tokens.weight"] = self.embed
+        gn = gains["norm"] if gains else ones
+        out[prefix + "model.norm.weight"] = gn.to(BF16)
+        out[prefix + "lm_head.weight"] = unfold(self.lm_head, gn)
+        for i, L in enumerate(self.layers):
+            p = f"{prefix}model.layers.{i}."
+            g1 = gains["ln1"][i] if gains else ones
+            g2 = gains["ln2"][i] if gains else ones
+            q, k, v = L["wqkv"].split(d, 0)
+            out[p + "self_attn.q_proj.weight"], out[p + "self_attn.k_proj.weight"], out[p + "self_attn.v_proj.weight"] = \
+                unfold(q, g1), unfold(k, g1), unfold(v, g1)
+            out[p + "self_attn.o_proj.weight"] = L["wo"]
+            gu = L["wgu"].view(f // 16, 2, 16, d)      # ops.pack_glu_weight: 16-row blocks [gate | up]
+            out[p + "mlp.gate_proj.weight"] = unfold(gu[:, 0].reshape(f, d), g2)
+            out[p + "mlp.up_proj.weight"] = unfold(gu[:, 1].reshape(f, d), g2)
+            out[p + "mlp.down_proj.weight"] = L["wdown"]
+            out[p + "input_layernorm.weight"] = g1.to(BF16)
+            out[p + "post_attention_layernorm.weight"] = g2.to(BF16)
+        return out
+
+    def parameters(self):
+        yield self.embed
+        yield self.lm_head
+        for L in self.layers:
+            yield from (L["wqkv"], L["wo"], L["wgu"], L["wdown"])
 
     def weight_bytes(self):
         n = self.lm_head.numel()
@@ -299,7 +342,7 @@ class LlamaEngine:
         """Run n greedy decode steps for slots 0..B-1 (no host sync)."""
         if n <= 0:
             return
-        if not use_graph:
+        if not use_graph or self.device.type != "cuda":   # (host-logic tests drive the same step un-graphed)
             for _ in range(n):
                 self._step_kernels(B)
             return

@@ -133,6 +133,11 @@ def gemm(a, w, bias=None, act=ACT_NONE, glu=GLU_NONE, residual=None, alpha=1.0, 
     return out.reshape(*a.shape[:-1], n_out) if a.dim() != 2 else out
 
 
+def set_gemm_impl(impl):
+    """0 = specialised v2 kernel whenever eligible (default), 1 = generic kernel only; returns the previous setting."""
+    return _lib.load().vb200_set_gemm_impl(int(impl))
+
+
 def pack_conv_weight(w):
     """[cout, cin, kh, kw] (torch Conv2d) or [cout, cin, kt, 1, 1] (Conv3d (k,1,1)) ->
     [cout, kh*kw, ceil64(cin)] bf16, zero padded: the K-major layout of the implicit GEMM."""
@@ -171,8 +176,10 @@ def conv_nhwc(x, wt, kh, kw, stride=1, pad_h=None, pad_w=None, bias=None, act=AC
         _req(residual.is_contiguous() and residual.shape == out.shape, "bad residual")
         epi.residual = residual.data_ptr()
         epi.ldr = n_out
+    need = lib.vb200_conv_nhwc_workspace_size(nb, h, w, cin, cout, kh, kw, stride, pad_h, pad_w)
+    ws = workspace(need, x.device) if need else None
     check(lib.vb200_conv_nhwc_bf16(x.data_ptr(), wt.data_ptr(), out.data_ptr(), nb, h, w, cin, cout, kh, kw,
-                                   stride, pad_h, pad_w, C.byref(epi), _stream()), "vb200_conv_nhwc_bf16")
+                                   stride, pad_h, pad_w, C.byref(epi), _ptr(ws), need, _stream()), "vb200_conv_nhwc_bf16")
     _launches[0] += 1
     return out
 
@@ -224,7 +231,7 @@ def groupnorm_nhwc(x, weight, bias, groups, eps, act=ACT_NONE, n=None, out=None)
     n = x.shape[0] if n is None else n
     spatial = x.numel() // (n * c)
     out = torch.empty_like(x) if out is None else out
-    need = lib.vb200_groupnorm_workspace_size(n, groups)
+    need = lib.vb200_groupnorm_workspace_size(n, groups, c)
     ws = workspace(need, x.device, "gn")
     check(lib.vb200_groupnorm_nhwc(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), n, spatial, c,
                                    groups, float(eps), int(act), ws.data_ptr(), need, _stream()),

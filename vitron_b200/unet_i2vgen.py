@@ -435,6 +435,63 @@ class GraphedCFGDenoiser:
         return self.out
 
 
+class GraphedBranch:
+    """ONE UNet forward with fixed conditioning, captured in a CUDA graph (xt / t are static buffers). Building block of the
+    CFG-branch split: each GPU of a pair owns one of the two classifier-free-guidance branches."""
+
+    def __init__(self, unet, cond, xt_like, t_like):
+        self.unet, self.cond = unet, cond
+        self.xt = xt_like.detach().clone().float().contiguous()
+        self.t = t_like.detach().clone()
+        self.graph, self.out, self.launches = None, None, 0
+
+    def __call__(self, xt, t):
+        self.xt.copy_(xt)
+        self.t.copy_(t)
+        if self.graph is None:
+            s = torch.cuda.Stream(device=self.xt.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self.unet(self.xt, self.t, **self.cond)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                self.out = self.unet(self.xt, self.t, **self.cond).float().contiguous()
+            self.launches = ops.launch_count() - l0
+            self.graph = g
+        self.graph.replay()
+        ops.count_launches(self.launches)
+        return self.out
+
+
+class CFGSplitDenoiser:
+    """Classifier-free guidance with the two UNet evaluations of a DDIM step on TWO ranks (the cond / uncond
+    branches of diffusion_ddim.py:153-158 are independent given x_t). Rank `role` 0 of the pair evaluates the conditional
+    branch, role 1 the unconditional one; ONE collective per step — an all_gather of the two [b, 4, f, h, w] fp32 branch outputs
+    inside the pair's process group (655 KB at the 16 x 40 x 64 latent) — after which both ranks hold (y, u), compute the same
+    u + s (y - u) and therefore the same x_{t-1}: no broadcast of the latent is needed, the pair stays in lock-step.
+
+    `branch` is any callable (xt, t) -> branch output (GraphedBranch on the GPU); `combine(y, u, scale)` defaults to the
+    cfg_combine kernel; `group` is the 2-rank torch.distributed group (None = the default group of a 2-rank job)."""
+
+    def __init__(self, branch, role, guide_scale, group=None, combine=None):
+        self.branch, self.role, self.scale, self.group = branch, int(role), float(guide_scale), group
+        self.combine = combine or ops.cfg_combine
+        self._buf = None
+
+    def __call__(self, xt, t):
+        import torch.distributed as dist
+        mine = self.branch(xt, t).float().contiguous()
+        b = mine.shape[0]
+        if self._buf is None or self._buf.shape[0] != 2 * b or self._buf.shape[1:] != mine.shape[1:]:
+            self._buf = torch.empty((2 * b, *mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(self._buf, mine, group=self.group)   # rows [0, b) = role 0 (cond), [b, 2b) = role 1
+        return self.combine(self._buf[:b], self._buf[b:], self.scale)
+
+
 # ====================================================================================== DDIM sampler
 def _cosine_betas(num_timesteps=1000, cosine_s=0.008, zero_terminal_snr=True):
     """schedules.py:50-57 (+ rescale_zero_terminal_snr :121-143), float64."""
@@ -479,7 +536,7 @@ class DiffusionDDIM:
     @torch.no_grad()
     def ddim_sample(self, xt, t, model, model_kwargs, guide_scale=None, ddim_timesteps=20, eta=0.0, clamp=None):
         stride = self.num_timesteps // ddim_timesteps
-        if isinstance(model, GraphedCFGDenoiser):
+        if isinstance(model, (GraphedCFGDenoiser, CFGSplitDenoiser)):
             out = model(xt, t)
         elif guide_scale is None:
             out = model(xt, t, **model_kwargs).float()

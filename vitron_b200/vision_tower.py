@@ -61,6 +61,9 @@ class VisionTransformerB200:
         self.w = dict(cls=get("embeddings.class_embedding").reshape(-1),
                       pos=get("embeddings.position_embedding.weight"), wpatch=wpatch,
                       pre_w=get("pre_layrnorm.weight"), pre_b=get("pre_layrnorm.bias"))
+        for n in ("post_layernorm.weight", "post_layernorm.bias"):   # not on the path (hidden_states[-2]); kept for state_dict()
+            if prefix + n in sd:
+                self.w[n] = get(n)
         self.layers = []
         for i in range(c.num_hidden_layers):
             p = f"encoder.layers.{i}."
@@ -85,6 +88,44 @@ class VisionTransformerB200:
                              tln2w=get(p + "temporal_layer_norm2.weight"), tln2b=get(p + "temporal_layer_norm2.bias"))
             self.layers.append(L)
         return self
+
+    def state_dict(self, prefix=""):
+        """The reference's parameter names rebuilt from the packed device tensors."""
+        c, out, d = self.config, {}, self.config.hidden_size
+        w = self.w
+        out[prefix + "embeddings.class_embedding"] = w["cls"]
+        out[prefix + "embeddings.position_embedding.weight"] = w["pos"]
+        k = c.num_channels * c.patch_size ** 2
+        out[prefix + "embeddings.patch_embedding.weight"] = w["wpatch"][:, :k].reshape(d, c.num_channels, c.patch_size, c.patch_size)
+        out[prefix + "pre_layrnorm.weight"], out[prefix + "pre_layrnorm.bias"] = w["pre_w"], w["pre_b"]
+        for n in ("post_layernorm.weight", "post_layernorm.bias"):
+            if n in w:
+                out[prefix + n] = w[n]
+        for i, L in enumerate(self.layers):
+            p = f"{prefix}encoder.layers.{i}."
+            for n, wq, bq in zip("qkv", L["wqkv"].split(d, 0), L["bqkv"].split(d, 0)):
+                out[p + f"self_attn.{n}_proj.weight"], out[p + f"self_attn.{n}_proj.bias"] = wq, bq
+            out[p + "self_attn.out_proj.weight"], out[p + "self_attn.out_proj.bias"] = L["wo"], L["bo"]
+            out[p + "layer_norm1.weight"], out[p + "layer_norm1.bias"] = L["ln1w"], L["ln1b"]
+            out[p + "layer_norm2.weight"], out[p + "layer_norm2.bias"] = L["ln2w"], L["ln2b"]
+            out[p + "mlp.fc1.weight"], out[p + "mlp.fc1.bias"] = L["w1"], L["b1"]
+            out[p + "mlp.fc2.weight"], out[p + "mlp.fc2.bias"] = L["w2"], L["b2"]
+            if "temb" in L:
+                out[p + "temporal_embedding"] = L["temb"].reshape(1, -1, d)
+                for n, wq, bq in zip("qkv", L["twqkv"].split(d, 0), L["tbqkv"].split(d, 0)):
+                    out[p + f"temporal_attn.{n}_proj.weight"], out[p + f"temporal_attn.{n}_proj.bias"] = wq, bq
+                out[p + "temporal_attn.out_proj.weight"], out[p + "temporal_attn.out_proj.bias"] = L["two"], L["tbo"]
+                out[p + "temporal_layer_norm1.weight"], out[p + "temporal_layer_norm1.bias"] = L["tlnw"], L["tlnb"]
+            if "tw1" in L:
+                out[p + "temporal_mlp.fc1.weight"], out[p + "temporal_mlp.fc1.bias"] = L["tw1"], L["tb1"]
+                out[p + "temporal_mlp.fc2.weight"], out[p + "temporal_mlp.fc2.bias"] = L["tw2"], L["tb2"]
+                out[p + "temporal_layer_norm2.weight"], out[p + "temporal_layer_norm2.bias"] = L["tln2w"], L["tln2b"]
+        return out
+
+    def parameters(self):
+        yield from self.w.values()
+        for L in self.layers:
+            yield from L.values()
 
     def num_layers_for(self, select_layer):
         L = self.config.num_hidden_layers
@@ -151,6 +192,22 @@ class _TowerBase:
 
     def load_model(self):  # reference API; weights come from load_state_dict here
         self.is_loaded = True
+
+    # nn.Module face used by the reference's builder (builder.py:152-163: `tower.to(device=..., dtype=...)`)
+    def to(self, *args, **kwargs):
+        from .module_face import check_to
+        check_to(self.device, args, kwargs)
+        return self
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return self.vit.parameters()
+
+    def state_dict(self, prefix=""):
+        attr = "video_tower." if isinstance(self, LanguageBindVideoTower) else "image_tower."
+        return self.vit.state_dict(prefix + attr)
 
     @property
     def config(self):

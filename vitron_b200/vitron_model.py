@@ -15,6 +15,7 @@ from types import SimpleNamespace
 import torch
 
 from . import ops
+from .module_face import ModuleFace
 from .adapters import RegionExtractor, VisionProjector
 from .llama import LlamaConfig, LlamaEngine
 from .vision_tower import LanguageBindImageTower, LanguageBindVideoTower, VisionConfig
@@ -146,7 +147,7 @@ class CausalLMOutput(SimpleNamespace):
     pass
 
 
-class VitronLlamaForCausalLM:
+class VitronLlamaForCausalLM(ModuleFace):
     def __init__(self, config, device="cuda", max_batch=8, max_seq_len=2048):
         self.config = config
         self.device = torch.device(device)
@@ -181,7 +182,45 @@ class VitronLlamaForCausalLM:
     def engine(self):
         return self.model.engine
 
-    def eval(self):
+    def state_dict(self):
+        """Reference-named tensors of everything this model owns (SURVEY.md Appendix B names)."""
+        out = dict(self.engine.state_dict())
+        m = self.model
+        if m.mm_projector is not None:
+            out.update(m.mm_projector.state_dict("model.mm_projector."))
+        if m.region_extractor is not None and m.region_extractor.mlp:
+            out.update(m.region_extractor.state_dict("model.region_extractor."))
+        if m.image_tower is not None and m.image_tower.vit.layers:
+            out.update(m.image_tower.vit.state_dict("model.image_tower.image_tower."))
+        if m.video_tower is not None and m.video_tower.vit.layers:
+            out.update(m.video_tower.vit.state_dict("model.video_tower.video_tower."))
+        return out
+
+    def parameters(self):
+        yield from self.engine.parameters()
+        m = self.model
+        for sub in (m.mm_projector, m.region_extractor, m.image_tower, m.video_tower):
+            if sub is not None:
+                yield from sub.parameters()
+
+    def resize_token_embeddings(self, new_num_tokens):
+        """builder.py:146 `model.resize_token_embeddings(len(tokenizer))` after the special tokens were added: embedding and
+        lm_head rows are appended (zeros: the reference's new rows are unseeded random values that inference never reads) or
+        dropped; the decode state buffers follow the vocabulary."""
+        eng = self.engine
+        V, d = eng.embed.shape
+        if new_num_tokens == V:
+            return self
+        def fit(w):
+            out = torch.zeros((new_num_tokens, d), dtype=w.dtype, device=w.device)
+            n = min(V, new_num_tokens)
+            out[:n] = w[:n]
+            return out
+        eng.embed, eng.lm_head = fit(eng.embed), fit(eng.lm_head)
+        eng.cfg.vocab_size = new_num_tokens
+        eng.d_logits = torch.zeros((eng.max_batch, new_num_tokens), dtype=torch.float32, device=eng.device)
+        eng._graphs = {}
+        self.config.vocab_size = new_num_tokens
         return self
 
     def load_state_dict(self, sd, strict=True):
