@@ -98,7 +98,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                                                  : 512;
   constexpr bool WS = (F & F_WS) != 0;
   constexpr bool GLU = (F & F_GLU) != 0;
-  constexpr bool F32 = (F & F_F32) != 0;
+  constexpr bool F32C = (F & F_F32) != 0;  // fp32 output POSSIBLE in this variant; p.out_fp32 decides at run time
   constexpr int NCH = BLOCK_N / 32;       // 32-column accumulator chunks per tile
   constexpr int OUTS = GLU ? 16 : 32;     // outputs one chunk produces
   static_assert(BLOCK_N % 32 == 0, "v2 tiles are whole 32-column chunks");
@@ -247,7 +247,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if constexpr (WS)
           orow_ptr = reinterpret_cast<uint8_t*>(p.ws + static_cast<size_t>(t.split) * p.ws_split_stride +
                                                 static_cast<size_t>(orow) * p.ws_ld + col0);
-        else if constexpr (F32)
+        else if (F32C && p.out_fp32)
           orow_ptr = reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(orow) * p.ldo +
                                                 (GLU ? col0 / 2 : col0));
         else
@@ -255,8 +255,12 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                                 (GLU ? col0 / 2 : col0));
       }
 
+      // residual ring: the loads of up to RD chunks are issued BEFORE the wait for the accumulator (they do not depend
+      // on it), so their L2 latency (~800 clk) overlaps the MMA of this tile instead of stalling every chunk
+      constexpr int MYCH = (NCH + 1) / 2;            // chunks a warp handles at most
+      constexpr int RD = MYCH < 3 ? MYCH : 3;
       uint32_t v[2][32];
-      uint32_t rres[2][16];
+      uint32_t rres[RD][16];
       auto prefetch_res = [&](int ci, uint32_t (&dst)[16]) {
         if constexpr (!WS && (F & F_RES) != 0) {
           if (rrow != nullptr && col0 + (ci + 1) * 32 <= p.N) {
@@ -274,23 +278,20 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       };
 
+#pragma unroll
+      for (int i = 0; i < RD; ++i)
+        if (NCH % 2 == 0 || ehalf + 2 * i < NCH) prefetch_res(ehalf + 2 * i, rres[i]);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (NCH % 2 == 0 || ehalf < NCH) {
-        tmem_ld_32x32(taddr + ehalf * 32, v[0]);
-        prefetch_res(ehalf, rres[0]);
-      }
+      if (NCH % 2 == 0 || ehalf < NCH) tmem_ld_32x32(taddr + ehalf * 32, v[0]);
 #pragma unroll
-      for (int it = 0; it < (NCH + 1) / 2; ++it) {
+      for (int it = 0; it < MYCH; ++it) {
         const int ci = ehalf + 2 * it;
         if (NCH % 2 == 0 || ci < NCH) {
           tmem_ld_wait();
-          if (ci + 2 < NCH) {
-            tmem_ld_32x32(taddr + (ci + 2) * 32, v[(it + 1) & 1]);
-            prefetch_res(ci + 2, rres[(it + 1) & 1]);
-          }
+          if (ci + 2 < NCH) tmem_ld_32x32(taddr + (ci + 2) * 32, v[(it + 1) & 1]);
           uint32_t(&vv)[32] = v[it & 1];
-          uint32_t(&rr)[16] = rres[it & 1];
+          uint32_t(&rr)[16] = rres[it % RD];
           const int gc = col0 + ci * 32;  // first accumulator column of this chunk
           if (gc < p.N) {
             const bool full = gc + 32 <= p.N;
@@ -380,9 +381,10 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                   for (int j = 0; j < OUTS; ++j) f[j] *= p.alpha;
                 }
+                if (it + RD < MYCH && (NCH % 2 == 0 || ci + 2 * RD < NCH)) prefetch_res(ci + 2 * RD, rres[it % RD]);
               }
               if (orow >= 0) {
-                if constexpr (F32) {
+                if (F32C && p.out_fp32) {
                   float* dst = reinterpret_cast<float*>(orow_ptr) + ci * OUTS;
 #pragma unroll
                   for (int q = 0; q < OUTS / 8; ++q) {
@@ -413,9 +415,9 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int j = 0; j < 32; ++j) tmp[j] = vv[j];
                 epi_ragged(tmp, p.N - gc, rs, p.bias != nullptr ? p.bias + gc : nullptr, rb != nullptr ? rb + ci * 32 : nullptr,
                            rrow != nullptr ? rrow + ci * 32 : nullptr, p.alpha, (F & F_ACT) ? p.act : VB_ACT_NONE,
-                           F32 ? static_cast<void*>(reinterpret_cast<float*>(orow_ptr) + ci * 32)
-                               : static_cast<void*>(reinterpret_cast<bf16*>(orow_ptr) + ci * 32),
-                           F32 ? 1 : 0);
+                           (F32C && p.out_fp32) ? static_cast<void*>(reinterpret_cast<float*>(orow_ptr) + ci * 32)
+                                                : static_cast<void*>(reinterpret_cast<bf16*>(orow_ptr) + ci * 32),
+                           (F32C && p.out_fp32) ? 1 : 0);
               }
             }
           }

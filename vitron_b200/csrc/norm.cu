@@ -502,6 +502,8 @@ extern "C" int vb200_layernorm(const void* x, int64_t ldx, const void* weight, c
   return launch_rownorm<true>(x, ldx, weight, bias, out, ldo, rows, d, eps, stream);
 }
 
+constexpr int GN_DYN_SMEM_MAX = 220 * 1024;  // dynamic smem budget of gn_onepass_kernel (+ 5 KB static <= 227 KB)
+
 static size_t gn_align16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
 
 extern "C" size_t vb200_groupnorm_workspace_size(int64_t n, int64_t groups, int64_t c) {
@@ -516,9 +518,10 @@ static int gn_launch(const bf16* x, const bf16* w, const bf16* b, bf16* out, GnW
   auto kern = gn_onepass_kernel<ACT, CACHED>;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // 227 KB per CTA minus the kernel's static shared memory (gsum + flags: 5 KB)
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_DYN_SMEM_MAX);
     if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
-    smem_set = 227 * 1024;
+    smem_set = GN_DYN_SMEM_MAX;
   }
   kern<<<grid, threads, smem, stream>>>(x, w, b, out, ws, spatial, c, groups, rpc, rpp, eps);
   VB_LAUNCH_CHECK();
@@ -557,7 +560,7 @@ extern "C" int vb200_groupnorm_nhwc(const void* x, const void* weight, const voi
   per = (spatial + rpc - 1) / rpc;
   const size_t part_bytes = static_cast<size_t>(rpp) * c * 2 * sizeof(float);
   const size_t slab_bytes = static_cast<size_t>(rpc) * c * 2;
-  const bool cached = part_bytes + slab_bytes <= 220 * 1024;
+  const bool cached = part_bytes + slab_bytes <= static_cast<size_t>(GN_DYN_SMEM_MAX);
   const size_t smem = part_bytes + (cached ? slab_bytes : 0);
   dim3 grid(static_cast<unsigned>(per), static_cast<unsigned>(n));
   const bf16* xp = reinterpret_cast<const bf16*>(x);
