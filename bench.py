@@ -381,7 +381,7 @@ def unet_gemm_roofline(unet, noise, cond, tf_peak, peak_kind):
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g), ops.pdl(True):   # same launch mode as the benchmarked step
         replay()
     for _ in range(2):
         g.replay()
@@ -517,6 +517,67 @@ def bench_unet(device, tf_peak, peak_kind, steps=10, rank=0, world=1, with_cpu=T
     return out
 
 
+VIDEO_CLIPS, VIDEO_FRAMES, VIDEO_TEXT, VIDEO_NEW = 64, 8, 64, 32
+
+
+def bench_video(device, rank, world, steps=2):
+    """BASELINE.json configs[2]: 8-frame 224x224 clips -> LanguageBind video tower (temporal attention) + projector +
+    Vicuna-7B prefill over 8 x 256 vision + 65 text tokens + 32 greedy tokens, data-parallel batch 64 over N GPUs: the 64
+    clips are SHARDED 64/N per rank (strong scaling), inputs start in pinned host memory (H2D inside the timed region), one
+    NCCL all_gather of the generated ids. value = 64 clips / max-over-ranks step time."""
+    from vitron_b200 import ops, param_shapes as PS
+    from vitron_b200.dist import gather_results, shard_range
+    from vitron_b200.vision_tower import VisionConfig
+    from vitron_b200.vitron_model import VitronConfig, VitronLlamaForCausalLM
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+    lo, hi = shard_range(VIDEO_CLIPS, rank, world)
+    clips = hi - lo
+    T = VIDEO_FRAMES
+    S = T * 256 + VIDEO_TEXT + 1
+    vcfg = VisionConfig(**VIT_L14, add_time_attn=True, num_frames=T)
+    cfg = VitronConfig(llm=VICUNA_7B, vision=None, video=vcfg, tokenizer_model_max_length=4096, eos_token_id=None)
+    model = VitronLlamaForCausalLM(cfg, device, max_batch=clips, max_seq_len=S + VIDEO_NEW)
+    sd = PS.random_state_dict(PS.vitron_shapes(cfg), device, seed=0)
+    model.load_state_dict(sd)
+    del sd
+    torch.cuda.empty_cache()
+    g = torch.Generator().manual_seed(100 + rank)
+    vids = [torch.randn((3, T, 224, 224), generator=g).pin_memory() for _ in range(clips)]
+    ids = torch.cat([torch.ones((clips, 1), dtype=torch.long), torch.full((clips, T), -200, dtype=torch.long),
+                     torch.randint(3, 32000, (clips, VIDEO_TEXT), generator=g)], 1).pin_memory()
+
+    def step():
+        out = model.generate(ids.to(device, non_blocking=True), images=[v.to(device, non_blocking=True) for v in vids],
+                             max_new_tokens=VIDEO_NEW, do_sample=False, sync_every=VIDEO_NEW)
+        new = out[:, -VIDEO_NEW:].contiguous()
+        if world > 1:
+            new = gather_results(new, VIDEO_CLIPS)
+        return new.cpu()
+    step()
+    if world > 1:
+        dist.barrier()
+    l0 = ops.launch_count()
+    ms = timed(step, steps)
+    launches = (ops.launch_count() - l0) // steps
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    out = {"metric": "video clips/s: 8-frame LanguageBind video tower + Vicuna-7B prefill (2113 tokens) + 32 greedy tokens, global batch 64",
+           "value": VIDEO_CLIPS / (ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "strong", "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "BASELINE.json configs[2]: 64 clips sharded 64/N per GPU", "clips_per_gpu": clips, "frames": T,
+                      "prompt_tokens": S, "new_tokens": VIDEO_NEW, "parallelism": f"dp{world}"},
+           "generated_tokens_per_s": VIDEO_CLIPS * VIDEO_NEW / (ms * 1e-3), "gpu_launches": launches,
+           "h2d_bytes_per_step": clips * 3 * T * 224 * 224 * 4 + ids.numel() * 8, "d2h_bytes_per_step": VIDEO_CLIPS * VIDEO_NEW * 8}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world):
     from vitron_b200 import _lib, ops
     lib = _lib.load()
@@ -629,6 +690,13 @@ def run_ours(args, rank, world):
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": "tokens/s", "cores": cpu_info.get("threads"),
                                     "host_cores": _host_cores(), "kind": "port", "sample": CPU_SAMPLE_TEXT, **cpu_info}
+    # ---- configs[2]: the video job BASELINE.json names for 1/2/4/8 GPUs (strong scaling over a fixed batch of 64)
+    video_line = None
+    if not args.no_video:
+        del model
+        model = None
+        torch.cuda.empty_cache()
+        video_line = bench_video(device, rank, world)
     # ---- the UNet half of the metric (every rank takes part when N > 1)
     unet_line = None
     if not args.no_unet:
@@ -638,6 +706,8 @@ def run_ours(args, rank, world):
         unet_line = bench_unet(device, tf_peak_all, kind_all, steps=max(10, args.steps), rank=rank, world=world,
                                with_cpu=(rank == 0))
     if rank == 0:
+        if video_line is not None:
+            line["video_cfg2"] = video_line
         if unet_line is not None:
             line["unet"] = unet_line
         print(json.dumps(line), flush=True)
@@ -655,7 +725,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-input", default="raw", choices=["raw", "processed"],
                     help="e2e arm input: raw uint8 336x336 images (device-side transform) or pre-processed fp32 pixels")
-    ap.add_argument("--no-unet", action="store_true", help="skip the secondary i2vgen-xl UNet3D steps/s measurement")
+    ap.add_argument("--no-unet", action="store_true", help="skip the i2vgen-xl UNet3D steps/s measurement")
+    ap.add_argument("--no-video", action="store_true", help="skip the configs[2] video batch-64 measurement")
     ap.add_argument("--profile", action="store_true",
                     help="ncu launch-list mode: one un-graphed step with 4 decode tokens, no timing loops")
     args = ap.parse_args()

@@ -103,6 +103,10 @@ int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int64_t nb, i
 /* 0 = the compile-time-specialised kernel (gemm_v2) whenever the operands allow its 256-bit epilogue accesses
  * (default), 1 = the generic kernel only. Returns the previous setting. For A/B measurements and parity tests. */
 int vb200_set_gemm_impl(int impl);
+/* Measurement aids of the v2 kernel: resident_b 0 / 1 switches the small-K "weight slab stays in shared memory" variant
+ * (default 1), dbg bit 0 makes the epilogue skip its work (wrong results: timing of the main loop alone). -1 keeps a
+ * setting. Returns the previous (resident_b | dbg << 8). */
+int vb200_set_gemm_debug(int resident_b, int dbg);
 
 /* direct (SIMT) convolution for the two odd-shaped layers (cin < 8-aligned or tiny cout) */
 int vb200_conv_nhwc_direct(const void* X, const void* Wt, const void* bias, void* out, int64_t nb,
@@ -139,6 +143,18 @@ int vb200_attention(const void* q, const void* k, const void* v, void* out, int6
                     int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh,
                     float scale, int causal, const int32_t* kv_len, const uint8_t* mask,
                     int64_t m_sb, int64_t m_sh, int64_t m_sq, cudaStream_t stream);
+/* Same with a workspace: few-query attention over long memories (SEEM: 101 queries x 8 heads over up to 16384 keys is 8
+ * CTAs) is split over the keys — every CTA writes its un-normalised partial O and (max, sum) to the workspace and a merge
+ * kernel combines them. vb200_attention_workspace_size reports the bytes (0 when the shape is not split); no zero-fill
+ * needed. With workspace == NULL the call runs unsplit (= vb200_attention). */
+size_t vb200_attention_workspace_size(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t head_dim, int causal);
+int vb200_attention_ws(const void* q, const void* k, const void* v, void* out, int64_t B, int64_t H,
+                       int64_t Sq, int64_t Skv, int64_t head_dim, int64_t q_sb, int64_t q_ss,
+                       int64_t q_sh, int64_t k_sb, int64_t k_ss, int64_t k_sh, int64_t v_sb,
+                       int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh,
+                       float scale, int causal, const int32_t* kv_len, const uint8_t* mask,
+                       int64_t m_sb, int64_t m_sh, int64_t m_sq, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream);
 /* tiny sequences (S <= 32, head_dim 64): temporal attention of the video tower
  * (modeling_video.py:105-127) and of TemporalTransformer (util.py:1061-1066). */
 int vb200_attention_short(const void* q, const void* k, const void* v, void* out, int64_t nseq,

@@ -268,6 +268,10 @@ ATT_TC = [
     (2, 4, 768, 768, 128, True), (8, 16, 257, 257, 64, False), (2, 5, 2560, 2560, 64, False),
     (2, 5, 640, 145, 64, False), (1, 8, 101, 1024, 64, False), (3, 2, 70, 200, 128, True),
     (1, 2, 1, 130, 128, True), (1, 3, 130, 1, 64, False), (2, 2, 129, 63, 128, False), (1, 32, 1728, 1728, 128, True),
+    # GLIGEN gated self-attention (visual + 30 grounding tokens; heads x 40 / 80 / 160): zero-padded by the TMA unit
+    (2, 8, 1054, 1054, 80, False), (2, 8, 286, 286, 160, False), (1, 8, 4126, 4126, 40, False), (2, 3, 200, 77, 40, True),
+    # few queries over a long memory: split over the keys + merge kernel (SEEM cross-attention levels)
+    (1, 8, 101, 16384, 64, False), (1, 8, 101, 4096, 64, False), (2, 2, 130, 2000, 128, False), (1, 4, 100, 1100, 80, False),
 ]
 
 
@@ -288,6 +292,30 @@ def test_attention_tcgen05(cuda, B, H, Sq, Skv, D, causal, amp):
         ops.set_attention_impl(0)
     close(out, ref, 2e-2, 2e-2, "tcgen05 attention")
     close(out, out_mma, 2e-2, 2e-2, "tcgen05 vs mma.sync")
+
+
+@pytest.mark.parametrize("B,H,Sq,Skv,D", [(1, 8, 101, 1024, 64), (2, 8, 101, 4096, 64), (2, 4, 300, 1000, 64), (1, 2, 130, 77, 128),
+                                          (2, 8, 286, 286, 160)])
+def test_attention_tcgen05_bool_mask(cuda, B, H, Sq, Skv, D):
+    """SEEM masked cross-attention (101 queries over 32^2 / 64^2 memories, mask shared by the heads) and general
+    per-head masks on the tcgen05 kernel: 16-byte mask rows (Skv % 16 == 0) and the byte-wise path (Skv = 1000, 77)."""
+    from vitron_b200 import ops
+    q, k, v = rnd((B, Sq, H, D), cuda, 1), rnd((B, Skv, H, D), cuda, 2), rnd((B, Skv, H, D), cuda, 3)
+    g = torch.Generator().manual_seed(5)
+    for shape in ((B, 1, Sq, Skv), (B, H, Sq, Skv), (1, 1, Sq, Skv)):
+        mask = (torch.rand(shape, generator=g) < 0.6).to(cuda)
+        mask[0, 0, 5] = True          # a fully masked row -> zeros
+        mask[0, 0, 7, :64] = True     # a fully masked first key block followed by live keys
+        ref = sdpa_ref(q, k, v, 1 / math.sqrt(D), mask=mask)
+        try:
+            ops.set_attention_impl(2)
+            out = ops.attention(q, k, v, mask=mask)
+            ops.set_attention_impl(1)
+            out_mma = ops.attention(q, k, v, mask=mask)
+        finally:
+            ops.set_attention_impl(0)
+        close(out, ref, 2e-2, 2e-2, f"tcgen05 masked attention {shape}")
+        close(out, out_mma, 2e-2, 2e-2, "tcgen05 vs mma.sync (masked)")
 
 
 def test_attention_tcgen05_layouts(cuda):

@@ -132,3 +132,26 @@ def test_seem_vs_reference_golden(cuda):
     assert_close(out["aux_outputs"][0]["pred_logits"], ref["aux_outputs"][0]["pred_logits"], "golden layer-0 class logits", 0.03, 0.03)
     assert_close(out["pred_masks"], ref["pred_masks"], "golden pred_masks", 0.3, 0.08)
     assert_close(out["pred_maskembs"], ref["pred_maskembs"], "golden pred_maskembs", 0.3, 0.08)
+
+
+def test_seem_head_graph_replay_equals_eager(cuda):
+    """XDecoderHead.enable_graph(): the CUDA-graph replay of the whole head returns exactly what the eager launch sequence
+    returns (same kernels, same order), on two consecutive inputs (static buffers are refreshed)."""
+    in_ch, C, ffn, Q, heads, dim_proj = (32, 64, 64, 96), 128, 256, 16, 2, 64
+    sd, head = build(cuda, in_ch, C, ffn, Q, 1, 3, heads, dim_proj, 9)
+    g = torch.Generator().manual_seed(5)
+    sizes = [(32, 48), (16, 24), (8, 12), (4, 6)]
+    outs = []
+    for rep in range(2):
+        feats = {f"res{i + 2}": torch.randn((1, c, *sizes[i]), generator=g).to(cuda) for i, c in enumerate(in_ch)}
+        head.enable_graph(False)
+        eager = head(feats)
+        e_masks, e_emb = eager["pred_masks"].clone(), eager["pred_maskembs"].clone()
+        head.enable_graph(True)
+        got = head(feats)
+        # same kernels in the same order; the GroupNorm group sums are fp32 atomics (order-dependent in the last bits), so the
+        # comparison is to rounding level, not bit-wise
+        for a, b_ in ((got["pred_masks"], e_masks), (got["pred_maskembs"], e_emb)):
+            assert (a.float() - b_.float()).abs().max().item() <= 2e-2 * b_.float().abs().max().item(), rep
+        outs.append(e_masks)
+    assert not torch.equal(outs[0], outs[1])

@@ -30,8 +30,9 @@ with torch.no_grad():
             unet(x, t, **kw)
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
+    from vitron_b200 import ops
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph), ops.pdl("nopdl" not in sys.argv):
         out = unet(x, t, **kw)
     for _ in range(3):
         graph.replay()

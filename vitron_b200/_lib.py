@@ -41,6 +41,7 @@ SIGNATURES = {
     "vb200_conv_nhwc_bf16": (_i32, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
                                     C.POINTER(Epilogue), _p, _sz, _p]),
     "vb200_set_gemm_impl": (_i32, [_i32]),
+    "vb200_set_gemm_debug": (_i32, [_i32, _i32]),
     "vb200_conv_nhwc_direct": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
     "vb200_rmsnorm": (_i32, [_p, _i64, _p, _p, _i64, _i64, _i64, _f, _p]),
     "vb200_row_rstd": (_i32, [_p, _i64, _p, _i64, _i64, _f, _p]),
@@ -49,6 +50,9 @@ SIGNATURES = {
     "vb200_groupnorm_nhwc": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _i32, _p, _sz, _p]),
     "vb200_attention": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64] + [_i64] * 12 +
                         [_f, _i32, _p, _p, _i64, _i64, _i64, _p]),
+    "vb200_attention_workspace_size": (_sz, [_i64, _i64, _i64, _i64, _i64, _i32]),
+    "vb200_attention_ws": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64] + [_i64] * 12 +
+                           [_f, _i32, _p, _p, _i64, _i64, _i64, _p, _sz, _p]),
     "vb200_attention_short": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64] + [_i64] * 17 + [_f, _p]),
     "vb200_add_rowgroup": (_i32, [_p, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "vb200_rope_kv_append": (_i32, [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _f, _p]),

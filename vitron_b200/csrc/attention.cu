@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(const AttnParams
   extern __shared__ __align__(16) uint8_t fa_smem[];
   bf16* sQ = reinterpret_cast<bf16*>(fa_smem);
   bf16* sK = sQ + 64 * LD;         // [2][64][LD]
+  pdl_trigger();
+  pdl_wait();
   bf16* sV = sK + 2 * 64 * LD;     // [2][64][LD]
 
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -262,7 +264,7 @@ static int launch_fa(const AttnParams& p, cudaStream_t stream) {
     attr = true;
   }
   dim3 grid((p.Sq + FA_BM - 1) / FA_BM, p.H, p.B);
-  kern<<<grid, FA_THREADS, smem, stream>>>(p);
+  { cudaError_t le = vb_launch(kern, grid, dim3(FA_THREADS), smem, stream, p); if (le != cudaSuccess) { vb_set_last_error(le); return VB_ERR_CUDA; } }
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
@@ -344,6 +346,8 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) attn_short_mma_kernel(const ShortParams p) {
   constexpr int HD = 64, LD = HD + 8;
   __shared__ __align__(16) bf16 sm[WARPS][3][16][LD];
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long item = static_cast<long long>(blockIdx.x) * WARPS + warp;
   if (item >= p.nseq * p.H) return;  // no CTA-wide barriers below
@@ -454,13 +458,21 @@ using namespace vb;
 int vb_attention_tc(const void* q, const void* k, const void* v, void* out, int64_t B, int64_t H, int64_t Sq,
                     int64_t Skv, int64_t head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb,
                     int64_t k_ss, int64_t k_sh, int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss,
-                    int64_t o_sh, float scale, int causal, const int32_t* kv_len, cudaStream_t stream);
+                    int64_t o_sh, float scale, int causal, const int32_t* kv_len, const uint8_t* mask, int64_t m_sb,
+                    int64_t m_sh, int64_t m_sq, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t vb_attention_tc_workspace(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t head_dim, int causal);
 
 static int g_attention_impl = 0;  // 0 auto, 1 mma.sync only, 2 tcgen05 whenever the shape is supported
 extern "C" int vb200_set_attention_impl(int impl) {
   VB_CHECK_ARG(impl >= 0 && impl <= 2);
   g_attention_impl = impl;
   return VB_OK;
+}
+
+extern "C" size_t vb200_attention_workspace_size(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t head_dim, int causal) {
+  if (B <= 0 || H <= 0 || Sq <= 0 || Skv <= 0 || head_dim <= 0) return 0;
+  if (Sq < 96 && g_attention_impl != 2) return 0;
+  return vb_attention_tc_workspace(B, H, Sq, Skv, head_dim, causal);
 }
 
 extern "C" int vb200_attention(const void* q, const void* k, const void* v, void* out, int64_t B,
@@ -470,17 +482,28 @@ extern "C" int vb200_attention(const void* q, const void* k, const void* v, void
                                int64_t o_sh, float scale, int causal, const int32_t* kv_len,
                                const uint8_t* mask, int64_t m_sb, int64_t m_sh, int64_t m_sq,
                                cudaStream_t stream) {
+  return vb200_attention_ws(q, k, v, out, B, H, Sq, Skv, head_dim, q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb,
+                            o_ss, o_sh, scale, causal, kv_len, mask, m_sb, m_sh, m_sq, nullptr, 0, stream);
+}
+
+extern "C" int vb200_attention_ws(const void* q, const void* k, const void* v, void* out, int64_t B,
+                                  int64_t H, int64_t Sq, int64_t Skv, int64_t head_dim, int64_t q_sb,
+                                  int64_t q_ss, int64_t q_sh, int64_t k_sb, int64_t k_ss, int64_t k_sh,
+                                  int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss,
+                                  int64_t o_sh, float scale, int causal, const int32_t* kv_len,
+                                  const uint8_t* mask, int64_t m_sb, int64_t m_sh, int64_t m_sq,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   VB_CHECK_ARG(q && k && v && out);
   VB_CHECK_ARG(B > 0 && H > 0 && Sq > 0 && Skv >= 0 && head_dim > 0 && head_dim % 8 == 0);
   VB_CHECK_ARG(H <= 65535 && B <= 65535);
   const int64_t strides[12] = {q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh};
   for (int i = 0; i < 12; ++i) VB_CHECK_ARG(strides[i] % 8 == 0);
-  // tcgen05 / TMEM kernel (attention_tc.cu) for unmasked head_dim 64 / 128 with enough query rows to fill
-  // its 128-row tiles; everything else (boolean masks, head_dim 40/80/160, short queries) stays on mma.sync.
-  if (!mask && g_attention_impl != 1 && (head_dim == 64 || head_dim == 128) && Skv >= 1 &&
-      (Sq >= 96 || g_attention_impl == 2)) {
+  // tcgen05 / TMEM kernel (attention_tc.cu): head_dim 64 / 128 natively, 40 / 80 / 160 zero-padded by the TMA unit,
+  // boolean masks applied in registers; taken whenever the query rows fill most of a 128-row tile. Short queries and
+  // operand layouts a tensor map cannot describe stay on the mma.sync kernel below.
+  if (g_attention_impl != 1 && Skv >= 1 && (Sq >= 96 || g_attention_impl == 2)) {
     int r = vb_attention_tc(q, k, v, out, B, H, Sq, Skv, head_dim, q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss,
-                            v_sh, o_sb, o_ss, o_sh, scale, causal, kv_len, stream);
+                            v_sh, o_sb, o_ss, o_sh, scale, causal, kv_len, mask, m_sb, m_sh, m_sq, workspace, workspace_bytes, stream);
     if (r != VB_ERR_UNSUPPORTED) return r;
   }
   AttnParams p;
@@ -526,7 +549,7 @@ extern "C" int vb200_attention_short(const void* q, const void* k, const void* v
   const int64_t all[16] = {q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh, q_so, k_so, v_so, o_so};
   for (int i = 0; i < 16; ++i) vec16 = vec16 && (all[i] % 8 == 0);
   if (vec16) {
-    attn_short_mma_kernel<4><<<static_cast<unsigned>((items + 3) / 4), 128, 0, stream>>>(p);
+    { cudaError_t le = vb_launch(attn_short_mma_kernel<4>, dim3(static_cast<unsigned>((items + 3) / 4)), dim3(128), 0, stream, p); if (le != cudaSuccess) { vb_set_last_error(le); return VB_ERR_CUDA; } }
     VB_LAUNCH_CHECK();
     return VB_OK;
   }

@@ -1,6 +1,11 @@
 // vitron_b200 — flash attention on tcgen05 tensor cores with TMEM accumulators (sm_100a).
 //
-//   O = softmax(Q K^T * scale [causal, kv_len]) V       head_dim 64 or 128, bf16 in / out, fp32 math
+//   O = softmax(Q K^T * scale [causal, kv_len, bool mask]) V     bf16 in / out, fp32 math
+//   head_dim 64 / 128 natively; 40 / 80 / 160 (GLIGEN, attention.py:192-257) run the 64 / 128 / 192-column
+//   instantiation: the tensor maps carry the true head_dim, so the TMA unit zero-fills the padding columns of
+//   Q / K / V in shared memory (they add 0 to QK^T and produce zero O columns that are never stored).
+//   Boolean masks (SEEM masked cross-attention, utils/attn.py:296-316): uint8 [B|1, H|1, Sq, Skv], non-zero = masked
+//   out, applied to S in registers; a row with every key masked yields zeros.
 //
 // One CTA = 128 query rows of one (batch, head); keys stream through in blocks of 64.
 //   warp 0      TMA producer: Q once, K_j / V_j into 2-stage 128B-swizzled rings (4-D tensor maps over the
@@ -29,9 +34,15 @@ struct TcAttnParams {
   bf16* o;
   long long o_sb, o_ss, o_sh;
   int B, H, Sq, Skv;
+  int D;                 // true head dim (<= the kernel's HD; the difference is zero padding)
   float scale_log2;
   int causal;
   const int32_t* kv_len;
+  const uint8_t* mask;   // or null
+  long long m_sb, m_sh, m_sq;
+  int splits;            // > 1: the key blocks are divided over `splits` CTAs per query tile (few-query attention: SEEM's
+  float* ws_o;           //      101 queries over 16384 keys would otherwise run on 8 CTAs); each writes its un-normalised
+  float* ws_ml;          //      O (fp32) and (m, l) to the workspace, attn_split_merge_kernel combines them
 };
 
 // Bounded mbarrier wait: a protocol or descriptor bug must never hang the GPU. After 4 s without progress the
@@ -104,12 +115,14 @@ template <int HD>
 __global__ void __launch_bounds__(TC_THREADS)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const TcAttnParams p) {
+  pdl_trigger();
+  pdl_wait();   // (the tcgen05 / mbarrier set-up below touches no global data, but the kernel's first TMA load follows at once)
   constexpr int KC = HD / 64;                   // 64-element chunks along the head dim
   constexpr int Q_BYTES = TC_BM * HD * 2;       // [KC][128][64]
   constexpr int K_BYTES = TC_BN * HD * 2;       // [KC][64][64]   K-major
   constexpr int V_BYTES = TC_BN * HD * 2;       // [KC][64 keys][64]   MN-major atoms
   constexpr int P_BYTES = TC_BM * TC_BN * 2;    // [128][64]   K-major
-  constexpr uint32_t TMEM_COLS = (2 * TC_BN + HD <= 128) ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = (2 * TC_BN + HD <= 128) ? 128 : (2 * TC_BN + HD <= 256) ? 256 : 512;
   constexpr uint32_t S_COL = 0, O_COL = 2 * TC_BN;
 
   // No static shared memory in this kernel, so the dynamic window starts at the (1024-byte aligned) base of the
@@ -133,13 +146,17 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   volatile uint32_t* abort_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qb = blockIdx.x / p.splits, sp = blockIdx.x - qb * p.splits, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * TC_BM;
   const int kv_len = p.kv_len ? min(p.kv_len[b], p.Skv) : p.Skv;
   const int causal_off = p.Skv - p.Sq;
   int kv_end = kv_len;
   if (p.causal) kv_end = min(kv_len, q0 + TC_BM + causal_off);
-  const int nblk = kv_end > 0 ? (kv_end + TC_BN - 1) / TC_BN : 0;
+  const int nblk_all = kv_end > 0 ? (kv_end + TC_BN - 1) / TC_BN : 0;
+  // this CTA's share of the key blocks: [jb0, jb0 + nblk)
+  const int per_split = (nblk_all + p.splits - 1) / p.splits;
+  const int jb0 = sp * per_split;
+  const int nblk = max(0, min(nblk_all, jb0 + per_split) - jb0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_q);
@@ -177,11 +194,11 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tc_wait(&k_empty[st], ph ^ 1, abort_flag, 5);
         mbar_arrive_expect_tx(&k_full[st], K_BYTES);
 #pragma unroll
-        for (int c = 0; c < KC; ++c) tma_load_4d(sK + st * K_BYTES + c * (TC_BN * 128), &tmap_k, &k_full[st], c * 64, j * TC_BN, h, b);
+        for (int c = 0; c < KC; ++c) tma_load_4d(sK + st * K_BYTES + c * (TC_BN * 128), &tmap_k, &k_full[st], c * 64, (jb0 + j) * TC_BN, h, b);
         tc_wait(&v_empty[st], ph ^ 1, abort_flag, 6);
         mbar_arrive_expect_tx(&v_full[st], V_BYTES);
 #pragma unroll
-        for (int c = 0; c < KC; ++c) tma_load_4d(sV + st * V_BYTES + c * (TC_BN * 128), &tmap_v, &v_full[st], c * 64, j * TC_BN, h, b);
+        for (int c = 0; c < KC; ++c) tma_load_4d(sV + st * V_BYTES + c * (TC_BN * 128), &tmap_v, &v_full[st], c * 64, (jb0 + j) * TC_BN, h, b);
       }
     }
   } else if (warp == 1) {
@@ -242,9 +259,21 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tc_wait(&s_full[st], (j >> 1) & 1, abort_flag, 7);
       tc_fence_after();
       const uint32_t s_addr = tmem_base + lane_addr + S_COL + st * TC_BN;
-      const int kbase = j * TC_BN;
+      const int kbase = (jb0 + j) * TC_BN;
       // CTA-uniform: does any row of this tile see a masked key in this block?
       const bool need_mask = (kbase + TC_BN > kv_end) || (p.causal && kbase + TC_BN - 1 > q0 + causal_off);
+      // boolean mask bytes of this row / key block: fetched before the wait on the TMEM load
+      uint4 mb[4];
+      bool mvec = false;
+      const uint8_t* mrow = nullptr;
+      if (p.mask != nullptr && qrow < p.Sq) {
+        mrow = p.mask + b * p.m_sb + h * p.m_sh + static_cast<long long>(qrow) * p.m_sq + kbase;
+        mvec = kbase + TC_BN <= p.Skv && (reinterpret_cast<uintptr_t>(mrow) & 15) == 0;
+        if (mvec) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mb[i] = __ldg(reinterpret_cast<const uint4*>(mrow) + i);
+        }
+      }
       uint32_t sv[2][32];
       tmem_ld_32x32(s_addr, sv[0]);
       tmem_ld_32x32(s_addr + 32, sv[1]);
@@ -256,6 +285,23 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i >= lim) sv[c][i] = 0xff800000u;  // -inf
+      }
+      if (mrow != nullptr) {
+        if (mvec) {
+#pragma unroll
+          for (int w = 0; w < 16; ++w) {
+            const uint32_t word = w % 4 == 0 ? mb[w / 4].x : w % 4 == 1 ? mb[w / 4].y : w % 4 == 2 ? mb[w / 4].z : mb[w / 4].w;
+#pragma unroll
+            for (int bt = 0; bt < 4; ++bt)
+              if ((word >> (8 * bt)) & 0xffu) sv[(w * 4 + bt) / 32][(w * 4 + bt) % 32] = 0xff800000u;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kbase + c * 32 + i < p.Skv && mrow[c * 32 + i]) sv[c][i] = 0xff800000u;
+        }
       }
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains: the softmax warps are
 #pragma unroll                                                      // latency-, not issue-bound
@@ -332,6 +378,34 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tc_wait(pv_done, (nblk - 1) & 1, abort_flag, 9);
       tc_fence_after();
     }
+    if (p.splits > 1) {
+      // ---- partial result of this key range: un-normalised O, the max its exponentials are relative to (exp2 domain), l
+      // (the TMEM loads are warp-aligned instructions: every lane executes them, only the stores are predicated)
+      const long long slot = ((static_cast<long long>(b) * p.H + h) * p.splits + sp) * p.Sq + min(qrow, p.Sq - 1);
+      if (qrow < p.Sq) {
+        p.ws_ml[slot * 2] = (m_used == -INFINITY) ? -INFINITY : m_used * p.scale_log2;
+        p.ws_ml[slot * 2 + 1] = l;
+      }
+      float* orow_ws = p.ws_o + slot * HD;
+#pragma unroll 1
+      for (int c = 0; c < HD; c += 32) {
+        uint32_t ov[32];
+        if (nblk > 0) {
+          tmem_ld_32x32(tmem_base + lane_addr + O_COL + c, ov);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ov[i] = 0;
+        }
+        if (qrow < p.Sq) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (c + i < p.D)
+              *reinterpret_cast<float4*>(orow_ws + c + i) = make_float4(__uint_as_float(ov[i]), __uint_as_float(ov[i + 1]),
+                                                                        __uint_as_float(ov[i + 2]), __uint_as_float(ov[i + 3]));
+        }
+      }
+    } else {
     const float inv = l > 0.f ? 1.f / l : 0.f;
     bf16* orow = p.o + b * p.o_sb + h * p.o_sh + static_cast<long long>(qrow) * p.o_ss;
 #pragma unroll 1
@@ -347,12 +421,14 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (qrow < p.Sq) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8)
+          if (c + i < p.D)
           *reinterpret_cast<uint4*>(orow + c + i) =
               make_uint4(pack_bf16(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv),
                          pack_bf16(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv),
                          pack_bf16(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv),
                          pack_bf16(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv));
       }
+    }
     }
   }
 
@@ -362,6 +438,38 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+// out[b, q, h, :] = sum_s O_s 2^(m_s - M) / sum_s l_s 2^(m_s - M): one thread per 4 head-dim columns of a (b, h, q) row
+__global__ void attn_split_merge_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml, bf16* __restrict__ out,
+                                        long long o_sb, long long o_ss, long long o_sh, int B, int H, int Sq, int D, int HD, int splits) {
+  pdl_trigger();
+  pdl_wait();
+  const int vecs = D / 4;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * H * Sq * vecs) return;
+  const int v = static_cast<int>(idx % vecs);
+  const long long row = idx / vecs;          // (b * H + h) * Sq + q
+  const int q = static_cast<int>(row % Sq);
+  const long long bh = row / Sq;
+  float M = -INFINITY;
+  for (int s = 0; s < splits; ++s) M = fmaxf(M, ws_ml[((bh * splits + s) * Sq + q) * 2]);
+  float L = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (M != -INFINITY) {
+    for (int s = 0; s < splits; ++s) {
+      const long long slot = (bh * splits + s) * Sq + q;
+      const float m = ws_ml[slot * 2];
+      if (m == -INFINITY) continue;
+      const float wgt = exp2f(m - M);
+      L += ws_ml[slot * 2 + 1] * wgt;
+      const float4 o = *reinterpret_cast<const float4*>(ws_o + slot * HD + v * 4);
+      a0 += o.x * wgt; a1 += o.y * wgt; a2 += o.z * wgt; a3 += o.w * wgt;
+    }
+  }
+  const float inv = L > 0.f ? 1.f / L : 0.f;
+  const int b = static_cast<int>(bh / H), h = static_cast<int>(bh % H);
+  bf16* dst = out + b * o_sb + h * o_sh + static_cast<long long>(q) * o_ss + v * 4;
+  *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(a0 * inv, a1 * inv), pack_bf16(a2 * inv, a3 * inv));
 }
 
 typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -409,8 +517,15 @@ static int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
-  dim3 grid((p.Sq + TC_BM - 1) / TC_BM, p.H, p.B);
-  kern<<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, p);
+  dim3 grid(((p.Sq + TC_BM - 1) / TC_BM) * p.splits, p.H, p.B);
+  { cudaError_t le = vb_launch(kern, grid, dim3(TC_THREADS), smem, stream, tq, tk, tv, p); if (le != cudaSuccess) { vb_set_last_error(le); return VB_ERR_CUDA; } }
+  if (p.splits > 1) {
+    const long long items = static_cast<long long>(p.B) * p.H * p.Sq * (p.D / 4);
+    cudaError_t le = vb_launch(attn_split_merge_kernel, dim3(static_cast<unsigned>((items + 255) / 256)), dim3(256), 0, stream,
+                               static_cast<const float*>(p.ws_o), static_cast<const float*>(p.ws_ml), p.o, p.o_sb, p.o_ss, p.o_sh,
+                               p.B, p.H, p.Sq, p.D, HD, p.splits);
+    if (le != cudaSuccess) { vb_set_last_error(le); return VB_ERR_CUDA; }
+  }
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
@@ -452,13 +567,35 @@ extern "C" int vb200_attention_tc_occupancy(int head_dim) {
   return n;
 }
 
+static int tc_hd(int64_t head_dim) { return head_dim <= 64 ? 64 : head_dim <= 128 ? 128 : 192; }
+
+// split-KV factor: only when the (query tile, head, batch) grid leaves most SMs idle and there are enough key blocks
+static int tc_splits(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int causal) {
+  if (causal) return 1;
+  const long long ctas = ((Sq + TC_BM - 1) / TC_BM) * H * B;
+  const long long nblk = (Skv + TC_BN - 1) / TC_BN;
+  const int sms = vb_num_sms();
+  if (ctas * 2 > sms || nblk < 8) return 1;
+  long long s = (2LL * sms + ctas - 1) / ctas;
+  if (s > nblk / 4) s = nblk / 4;
+  if (s > 32) s = 32;
+  return s < 2 ? 1 : static_cast<int>(s);
+}
+
+size_t vb_attention_tc_workspace(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t head_dim, int causal) {
+  const int s = tc_splits(B, H, Sq, Skv, causal);
+  if (s <= 1) return 0;
+  return static_cast<size_t>(s) * B * H * Sq * (tc_hd(head_dim) + 2) * sizeof(float);
+}
+
 // Returns VB_ERR_UNSUPPORTED when the shape / strides are outside what this kernel handles; the caller
 // (vb200_attention) then uses the mma.sync kernel.
 int vb_attention_tc(const void* q, const void* k, const void* v, void* out, int64_t B, int64_t H, int64_t Sq,
                     int64_t Skv, int64_t head_dim, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb,
                     int64_t k_ss, int64_t k_sh, int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss,
-                    int64_t o_sh, float scale, int causal, const int32_t* kv_len, cudaStream_t stream) {
-  if (head_dim != 64 && head_dim != 128) return VB_ERR_UNSUPPORTED;
+                    int64_t o_sh, float scale, int causal, const int32_t* kv_len, const uint8_t* mask, int64_t m_sb,
+                    int64_t m_sh, int64_t m_sq, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (head_dim != 40 && head_dim != 64 && head_dim != 80 && head_dim != 128 && head_dim != 160) return VB_ERR_UNSUPPORTED;
   if (Skv < 1 || Sq < 1) return VB_ERR_UNSUPPORTED;
   const int64_t st[12] = {q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh};
   for (int i = 0; i < 12; ++i)
@@ -483,6 +620,20 @@ int vb_attention_tc(const void* q, const void* k, const void* v, void* out, int6
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   p.kv_len = kv_len;
-  if (head_dim == 64) return launch_tc<64>(tq, tk, tv, p, stream);
-  return launch_tc<128>(tq, tk, tv, p, stream);
+  p.D = static_cast<int>(head_dim);
+  p.mask = mask;
+  p.m_sb = m_sb; p.m_sh = m_sh; p.m_sq = m_sq;
+  p.splits = 1;
+  p.ws_o = nullptr;
+  p.ws_ml = nullptr;
+  const size_t need = vb_attention_tc_workspace(B, H, Sq, Skv, head_dim, causal);
+  if (need > 0 && kv_len == nullptr && workspace != nullptr && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
+      (head_dim % 4) == 0) {
+    p.splits = tc_splits(B, H, Sq, Skv, causal);
+    p.ws_o = reinterpret_cast<float*>(workspace);
+    p.ws_ml = p.ws_o + static_cast<size_t>(p.splits) * B * H * Sq * tc_hd(head_dim);
+  }
+  if (head_dim <= 64) return launch_tc<64>(tq, tk, tv, p, stream);
+  if (head_dim <= 128) return launch_tc<128>(tq, tk, tv, p, stream);
+  return launch_tc<192>(tq, tk, tv, p, stream);
 }

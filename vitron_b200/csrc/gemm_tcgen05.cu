@@ -525,6 +525,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits,
                                      const bf16* __restrict__ rowbias, int rowbias_rows,
                                      const bf16* __restrict__ residual, long long ldr, float alpha,
                                      int act, int glu, int out_fp32, const float* __restrict__ rowscale) {
+  pdl_trigger();
+  pdl_wait();
   const int n_out_total = glu != VB_GLU_NONE ? ncols / 2 : ncols;
   const int groups = (n_out_total + 7) / 8;
   long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -664,6 +666,34 @@ static int validate_epi(const vb_epilogue* e, long long N) {
 
 // ------------------------------------------------------------------ v2 planning
 static int g_gemm_impl = 0;  // 0: v2 whenever eligible, 1: generic kernel only (A/B measurements, parity tests of both)
+static int g_gemm_resb = 1;  // resident-B variant: bit 0 = K <= 320 (5 k-blocks), bit 1 = also K <= 640 at BN = 128; 0 = off
+static int g_gemm_dbg = 0;   // GemmParams.dbg of the v2 launches (measurement aid)
+int resb_smem_bytes(int bn, int nkb);  // gemm_v2_resb.cu
+
+// Tile width of the resident-B variant for M x N x (nkb k-blocks), or 0 when it does not apply: the widest slab that
+// fits next to an A ring deep enough to cover the L2 latency (BN = 160 with 6 A stages at K <= 320; BN = 128 at K <= 640).
+static int resb_tile(long long M, long long N, int nkb, int need) {
+  if (!g_gemm_resb || (need != 0 && need != F_RES && need != F_GLU && need != F_ACT)) return 0;
+  if (nkb > 5 && !(g_gemm_resb & 2)) return 0;
+  if (M < 4096) return 0;                       // few m-tiles: nothing to amortise the slab load over
+  const int cands[3] = {160, 256, 128};
+  int best = 0;
+  float best_cost = 1e30f;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (resb_smem_bytes(bn, nkb) > SMEM_LIMIT) continue;
+    const long long nb = (N + bn - 1) / bn;
+    if (nb > vb_num_sms()) continue;
+    const int groups = vb_num_sms() / static_cast<int>(nb);
+    const long long mb = (M + BLOCK_M - 1) / BLOCK_M;
+    const long long per_cta = (mb + groups - 1) / groups;     // m-tiles of the busiest CTA
+    // per tile: MMA ~ bn / 256 units per k-block, A stream ~ 0.55 unit per k-block with a deep ring (BN 160), 0.9 with 3 stages
+    const float mma = static_cast<float>(bn) / 256.f, astream = bn == 160 ? 0.55f : 0.9f;
+    const float cost = static_cast<float>(per_cta) * nkb * (mma > astream ? mma : astream);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
 
 struct TilePlan {
   int bn, splits;
@@ -748,10 +778,10 @@ static int launch_gemm_v2(int bn, int need, const CUtensorMap& ta, const CUtenso
   // split-K: sum the partials in split order + the fused epilogue, one thread per 8 outputs of a row
   const int n_out = p.glu != VB_GLU_NONE ? p.N / 2 : p.N;
   const long long items = static_cast<long long>(p.M) * ((n_out + 7) / 8);
-  splitk_reduce_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, stream>>>(
-      p.ws, p.splits, p.ws_split_stride, p.ws_ld, p.M, p.N, p.out, p.ldo, p.bias, p.rowbias, p.rowbias_rows, p.residual,
-      p.ldr, p.alpha, p.act, p.glu, p.out_fp32, p.rowscale);
-  VB_LAUNCH_CHECK();
+  cudaError_t le = vb_launch(splitk_reduce_kernel, dim3(static_cast<unsigned>((items + 255) / 256)), dim3(256), 0, stream,
+                             static_cast<const float*>(p.ws), p.splits, p.ws_split_stride, p.ws_ld, p.M, p.N, p.out, p.ldo, p.bias,
+                             p.rowbias, p.rowbias_rows, p.residual, p.ldr, p.alpha, p.act, p.glu, p.out_fp32, p.rowscale);
+  if (le != cudaSuccess) { vb_set_last_error(le); return VB_ERR_CUDA; }
   return VB_OK;
 }
 
@@ -774,6 +804,13 @@ static void conv_pixel_tile(int wo, int ho, long long nb, int& tw, int& th, int&
 }  // namespace vb
 
 using namespace vb;
+
+extern "C" int vb200_set_gemm_debug(int resident_b, int dbg) {
+  const int prev = g_gemm_resb | (g_gemm_dbg << 8);
+  if (resident_b >= 0) g_gemm_resb = resident_b;
+  if (dbg >= 0) g_gemm_dbg = dbg;
+  return prev;
+}
 
 extern "C" int vb200_set_gemm_impl(int impl) {
   const int prev = g_gemm_impl;
@@ -864,6 +901,21 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   p.N = static_cast<int>(N);
   p.m_blocks = static_cast<int>((M + BLOCK_M - 1) / BLOCK_M);
   if (v2_eligible(epi, out, ldo, N)) {
+    p.dbg = g_gemm_dbg;
+    if (const int rbn = resb_tile(M, N, p.num_k_blocks, v2_need(epi, 1))) {
+      p.n_blocks = static_cast<int>((N + rbn - 1) / rbn);
+      p.splits = 1;
+      uint64_t dA[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+      uint64_t sA[1] = {static_cast<uint64_t>(lda) * 2};
+      uint32_t bA[2] = {BLOCK_K, BLOCK_M};
+      if (int r = make_tmap(&ta, A, 2, dA, sA, bA, estr2)) return r;
+      uint64_t dB[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+      uint64_t sB[1] = {static_cast<uint64_t>(ldw) * 2};
+      uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(rbn)};
+      if (int r = make_tmap(&tb, W, 2, dB, sB, bB, estr2)) return r;
+      const int r = launch_gemm_v2_resb(rbn, v2_need(epi, 1), ta, tb, p, stream);
+      if (r != VB_ERR_UNSUPPORTED) return r;
+    }
     TilePlan pl = plan_tiles(p.m_blocks, N, p.num_k_blocks, true, M);
     if (pl.splits > 1) {
       const size_t need_ws = GEMM_COUNTER_BYTES + static_cast<size_t>(pl.splits) * M * N * sizeof(float);

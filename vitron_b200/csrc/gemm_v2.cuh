@@ -83,13 +83,17 @@ static __device__ __noinline__ void epi_ragged(const uint32_t* acc, int n_valid,
   }
 }
 
-template <int BLOCK_N, int STAGES, int F>
+// RESB ("resident B"): for small K (a few k-blocks) the CTA keeps ALL k-blocks of ONE n-block of the weight matrix in shared
+// memory for its whole life and works on m-tiles of that n-block only; the ring then carries A alone. Without it every
+// 128 x BN tile re-fetches its B tile from L2: at K = 320 the level-0 UNet GEMMs moved 184 KB per tile for 0.85 us of MMA —
+// 8.6 TB/s of L2 -> SM traffic, L2-bandwidth bound (in-situ 16.7 us for M 40960, N = K = 320 against ~4 us of MMA).
+template <int BLOCK_N, int STAGES, int F, bool RESB = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = RESB ? A_BYTES : A_BYTES + B_BYTES;
   constexpr int ACC_STAGES = 2;
   constexpr uint32_t TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32)    ? 32
                                  : (ACC_STAGES * BLOCK_N <= 64)  ? 64
@@ -104,17 +108,29 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   static_assert(BLOCK_N % 32 == 0, "v2 tiles are whole 32-column chunks");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                                ~static_cast<uintptr_t>(1023));
+  uint8_t* sB_res = smem_al;                                                    // RESB: [num_k_blocks][BLOCK_N x 128 B]
+  uint8_t* smem = smem_al + (RESB ? p.num_k_blocks * B_BYTES : 0);              // the ring
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+  uint64_t* b_full = tmem_empty + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  // per-epilogue-warp copy of the tile's additive column vector (bias [+ rowbias when one row group covers the warp's
+  // rows]) in fp32: filled BEFORE the wait for the accumulator, read back as 16-byte broadcasts. (Loading the bias from
+  // global inside every chunk put one L2 round trip, ~700 clk, on the critical path of each of a tile's 5-8 chunks:
+  // 3.5 us per 128 x 160 tile at K = 320 against 0.85 us of MMA.)
+  float* ebias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // (smem = the ring base)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Programmatic dependent launch: this grid may be scheduled while its predecessor on the stream drains. Everything up
+  // to pdl_wait() below (barrier init, TMEM allocation, tensor-map prefetch) touches no global data; every global read AND
+  // write of the kernel comes after it. The successor is released at once: it parks at its own pdl_wait().
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
@@ -126,6 +142,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
     }
+    mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -136,16 +153,36 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
-  const int total_units = p.m_blocks * p.n_blocks * p.splits;
+  // work units of this CTA: (m-block, n-block, split) in grouped raster order, or — RESB — the m-blocks
+  // m = blockIdx.x / n_blocks, += gridDim.x / n_blocks of the ONE n-block blockIdx.x % n_blocks (grid is a multiple of n_blocks)
+  const int total_units = RESB ? p.m_blocks : p.m_blocks * p.n_blocks * p.splits;
+  const int unit_first = RESB ? static_cast<int>(blockIdx.x) / p.n_blocks : static_cast<int>(blockIdx.x);
+  const int unit_step = RESB ? static_cast<int>(gridDim.x) / p.n_blocks : static_cast<int>(gridDim.x);
+  const int my_n_blk = RESB ? static_cast<int>(blockIdx.x) % p.n_blocks : 0;
+  auto work_of = [&](int unit) {
+    if constexpr (RESB) {
+      TileCoord t;
+      t.m_blk = unit; t.n_blk = my_n_blk; t.split = 0;
+      return t;
+    } else {
+      return decode_work(p, unit);
+    }
+  };
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        TileCoord t = decode_work(p, unit);
+      if constexpr (RESB) {
+        mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(p.num_k_blocks) * B_BYTES);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb)
+          tma_load_2d(sB_res + kb * B_BYTES, &tmap_b, b_full, kb * BLOCK_K, my_n_blk * BLOCK_N);
+      }
+      for (int unit = unit_first; unit < total_units; unit += unit_step) {
+        TileCoord t = work_of(unit);
         int k0, k1;
         split_range(p, t.split, k0, k1);
         int cw = 0, ch = 0, cn = 0;
@@ -162,7 +199,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes + B_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes + (RESB ? 0 : B_BYTES));
           if (p.a_mode == 0) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, t.m_blk * BLOCK_M);
           } else {
@@ -171,7 +208,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int dy = tap / p.kw, dx = tap - dy * p.kw;
             tma_load_4d(sa, &tmap_a, &full_bar[stage], cc * BLOCK_K, cw + dx, ch + dy, cn);
           }
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, t.n_blk * BLOCK_N);
+          if constexpr (!RESB) tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, t.n_blk * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -183,8 +220,11 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      TileCoord t = decode_work(p, unit);
+    if constexpr (RESB) {
+      if (unit_first < total_units) mbar_wait(b_full, 0);
+    }
+    for (int unit = unit_first; unit < total_units; unit += unit_step) {
+      TileCoord t = work_of(unit);
       int k0, k1;
       split_range(p, t.split, k0, k1);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -195,7 +235,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          const uint32_t sb = RESB ? smem_u32(sB_res + kb * B_BYTES) : sa + A_BYTES;
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sb);
 #pragma unroll
@@ -217,9 +257,8 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int ehalf = (warp - 2) >> 2;  // the two warps of a quadrant take alternate 32-column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int n_out_total = GLU ? (p.N >> 1) : p.N;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      const TileCoord t = decode_work(p, unit);
+    for (int unit = unit_first; unit < total_units; unit += unit_step) {
+      const TileCoord t = work_of(unit);
       const int r = quad * 32 + lane;  // accumulator row owned by this thread
       const int orow = tile_row_to_orow(p, t.m_blk, r);
       const int col0 = t.n_blk * BLOCK_N;
@@ -242,6 +281,30 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             rrow = p.residual + static_cast<size_t>(orow) * p.ldr + (GLU ? col0 / 2 : col0);
         }
       }
+      bool rb_staged = false;
+      float* sb = ebias + (warp - 2) * BLOCK_N;
+      if constexpr (!WS) {
+        int gsel = -1;
+        if constexpr ((F & F_RB) != 0) {
+          if (p.rowbias != nullptr) {
+            const int gme = orow >= 0 ? orow / p.rowbias_rows : -1;
+            const int gmax = __reduce_max_sync(0xffffffffu, gme);
+            const int gmin = __reduce_min_sync(0xffffffffu, gme < 0 ? gmax : gme);
+            if (gmax >= 0 && gmin == gmax) { gsel = gmax; rb_staged = true; }
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = lane; c < BLOCK_N; c += 32) {
+          float bv = 0.f;
+          if (col0 + c < p.N) {
+            if (p.bias != nullptr) bv = __bfloat162float(p.bias[col0 + c]);
+            if (gsel >= 0) bv += __bfloat162float(p.rowbias[static_cast<size_t>(gsel) * p.N + col0 + c]);
+          }
+          sb[c] = bv;
+        }
+        __syncwarp();
+      }
       uint8_t* orow_ptr = nullptr;  // first output element of this thread's row inside the tile
       if (orow >= 0) {
         if constexpr (WS)
@@ -255,10 +318,11 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                                 (GLU ? col0 / 2 : col0));
       }
 
-      // residual ring: the loads of up to RD chunks are issued BEFORE the wait for the accumulator (they do not depend
-      // on it), so their L2 latency (~800 clk) overlaps the MMA of this tile instead of stalling every chunk
+      // residual: the first chunk's loads are issued BEFORE the wait for the accumulator (they do not depend on it), the
+      // next chunk's while the current one is processed. (A 3-deep ring issued up front was measured: no gain in the
+      // UNet, +5 % on the BN = 160 residual variant from the extra registers.)
       constexpr int MYCH = (NCH + 1) / 2;            // chunks a warp handles at most
-      constexpr int RD = MYCH < 3 ? MYCH : 3;
+      constexpr int RD = MYCH < 2 ? MYCH : 2;
       uint32_t v[2][32];
       uint32_t rres[RD][16];
       auto prefetch_res = [&](int ci, uint32_t (&dst)[16]) {
@@ -278,9 +342,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       };
 
-#pragma unroll
-      for (int i = 0; i < RD; ++i)
-        if (NCH % 2 == 0 || ehalf + 2 * i < NCH) prefetch_res(ehalf + 2 * i, rres[i]);
+      if (NCH % 2 == 0 || ehalf < NCH) prefetch_res(ehalf, rres[0]);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (NCH % 2 == 0 || ehalf < NCH) tmem_ld_32x32(taddr + ehalf * 32, v[0]);
@@ -289,11 +351,14 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int ci = ehalf + 2 * it;
         if (NCH % 2 == 0 || ci < NCH) {
           tmem_ld_wait();
-          if (ci + 2 < NCH) tmem_ld_32x32(taddr + (ci + 2) * 32, v[(it + 1) & 1]);
+          if (ci + 2 < NCH) {
+            tmem_ld_32x32(taddr + (ci + 2) * 32, v[(it + 1) & 1]);
+            if constexpr (RD > 1) prefetch_res(ci + 2, rres[(it + 1) % RD]);
+          }
           uint32_t(&vv)[32] = v[it & 1];
           uint32_t(&rr)[16] = rres[it % RD];
           const int gc = col0 + ci * 32;  // first accumulator column of this chunk
-          if (gc < p.N) {
+          if (gc < p.N && !(p.dbg & 1)) {
             const bool full = gc + 32 <= p.N;
             if constexpr (WS) {
               // ---------------- raw fp32 partials
@@ -315,24 +380,19 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             } else if (full) {
               // ---------------- fused epilogue, whole chunk, 256-bit accesses
               float f[32];
-              if (p.bias != nullptr) {
-                uint32_t b0[8], b1[8];
-                ldg_v8(p.bias + gc, b0);
-                ldg_v8(p.bias + gc + 16, b1);
+              {
+                const float4* sp = reinterpret_cast<const float4*>(sb + ci * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float2 x0 = unpack_bf16(b0[j]), x1 = unpack_bf16(b1[j]);
-                  f[2 * j] = fmaf(__uint_as_float(vv[2 * j]), rs, x0.x);
-                  f[2 * j + 1] = fmaf(__uint_as_float(vv[2 * j + 1]), rs, x0.y);
-                  f[16 + 2 * j] = fmaf(__uint_as_float(vv[16 + 2 * j]), rs, x1.x);
-                  f[16 + 2 * j + 1] = fmaf(__uint_as_float(vv[16 + 2 * j + 1]), rs, x1.y);
+                  const float4 bq = sp[j];
+                  f[4 * j] = fmaf(__uint_as_float(vv[4 * j]), rs, bq.x);
+                  f[4 * j + 1] = fmaf(__uint_as_float(vv[4 * j + 1]), rs, bq.y);
+                  f[4 * j + 2] = fmaf(__uint_as_float(vv[4 * j + 2]), rs, bq.z);
+                  f[4 * j + 3] = fmaf(__uint_as_float(vv[4 * j + 3]), rs, bq.w);
                 }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vv[j]) * rs;
               }
               if constexpr ((F & F_RB) != 0) {
-                if (rb != nullptr) {
+                if (rb != nullptr && !rb_staged) {
                   uint32_t b0[8], b1[8];
                   ldg_v8(rb + ci * 32, b0);
                   ldg_v8(rb + ci * 32 + 16, b1);
@@ -381,7 +441,6 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                   for (int j = 0; j < OUTS; ++j) f[j] *= p.alpha;
                 }
-                if (it + RD < MYCH && (NCH % 2 == 0 || ci + 2 * RD < NCH)) prefetch_res(ci + 2 * RD, rres[it % RD]);
               }
               if (orow >= 0) {
                 if (F32C && p.out_fp32) {
@@ -440,9 +499,36 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+// shared memory of a resident-B launch: B slab + A ring + barriers + epilogue bias copies; 0 = does not fit
+template <int BN, int STAGES>
+constexpr int resb_smem(int nkb) {
+  return nkb * BN * BLOCK_K * 2 + STAGES * BLOCK_M * BLOCK_K * 2 + 1024 + 256 + NUM_EPI_WARPS * BN * 4;
+}
+
+template <int BN, int STAGES, int F>
+int launch_v2_resb(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  const int smem = resb_smem<BN, STAGES>(p.num_k_blocks);
+  if (smem > SMEM_LIMIT || p.a_mode != 0 || p.splits != 1) return VB_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  auto kern = gemm_v2_kernel<BN, STAGES, F, true>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
+    attr_set = true;
+  }
+  // whole CTA groups of n_blocks: every CTA owns one n-block, its m-blocks are strided over the groups
+  int groups = vb_num_sms() / p.n_blocks;
+  if (groups < 1) return VB_ERR_UNSUPPORTED;
+  if (groups > p.m_blocks) groups = p.m_blocks;
+  const int grid = groups * p.n_blocks;
+  cudaError_t le = vb_launch(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, p);
+  if (le != cudaSuccess) { vb_set_last_error(le); return VB_ERR_CUDA; }
+  return VB_OK;
+}
+
 template <int BN, int STAGES, int F>
 int launch_v2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 1024 + 256 + NUM_EPI_WARPS * BN * 4;
   static_assert(smem <= SMEM_LIMIT, "smem budget");
   static bool attr_set = false;
   auto kern = gemm_v2_kernel<BN, STAGES, F>;
@@ -453,9 +539,19 @@ int launch_v2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
   }
   const int units = p.m_blocks * p.n_blocks * p.splits;
   const int grid = units < vb_num_sms() ? units : vb_num_sms();
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
-  VB_LAUNCH_CHECK();
+  cudaError_t le = vb_launch(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, p);
+  if (le != cudaSuccess) { vb_set_last_error(le); return VB_ERR_CUDA; }
   return VB_OK;
+}
+
+// resident-B variants exist for the feature sets of the small-K UNet / ViT GEMMs; RSTAGES = A-ring depth next to the B slab
+template <int BN, int RSTAGES>
+int dispatch_v2_resb(int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  if (need == 0) return launch_v2_resb<BN, RSTAGES, 0>(ta, tb, p, stream);
+  if (need == F_RES) return launch_v2_resb<BN, RSTAGES, F_RES>(ta, tb, p, stream);
+  if (need == F_GLU) return launch_v2_resb<BN, RSTAGES, F_GLU>(ta, tb, p, stream);
+  if (need == F_ACT) return launch_v2_resb<BN, RSTAGES, F_ACT>(ta, tb, p, stream);
+  return VB_ERR_UNSUPPORTED;
 }
 
 // variant of tile width BN covering the feature set `need` (F_* mask; F_WS selects the split-K variant)
@@ -473,6 +569,7 @@ int dispatch_v2(int need, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   return launch_v2<BN, STAGES, F_ALL>(ta, tb, p, stream);
 }
 
+int launch_gemm_v2_resb(int bn, int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream);
 int launch_gemm_v2_256(int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream);
 int launch_gemm_v2_160(int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream);
 int launch_gemm_v2_128(int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream);

@@ -58,6 +58,59 @@ def reserve_decode_workspace(max_batch, n_heads, head_dim, device):
     return workspace(need, torch.device(device), "dec")
 
 
+class pdl:
+    """Context manager: launch the vitron_b200 kernels issued inside with programmatic dependent launch (every kernel
+    launched through vb_launch starts with griddepcontrol.launch_dependents / .wait): consecutive kernels of a stream or of
+    a captured CUDA graph overlap launch latency and prologue (barrier init, TMEM allocation) with the predecessor's tail."""
+
+    def __init__(self, enabled=True):
+        self.enabled, self.prev = enabled, None
+
+    def __enter__(self):
+        self.prev = _lib.load().vb200_set_pdl(1 if self.enabled else 0)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().vb200_set_pdl(self.prev)
+        return False
+
+
+class GraphedCall:
+    """Capture `fn(**tensors)` (any composition of the ops below + allocation-only torch calls, no host syncs) in one CUDA graph
+    per input signature and replay it: launch-bound chains (the ~290 kernels of the SEEM mask decoder, ~10 us of host time
+    each) run at device speed. Inputs are copied into static buffers; the RETURNED tensors are static too and are overwritten
+    by the next call with the same signature — consume or clone them first."""
+
+    def __init__(self, fn, warmup=2):
+        self.fn, self.warmup, self.graphs = fn, warmup, {}
+
+    def __call__(self, **tensors):
+        key = tuple((k, tuple(v.shape), v.dtype, v.device.index) for k, v in sorted(tensors.items()))
+        ent = self.graphs.get(key)
+        if ent is None:
+            static = {k: v.detach().clone() for k, v in tensors.items()}
+            dev = next(iter(static.values())).device
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(self.warmup):  # workspaces, cached tables, cudaFuncSetAttribute calls
+                    self.fn(**static)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = launch_count()
+            with torch.cuda.graph(g), pdl(True):
+                out = self.fn(**static)
+            ent = (g, static, out, launch_count() - l0)
+            self.graphs[key] = ent
+        g, static, out, n = ent
+        for k, v in tensors.items():
+            static[k].copy_(v, non_blocking=True)
+        g.replay()
+        count_launches(n)
+        return out
+
+
 def _req(cond, msg):
     if not cond:
         raise ValueError(msg)
@@ -136,6 +189,11 @@ def gemm(a, w, bias=None, act=ACT_NONE, glu=GLU_NONE, residual=None, alpha=1.0, 
 def set_gemm_impl(impl):
     """0 = specialised v2 kernel whenever eligible (default), 1 = generic kernel only; returns the previous setting."""
     return _lib.load().vb200_set_gemm_impl(int(impl))
+
+
+def set_gemm_debug(resident_b=-1, dbg=-1):
+    """Measurement aids (see include/vitron_b200.h); returns the previous packed setting."""
+    return _lib.load().vb200_set_gemm_debug(int(resident_b), int(dbg))
 
 
 def pack_conv_weight(w):
@@ -236,7 +294,7 @@ def groupnorm_nhwc(x, weight, bias, groups, eps, act=ACT_NONE, n=None, out=None)
     check(lib.vb200_groupnorm_nhwc(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), n, spatial, c,
                                    groups, float(eps), int(act), ws.data_ptr(), need, _stream()),
           "vb200_groupnorm_nhwc")
-    _launches[0] += 2
+    _launches[0] += 1
     return out
 
 
@@ -264,10 +322,12 @@ def attention(q, k, v, scale=None, causal=False, kv_len=None, mask=None, out=Non
         m_sb = mask.stride(0) if mask.shape[0] > 1 else 0
         m_sh = mask.stride(1) if mask.shape[1] > 1 else 0
         m_sq = mask.stride(2)
-    check(lib.vb200_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Sq, Skv, D,
-                              *_bsh(q), *_bsh(k), *_bsh(v), *_bsh(out), float(scale), 1 if causal else 0,
-                              _ptr(kv_len), m_ptr, m_sb, m_sh, m_sq, _stream()), "vb200_attention")
-    _launches[0] += 1
+    need = lib.vb200_attention_workspace_size(B, H, Sq, Skv, D, 1 if causal else 0) if kv_len is None else 0
+    ws = workspace(need, q.device, "attn") if need else None
+    check(lib.vb200_attention_ws(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Sq, Skv, D,
+                                 *_bsh(q), *_bsh(k), *_bsh(v), *_bsh(out), float(scale), 1 if causal else 0,
+                                 _ptr(kv_len), m_ptr, m_sb, m_sh, m_sq, _ptr(ws), need, _stream()), "vb200_attention_ws")
+    _launches[0] += 2 if need else 1
     return out
 
 

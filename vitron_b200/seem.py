@@ -295,6 +295,13 @@ class XDecoderHead:
 
     def __init__(self, pixel_decoder, predictor):
         self.pixel_decoder, self.predictor = pixel_decoder, predictor
+        self._graphed = None
+
+    def enable_graph(self, on=True):
+        """Replay the whole head (pixel decoder + 9 decoder layers + 10 prediction heads, ~400 launches) from one CUDA graph
+        per feature-shape signature. The returned tensors are then static buffers, overwritten by the next call."""
+        self._graphed = ops.GraphedCall(lambda **f: self.layers(f)) if on else None
+        return self
 
     def load_state_dict(self, sd, prefix=""):
         self.pixel_decoder.load_state_dict(sd, prefix + "pixel_decoder.")
@@ -302,6 +309,9 @@ class XDecoderHead:
         return self
 
     def forward(self, features, mask=None, target_queries=None, target_vlp=None, task="seg", extra={}):
+        if (self._graphed is not None and not extra and mask is None and target_queries is None and target_vlp is None
+                and task == "seg" and all(torch.is_tensor(v) and v.is_cuda for v in features.values())):
+            return self._graphed(**features)
         return self.layers(features, mask, target_queries, target_vlp, task, extra)
 
     def layers(self, features, mask=None, target_queries=None, target_vlp=None, task="seg", extra={}):

@@ -426,7 +426,7 @@ class GraphedCFGDenoiser:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             l0 = ops.launch_count()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g), ops.pdl(True):
                 self.out = self._eval()
             self.launches = ops.launch_count() - l0
             self.graph = g
@@ -458,7 +458,7 @@ class GraphedBranch:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             l0 = ops.launch_count()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g), ops.pdl(True):
                 self.out = self.unet(self.xt, self.t, **self.cond).float().contiguous()
             self.launches = ops.launch_count() - l0
             self.graph = g
