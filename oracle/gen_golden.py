@@ -145,7 +145,7 @@ def _seem_attn_arch():
     }
 
 
-def build_reference_seem(t=SEEM_TINY, seed=41):
+def build_reference_seem(t=SEEM_TINY, seed=41, prompts=False):
     """The UNMODIFIED TransformerEncoderPixelDecoder + MultiScaleMaskedTransformerDecoder (through the
     detectron2-layer stubs of refshim.setup_seem), seeded weights; returns (pixel_decoder, predictor, sd)."""
     import torch.nn as nn
@@ -170,8 +170,8 @@ def build_reference_seem(t=SEEM_TINY, seed=41):
             return self.logit_scale.exp() * v_emb @ t_emb.unsqueeze(0).transpose(1, 2)
 
     # task switch of configs/seem/seem_focall_lang.yaml:60-86 (MASK, SPATIAL enabled; the rest disabled)
-    task_switch = {"bbox": False, "mask": True, "spatial": True, "grounding": False, "openimage": {"grounding": False, "mask": False},
-                   "visual": False, "audio": False}
+    task_switch = {"bbox": False, "mask": True, "spatial": True, "grounding": prompts, "openimage": {"grounding": False, "mask": False},
+                   "visual": prompts, "audio": prompts}
     md = MD(Lang(), t["C"], True, hidden_dim=t["C"], dim_proj=t["dim_proj"], num_queries=t["Q"], contxt_len=77,
             nheads=t["heads"], dim_feedforward=t["ffn"], dec_layers=t["dec_layers"], pre_norm=False, mask_dim=t["C"],
             task_switch=task_switch, enforce_input_project=False, max_spatial_len=[512, 512, 512, 512],
@@ -205,6 +205,55 @@ def gen_seem(seed=41):
     torch.save(fx, os.path.join(OUT, "seem_tiny.pt"))
     print("seem_tiny.pt", tuple(mf.shape), tuple(out["pred_masks"].shape), float(out["pred_masks"].abs().max()),
           len(out["aux_outputs"]), sorted(out.keys()))
+
+
+def gen_seem_prompts(seed=43):
+    """SEEM mask decoder with INTERACTIVE prompts from the unmodified reference class (seem.py:398-500 +
+    attention_data_struct.py): grounding tokens (text), spatial positive / negative point masks, audio tokens, and the
+    `refimg` -> visual-prompt route. Point counts stay below max_spatial_len, so rand_sample draws nothing."""
+    t = SEEM_TINY
+    pd, md, sd, shapes = build_reference_seem(t, seed, prompts=True)
+    g = torch.Generator().manual_seed(seed)
+    feats = {f"res{i + 2}": torch.randn((1, c, 32 >> i, 40 >> i), generator=g) for i, c in enumerate(t["in_channels"])}
+    t_emb = torch.randn((t["n_text"], t["dim_proj"]), generator=g)
+    t_emb = t_emb / t_emb.norm(dim=-1, keepdim=True)
+    md.lang_encoder.default_text_embeddings.copy_(t_emb)
+    C = t["C"]
+    gtok = torch.randn((5, 1, C), generator=g) * 0.5
+    atok = torch.randn((3, 1, C), generator=g) * 0.5
+    pos_mask = torch.zeros((1, 32, 40), dtype=torch.bool)
+    pos_mask[0, 5:9, 10:14] = True
+    neg_mask = torch.zeros((1, 32, 40), dtype=torch.bool)
+    neg_mask[0, 20:22, 30:33] = True
+    cases = {
+        "grounding": dict(grounding_tokens=gtok, grounding_nonzero_mask=torch.zeros((1, 5), dtype=torch.bool)),
+        "spatial": dict(spatial_query_pos_mask=[pos_mask], spatial_query_neg_mask=[neg_mask]),
+        "grounding+spatial+audio": dict(grounding_tokens=gtok, grounding_nonzero_mask=torch.zeros((1, 5), dtype=torch.bool),
+                                        spatial_query_pos_mask=[pos_mask], spatial_query_neg_mask=[neg_mask],
+                                        audio_tokens=atok, audio_nonzero_mask=torch.zeros((1, 3), dtype=torch.bool)),
+    }
+    keys = ("pred_logits", "pred_masks", "pred_maskembs", "pred_captions", "pred_pspatials", "pred_nspatials", "pred_pvisuals", "pred_nvisuals")
+    outs = {}
+    def switch(**on):   # tasks/interactive.py:53-57: the demo resets the task switches per request, then enables what it uses
+        for k in ("spatial", "visual", "grounding", "audio"):
+            md.task_switch[k] = bool(on.get(k, False))
+    with torch.no_grad():
+        mf, enc, multi = pd.forward_features(feats)
+        for name, extra in cases.items():
+            switch(grounding="grounding_tokens" in extra, spatial="spatial_query_pos_mask" in extra, audio="audio_tokens" in extra)
+            out = md(multi, mf, task="seg", extra=dict(extra))
+            outs[name] = {k: out[k] for k in keys if k in out and out[k] is not None}
+            outs[name]["aux0"] = {k: out["aux_outputs"][0][k] for k in keys if k in out["aux_outputs"][0] and out["aux_outputs"][0][k] is not None}
+        switch(spatial=True, visual=True)
+        ref = md(multi, mf, task="refimg", extra=dict(cases["spatial"]))                # evaluate_referring_image route
+        switch(visual=True)
+        vis_extra = dict(visual_query_pos=ref["visual_query_pos"], visual_query_neg=ref["visual_query_neg"],
+                         src_visual_queries=ref["src_visual_queries"], src_visual_maskings=ref["src_visual_maskings"])
+        out = md(multi, mf, task="seg", extra=dict(vis_extra))
+        outs["visual"] = {k: out[k] for k in keys if k in out and out[k] is not None}
+    fx = dict(seed=seed, cfg=dict(t), shapes=shapes, t_emb=t_emb, mask_features=mf, multi_scale=multi, cases=cases, refimg=ref, out=outs)
+    torch.save(fx, os.path.join(OUT, "seem_prompts_tiny.pt"))
+    print("seem_prompts_tiny.pt", {k: sorted(v.keys()) for k, v in outs.items()})
 
 
 FOCAL_TINY = dict(embed_dim=64, depths=(1, 1, 2, 1), focal_levels=(4, 4, 4, 4), focal_windows=(3, 3, 3, 3), mlp_ratio=4.0,
@@ -303,7 +352,7 @@ def gen_gligen_unet(seed=71):
     print("gligen_unet_tiny.pt", tuple(out.shape), float(out.abs().max()), len(shapes), "tensors")
 
 
-GENERATORS = {"vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen, "seem": gen_seem, "focal": gen_focal, "vae": gen_vae, "gligen_unet": gen_gligen_unet}
+GENERATORS = {"seem_prompts": gen_seem_prompts, "vitron_llm": gen_vitron_llm, "unet": gen_unet, "gligen": gen_gligen, "seem": gen_seem, "focal": gen_focal, "vae": gen_vae, "gligen_unet": gen_gligen_unet}
 
 
 def main(argv):

@@ -396,6 +396,53 @@ def test_gligen_grounded_sample_host_logic(monkeypatch):
     assert img.shape == ref.shape and e_inf < 0.08 and e_l2 < 0.06, (e_inf, e_l2)
 
 
+def test_seem_interactive_prompts_host_logic_against_reference_golden(monkeypatch):
+    """SEEM interactive prompts: grounding / audio token prompts, spatial positive / negative point prompts
+    and the refimg -> visual-prompt route of vitron_b200.seem against golden outputs of the UNMODIFIED reference decoder +
+    AttentionDataStruct (tests/golden/seem_prompts_tiny.pt, oracle/gen_golden.py::gen_seem_prompts); kernels replaced by the
+    torch statements of cpu_ops_emulator."""
+    import os
+    import torch
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200.seem import MultiScaleMaskedTransformerDecoder
+    cpu_ops_emulator.install(monkeypatch)
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "seem_prompts_tiny.pt"), weights_only=False)
+    t = fx["cfg"]
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    pr = MultiScaleMaskedTransformerDecoder(t["C"], t["dim_proj"], t["Q"], t["heads"], t["ffn"], t["dec_layers"], t["C"], device="cpu")
+    pr.load_state_dict(sd, "predictor.")
+    pr.set_text_embeddings(fx["t_emb"], t["logit_scale"])
+    assert pr.mask_sptial_embed is not None and pr.pn_indicator is not None
+
+    def check(out, ref, what):
+        for k, v in ref.items():
+            if k == "aux0":
+                continue
+            assert k in out, (what, k, sorted(out))
+            e_inf, e_l2 = _rel(out[k], v)
+            lim = (0.05, 0.04) if k in ("pred_pspatials", "pred_nspatials", "pred_pvisuals", "pred_nvisuals") else (0.3, 0.09)
+            assert tuple(out[k].shape) == tuple(v.shape) and e_inf < lim[0] and e_l2 < lim[1], (what, k, e_inf, e_l2)
+        for k, v in ref.get("aux0", {}).items():      # first decoder layer: no accumulated mask thresholding
+            e_inf, e_l2 = _rel(out["aux_outputs"][0][k], v)
+            assert e_inf < 0.04 and e_l2 < 0.03, (what, "aux0", k, e_inf, e_l2)
+    for name, extra in fx["cases"].items():
+        out = pr(fx["multi_scale"], fx["mask_features"], task="seg", extra=dict(extra))
+        check(out, fx["out"][name], name)
+    # refimg route (evaluate_referring_image): spatial prompts on a reference image become visual prompts of the target
+    ref = pr(fx["multi_scale"], fx["mask_features"], task="refimg", extra=dict(fx["cases"]["spatial"]))
+    assert sorted(ref) == ["src_visual_maskings", "src_visual_queries", "visual_query_neg", "visual_query_pos"]
+    for k in ("visual_query_pos", "visual_query_neg"):
+        e_inf, e_l2 = _rel(ref[k], fx["refimg"][k])
+        assert e_inf < 0.04 and e_l2 < 0.03, (k, e_inf, e_l2)
+    for a, b in zip(ref["src_visual_queries"], fx["refimg"]["src_visual_queries"]):
+        e_inf, e_l2 = _rel(a, b)
+        assert e_inf < 0.04 and e_l2 < 0.03, ("src_visual_queries", e_inf, e_l2)
+    out = pr(fx["multi_scale"], fx["mask_features"], task="seg",
+             extra={k: fx["refimg"][k] for k in ("visual_query_pos", "visual_query_neg", "src_visual_queries", "src_visual_maskings")})
+    check(out, fx["out"]["visual"], "visual")
+
+
 def test_argument_validation_of_the_widened_entry_points(lib):
     """Error behaviour of the §8(f) entry points without a device: null pointers, misaligned strides, unsupported kernel
     sizes and short workspaces are rejected with VB_ERR_* before any launch."""

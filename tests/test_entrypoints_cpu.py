@@ -68,7 +68,7 @@ def test_missing_injected_objects_fail_loudly():
     with pytest.raises(RuntimeError, match="seem_model"):
         E.inference({"image": torch.zeros((8, 8, 3), dtype=torch.uint8)}, [])
     with pytest.raises(NotImplementedError):
-        E.inference({"image": torch.zeros((8, 8, 3), dtype=torch.uint8)}, ["Stroke"])
+        E.inference({"image": torch.zeros((8, 8, 3), dtype=torch.uint8)}, ["Example"])
     with pytest.raises(RuntimeError, match="i2vgen_pipeline"):
         E.image_to_video("a.png", "a cat")
     assert E.image_to_video(None, "x") == (None, None)          # app.py:322-323

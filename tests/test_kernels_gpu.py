@@ -141,6 +141,86 @@ def test_gemm_v2_feature_matrix(cuda, gemm_impl):
         close(ops.gemm(a, w, bias=bias), ref, 5e-2, 2e-2, "split repeat")
 
 
+@pytest.mark.parametrize("M,N,K", [(40960, 320, 320), (8192, 960, 320), (5000, 640, 192), (4096, 2560, 320), (10240, 640, 640), (4224, 336, 128)])
+def test_gemm_resident_b(cuda, M, N, K):
+    """The small-K 'weight slab stays in shared memory' variant of the v2 kernel (and the same call with it switched off):
+    plain, residual (in place), GEGLU, activation; M with a ragged last tile, N with a ragged last chunk."""
+    from vitron_b200 import ops
+    a, w, bias = rnd((M, K), cuda, 1), rnd((N, K), cuda, 2, 0.05), rnd((N,), cuda, 3)
+    res = rnd((M, N), cuda, 4)
+    ref = a.float() @ w.float().t() + bias.float()
+    for rb in (3, 0):
+        prev = ops.set_gemm_debug(rb, 0)
+        try:
+            close(ops.gemm(a, w, bias=bias), ref, 3e-2 * math.sqrt(K / 64), 1.6e-2, f"resb={rb} plain")
+            close(ops.gemm(a, w, bias=bias, act=4), F.silu(ref), 3e-2 * math.sqrt(K / 64), 1.6e-2, f"resb={rb} act")
+            r2 = res.clone()
+            ops.gemm(a, w, bias=bias, residual=r2, out=r2, alpha=0.5)
+            close(r2, res.float() + 0.5 * ref, 3e-2 * math.sqrt(K / 64), 1.6e-2, f"resb={rb} residual in place")
+            if N % 32 == 0:
+                wa, wb = rnd((N // 2, K), cuda, 5, 0.05), rnd((N // 2, K), cuda, 6, 0.05)
+                out = ops.gemm(a, ops.pack_glu_weight(wa, wb), glu=2)
+                close(out, (a.float() @ wa.float().t()) * F.gelu(a.float() @ wb.float().t()), 4e-2 * math.sqrt(K / 64), 2e-2, f"resb={rb} geglu")
+        finally:
+            ops.set_gemm_debug(prev & 0xff, 0)
+
+
+@pytest.mark.parametrize("M,N,K", [(40960, 320, 320), (8192, 1280, 320), (5000, 640, 192), (4096, 2560, 320), (10240, 640, 640),
+                                   (4224, 336, 128), (4100, 512, 2048)])
+def test_gemm_cluster_pair(cuda, M, N, K):
+    """The cluster-pair variant of the v2 kernel (two CTAs on adjacent n-blocks, each half of the A tile fetched once and
+    multicast into both): plain, activation, residual in place, GEGLU, per-group rowbias; ragged M and N tails."""
+    from vitron_b200 import ops
+    a, w, bias = rnd((M, K), cuda, 1), rnd((N, K), cuda, 2, 0.05), rnd((N,), cuda, 3)
+    res = rnd((M, N), cuda, 4)
+    ref = a.float() @ w.float().t() + bias.float()
+    tol = 3e-2 * math.sqrt(K / 64)
+    prev = ops.set_gemm_debug(4, 0)
+    try:
+        l0 = ops.launch_count()
+        close(ops.gemm(a, w, bias=bias), ref, tol, 1.6e-2, "cluster plain")
+        close(ops.gemm(a, w, bias=bias, act=4), F.silu(ref), tol, 1.6e-2, "cluster act")
+        r2 = res.clone()
+        ops.gemm(a, w, bias=bias, residual=r2, out=r2, alpha=0.5)
+        close(r2, res.float() + 0.5 * ref, tol, 1.6e-2, "cluster residual in place")
+        if N % 32 == 0:
+            wa, wb = rnd((N // 2, K), cuda, 5, 0.05), rnd((N // 2, K), cuda, 6, 0.05)
+            out = ops.gemm(a, ops.pack_glu_weight(wa, wb), glu=2)
+            close(out, (a.float() @ wa.float().t()) * F.gelu(a.float() @ wb.float().t()), 1.4 * tol, 2e-2, "cluster geglu")
+        if M % 64 == 0 and N % 16 == 0:
+            rb = rnd((M // 64, N), cuda, 7)
+            close(ops.gemm(a, w, bias=bias, rowbias=rb, rowbias_rows=64), ref + rb.float().repeat_interleave(64, 0), tol, 1.6e-2,
+                  "cluster rowbias")
+        for _ in range(3):   # back-to-back launches: barrier phases / cluster exit handshake
+            close(ops.gemm(a, w, bias=bias), ref, tol, 1.6e-2, "cluster repeat")
+        assert ops.launch_count() > l0
+    finally:
+        ops.set_gemm_debug(prev & 0xff, 0)
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout,kh,kw,stride", [(16, 40, 64, 320, 320, 3, 3, 1), (16, 20, 32, 640, 1280, 3, 3, 1),
+                                                          (16, 40, 64, 320, 320, 3, 3, 2), (4, 40, 64, 320, 640, 1, 1, 1),
+                                                          (8, 37, 50, 128, 512, 3, 3, 1), (64, 8, 8, 256, 512, 3, 3, 1)])
+def test_conv_cluster_pair(cuda, nb, h, w, cin, cout, kh, kw, stride):
+    """Implicit-GEMM convolution on the cluster-pair kernel: the pixel tile's two halves (split along rows or samples) are
+    fetched by different CTAs; ragged tiles at the image border, stride 2, ResBlock epilogue."""
+    from vitron_b200 import ops
+    x = rnd((nb, h, w, cin), cuda, 1)
+    wt = rnd((cout, cin, kh, kw), cuda, 2, 0.03)
+    bias = rnd((cout,), cuda, 3)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias.float(), stride=stride, padding=(kh // 2, kw // 2)).permute(0, 2, 3, 1)
+    tol = 4e-2 * math.sqrt(cin * kh * kw / 576)
+    prev = ops.set_gemm_debug(4, 0)
+    try:
+        close(ops.conv_nhwc(x, ops.pack_conv_weight(wt), kh, kw, stride=stride, bias=bias), ref, tol, 2e-2, "cluster conv")
+        ho, wo = ref.shape[1], ref.shape[2]
+        rb, res = rnd((nb, cout), cuda, 4), rnd((nb, ho, wo, cout), cuda, 5)
+        out = ops.conv_nhwc(x, ops.pack_conv_weight(wt), kh, kw, stride=stride, bias=bias, rowbias=rb, rowbias_rows=ho * wo, residual=res)
+        close(out, res.float() + ref + rb.float()[:, None, None, :], 1.3 * tol, 2e-2, "cluster conv epilogue")
+    finally:
+        ops.set_gemm_debug(prev & 0xff, 0)
+
+
 def test_gemm_rowbias_strided(cuda, gemm_impl):
     from vitron_b200 import ops
     M, N, K = 640, 320, 256

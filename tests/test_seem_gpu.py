@@ -155,3 +155,36 @@ def test_seem_head_graph_replay_equals_eager(cuda):
             assert (a.float() - b_.float()).abs().max().item() <= 2e-2 * b_.float().abs().max().item(), rep
         outs.append(e_masks)
     assert not torch.equal(outs[0], outs[1])
+
+
+def test_seem_interactive_prompts_vs_reference_golden(cuda):
+    """Grounding / audio token prompts, spatial point prompts and the refimg -> visual route on the B200 kernels against the
+    golden outputs of the UNMODIFIED reference decoder (tests/golden/seem_prompts_tiny.pt): the self-attention over
+    [object queries | prompt tokens] runs as masked attention on the tcgen05 kernel."""
+    import os
+    from oracle.weights import seeded_state_dict
+    from vitron_b200.seem import MultiScaleMaskedTransformerDecoder
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "seem_prompts_tiny.pt"), weights_only=False)
+    t = fx["cfg"]
+    sd = seeded_state_dict(fx["shapes"], fx["seed"])
+    pr = MultiScaleMaskedTransformerDecoder(t["C"], t["dim_proj"], t["Q"], t["heads"], t["ffn"], t["dec_layers"], t["C"], device=cuda)
+    pr.load_state_dict(sd, "predictor.")
+    pr.set_text_embeddings(fx["t_emb"], t["logit_scale"])
+    multi, mf = [m.to(cuda) for m in fx["multi_scale"]], fx["mask_features"].to(cuda)
+    dev = lambda e: {k: ([m.to(cuda) for m in v] if isinstance(v, list) else v.to(cuda)) for k, v in e.items()}
+
+    def check(out, ref, what):
+        for k, v in ref.items():
+            if k == "aux0":
+                continue
+            lim = (0.05, 0.04) if "spatial" in k or "visual" in k else (0.3, 0.09)
+            assert_close(out[k], v, f"{what} {k}", *lim)
+        for k, v in ref.get("aux0", {}).items():
+            assert_close(out["aux_outputs"][0][k], v, f"{what} layer-0 {k}", 0.04, 0.03)
+    for name, extra in fx["cases"].items():
+        check(pr(multi, mf, task="seg", extra=dev(extra)), fx["out"][name], name)
+    ref = pr(multi, mf, task="refimg", extra=dev(fx["cases"]["spatial"]))
+    for k in ("visual_query_pos", "visual_query_neg"):
+        assert_close(ref[k], fx["refimg"][k], k, 0.04, 0.03)
+    vis = {k: ref[k] for k in ("visual_query_pos", "visual_query_neg", "src_visual_queries", "src_visual_maskings")}
+    check(pr(multi, mf, task="seg", extra=vis), fx["out"]["visual"], "visual")

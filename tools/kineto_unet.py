@@ -31,6 +31,9 @@ with torch.no_grad():
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
     from vitron_b200 import ops
+    for a_ in sys.argv:
+        if a_.startswith("rb="):
+            ops.set_gemm_debug(int(a_[3:]), 0)
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph), ops.pdl("nopdl" not in sys.argv):
         out = unet(x, t, **kw)

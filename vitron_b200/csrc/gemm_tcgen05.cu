@@ -667,6 +667,7 @@ static int validate_epi(const vb_epilogue* e, long long N) {
 // ------------------------------------------------------------------ v2 planning
 static int g_gemm_impl = 0;  // 0: v2 whenever eligible, 1: generic kernel only (A/B measurements, parity tests of both)
 static int g_gemm_resb = 1;  // resident-B variant: bit 0 = K <= 320 (5 k-blocks), bit 1 = also K <= 640 at BN = 128; 0 = off
+                             // bit 2: cluster-pair variant (A tile multicast to two CTAs working on adjacent n-blocks)
 static int g_gemm_dbg = 0;   // GemmParams.dbg of the v2 launches (measurement aid)
 int resb_smem_bytes(int bn, int nkb);  // gemm_v2_resb.cu
 
@@ -691,6 +692,27 @@ static int resb_tile(long long M, long long N, int nkb, int need) {
     const float mma = static_cast<float>(bn) / 256.f, astream = bn == 160 ? 0.55f : 0.9f;
     const float cost = static_cast<float>(per_cta) * nkb * (mma > astream ? mma : astream);
     if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+// Tile width of the cluster-pair variant (even number of n-blocks required), or 0 when it does not apply.
+static int cl_tile(long long mb, long long N, int nkb, int need) {
+  if (!(g_gemm_resb & 4)) return 0;
+  if (need != 0 && need != F_RES && need != F_GLU && need != F_ACT && need != F_RB && need != (F_RB | F_RES)) return 0;
+  if (mb < 32) return 0;
+  const int cands[3] = {256, 160, 128};
+  const float tk[3] = {1.0f, 0.66f, 0.56f};    // A crosses the fabric once per pair: narrow tiles approach their MMA time
+  int best = 0;
+  float best_t = 1e30f;
+  const int clusters = vb_num_sms() / 2;
+  for (int i = 0; i < 3; ++i) {
+    const long long nb = (N + cands[i] - 1) / cands[i];
+    if (nb & 1) continue;
+    const long long units = mb * (nb / 2);
+    const long long waves = (units + clusters - 1) / clusters;
+    const float t = static_cast<float>(waves) * (nkb * tk[i] + 2.0f * cands[i] / 256.f);
+    if (t < best_t - 1e-4f) { best_t = t; best = cands[i]; }
   }
   return best;
 }
@@ -902,6 +924,20 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   p.m_blocks = static_cast<int>((M + BLOCK_M - 1) / BLOCK_M);
   if (v2_eligible(epi, out, ldo, N)) {
     p.dbg = g_gemm_dbg;
+    if (const int cbn = cl_tile(p.m_blocks, N, p.num_k_blocks, v2_need(epi, 1))) {
+      p.n_blocks = static_cast<int>((N + cbn - 1) / cbn);
+      p.splits = 1;
+      uint64_t dA[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+      uint64_t sA[1] = {static_cast<uint64_t>(lda) * 2};
+      uint32_t bA[2] = {BLOCK_K, BLOCK_M / 2};   // each CTA of the pair loads (and multicasts) half of the A tile
+      if (int r = make_tmap(&ta, A, 2, dA, sA, bA, estr2)) return r;
+      uint64_t dB[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+      uint64_t sB[1] = {static_cast<uint64_t>(ldw) * 2};
+      uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(cbn)};
+      if (int r = make_tmap(&tb, W, 2, dB, sB, bB, estr2)) return r;
+      const int r = launch_gemm_v2_cl(cbn, v2_need(epi, 1), ta, tb, p, stream);
+      if (r != VB_ERR_UNSUPPORTED) return r;
+    }
     if (const int rbn = resb_tile(M, N, p.num_k_blocks, v2_need(epi, 1))) {
       p.n_blocks = static_cast<int>((N + rbn - 1) / rbn);
       p.splits = 1;
@@ -1059,6 +1095,16 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
   } else {
     bn = pick_block_n(static_cast<long long>(p.m_blocks) * BLOCK_M, cout, epi->glu);
   }
+  // cluster pair: the A pixel tile splits into two contiguous halves along its outermost extent (samples, else rows)
+  int cl_bn = 0, box_h = th, box_n = tn;
+  if (v2 && p.splits == 1 && ((tw * th * tn) % 16) == 0 && ((tn % 2) == 0 || (tn == 1 && (th % 2) == 0))) {
+    cl_bn = cl_tile(p.m_blocks, cout, p.num_k_blocks, v2_need(epi, 1));
+    if (cl_bn) {
+      bn = cl_bn;
+      if ((tn % 2) == 0) { box_n = tn / 2; p.half_dn = tn / 2; }
+      else { box_h = th / 2; p.half_dh = (th / 2) * stride; }
+    }
+  }
   p.n_blocks = static_cast<int>((cout + bn - 1) / bn);
 
   CUtensorMap ta, tb;
@@ -1068,7 +1114,7 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
                     static_cast<uint64_t>(cin) * w * h * 2};
   // box extents are in traversed global elements: (tw-1)*stride+1 columns yield tw samples
   uint32_t bA[4] = {BLOCK_K, static_cast<uint32_t>((tw - 1) * stride + 1),
-                    static_cast<uint32_t>((th - 1) * stride + 1), static_cast<uint32_t>(tn)};
+                    static_cast<uint32_t>((box_h - 1) * stride + 1), static_cast<uint32_t>(box_n)};
   uint32_t eA[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
   if (int r = make_tmap(&ta, X, 4, dA, sA, bA, eA)) return r;
   uint64_t dB[2] = {static_cast<uint64_t>(kh) * kw * cin_pad, static_cast<uint64_t>(cout)};
@@ -1076,6 +1122,10 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
   uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
   const uint32_t estr2[2] = {1, 1};
   if (int r = make_tmap(&tb, Wt, 2, dB, sB, bB, estr2)) return r;
+  if (cl_bn) {
+    p.dbg = g_gemm_dbg;
+    return launch_gemm_v2_cl(bn, v2_need(epi, 1), ta, tb, p, stream);
+  }
   if (v2) return launch_gemm_v2(bn, v2_need(epi, p.splits), ta, tb, p, stream);
   CUtensorMap tc = tb;
   p.c_box = c_box_for(bn, epi->glu, epi->out_fp32, p.ldo, out);

@@ -87,7 +87,13 @@ static __device__ __noinline__ void epi_ragged(const uint32_t* acc, int n_valid,
 // memory for its whole life and works on m-tiles of that n-block only; the ring then carries A alone. Without it every
 // 128 x BN tile re-fetches its B tile from L2: at K = 320 the level-0 UNet GEMMs moved 184 KB per tile for 0.85 us of MMA —
 // 8.6 TB/s of L2 -> SM traffic, L2-bandwidth bound (in-situ 16.7 us for M 40960, N = K = 320 against ~4 us of MMA).
-template <int BLOCK_N, int STAGES, int F, bool RESB = false>
+// CL ("cluster pair"): two CTAs of a thread-block cluster work on the SAME m-block and ADJACENT n-blocks (2j, 2j + 1). Each
+// loads one half of the A tile of every k-step and the TMA unit MULTICASTS it into both CTAs' shared memory, so the large
+// streamed operand crosses the L2 -> SM fabric once per pair instead of once per CTA (measured: the main loop of the
+// small-K UNet GEMMs runs at a constant ~5.5 TB/s of A traffic, A being re-read once per n-block). A ring slot may be
+// refilled when BOTH CTAs' MMAs have retired it: tcgen05.commit arrives on the slot's empty barrier of both CTAs
+// (UTCBAR.MULTICAST); the barriers expect two arrivals.
+template <int BLOCK_N, int STAGES, int F, bool RESB = false, bool CL = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
@@ -136,7 +142,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_b);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL ? 2 : 1);
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -153,18 +159,36 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  uint32_t crank = 0;
+  if constexpr (CL) {
+    cluster_sync_all();   // the peer's barriers exist before anything is multicast into / arrives on them
+    crank = cluster_ctarank();
+  }
   pdl_wait();
 
   // work units of this CTA: (m-block, n-block, split) in grouped raster order, or — RESB — the m-blocks
   // m = blockIdx.x / n_blocks, += gridDim.x / n_blocks of the ONE n-block blockIdx.x % n_blocks (grid is a multiple of n_blocks)
-  const int total_units = RESB ? p.m_blocks : p.m_blocks * p.n_blocks * p.splits;
-  const int unit_first = RESB ? static_cast<int>(blockIdx.x) / p.n_blocks : static_cast<int>(blockIdx.x);
-  const int unit_step = RESB ? static_cast<int>(gridDim.x) / p.n_blocks : static_cast<int>(gridDim.x);
+  const int total_units = RESB ? p.m_blocks : CL ? p.m_blocks * (p.n_blocks >> 1) : p.m_blocks * p.n_blocks * p.splits;
+  const int unit_first = RESB ? static_cast<int>(blockIdx.x) / p.n_blocks : CL ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_step = RESB ? static_cast<int>(gridDim.x) / p.n_blocks : CL ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int my_n_blk = RESB ? static_cast<int>(blockIdx.x) % p.n_blocks : 0;
   auto work_of = [&](int unit) {
     if constexpr (RESB) {
       TileCoord t;
       t.m_blk = unit; t.n_blk = my_n_blk; t.split = 0;
+      return t;
+    } else if constexpr (CL) {
+      // grouped raster over (m-block, n-PAIR); this CTA takes n-block 2 * pair + rank
+      TileCoord t;
+      const int npairs = p.n_blocks >> 1;
+      const int per_group = 16 * npairs;
+      const int group = unit / per_group;
+      const int first_m = group * 16;
+      const int gsize = min(p.m_blocks - first_m, 16);
+      const int in_group = unit - group * per_group;
+      t.m_blk = first_m + in_group % gsize;
+      t.n_blk = 2 * (in_group / gsize) + static_cast<int>(crank);
+      t.split = 0;
       return t;
     } else {
       return decode_work(p, unit);
@@ -196,11 +220,24 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           cn = tin * p.tn;
         }
         for (int kb = k0; kb < k1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if constexpr (CL) mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+          else mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes + (RESB ? 0 : B_BYTES));
-          if (p.a_mode == 0) {
+          if constexpr (CL) {
+            // this CTA's half of the A tile, multicast to both CTAs of the pair (tmap_a's box is the half tile)
+            uint8_t* dst = sa + crank * (p.a_box_bytes >> 1);
+            if (p.a_mode == 0) {
+              tma_load_2d_mc(dst, &tmap_a, &full_bar[stage], kb * BLOCK_K, t.m_blk * BLOCK_M + static_cast<int>(crank) * (BLOCK_M / 2), 3);
+            } else {
+              int tap = kb / p.cin_chunks;
+              int cc = kb - tap * p.cin_chunks;
+              int dy = tap / p.kw, dx = tap - dy * p.kw;
+              tma_load_4d_mc(dst, &tmap_a, &full_bar[stage], cc * BLOCK_K, cw + dx, ch + dy + static_cast<int>(crank) * p.half_dh,
+                             cn + static_cast<int>(crank) * p.half_dn, 3);
+            }
+          } else if (p.a_mode == 0) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, t.m_blk * BLOCK_M);
           } else {
             int tap = kb / p.cin_chunks;
@@ -231,7 +268,8 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
       for (int kb = k0; kb < k1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        if constexpr (CL) mbar_wait_bounded(&full_bar[stage], phase);
+        else mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -241,7 +279,8 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
-          tc_commit(&empty_bar[stage]);
+          if constexpr (CL) tc_commit_mc(&empty_bar[stage], 3);   // both CTAs of the pair wrote into this slot
+          else tc_commit(&empty_bar[stage]);
           if (kb == k1 - 1) tc_commit(&tmem_full[acc]);
         }
         __syncwarp();
@@ -343,7 +382,8 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       };
 
       if (NCH % 2 == 0 || ehalf < NCH) prefetch_res(ehalf, rres[0]);
-      mbar_wait(&tmem_full[acc], acc_phase);
+      if constexpr (CL) mbar_wait_bounded(&tmem_full[acc], acc_phase);
+      else mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (NCH % 2 == 0 || ehalf < NCH) tmem_ld_32x32(taddr + ehalf * 32, v[0]);
 #pragma unroll
@@ -493,6 +533,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -524,6 +565,62 @@ int launch_v2_resb(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   cudaError_t le = vb_launch(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, p);
   if (le != cudaSuccess) { vb_set_last_error(le); return VB_ERR_CUDA; }
   return VB_OK;
+}
+
+// cluster-pair launch: grid = 2 x clusters (<= SM count), cluster dimension 2, PDL attribute when enabled
+template <int BN, int STAGES, int F>
+int launch_v2_cl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 1024 + 256 + NUM_EPI_WARPS * BN * 4;
+  static_assert(smem <= SMEM_LIMIT, "smem budget");
+  if ((p.n_blocks & 1) || p.splits != 1) return VB_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  static int max_clusters = 0;
+  auto kern = gemm_v2_kernel<BN, STAGES, F, false, true>;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
+    // co-resident pairs (a GPC with an odd number of usable SMs leaves one without a partner)
+    cfg.gridDim = dim3(2 * (vb_num_sms() / 2));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = vb_num_sms() / 2; }
+    max_clusters = n < vb_num_sms() / 2 ? n : vb_num_sms() / 2;
+    attr_set = true;
+  }
+  const int units = p.m_blocks * (p.n_blocks >> 1);
+  int clusters = max_clusters;
+  if (clusters > units) clusters = units;
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = vb_pdl_enabled() ? 2 : 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  if (le != cudaSuccess) { vb_set_last_error(le); return VB_ERR_CUDA; }
+  return VB_OK;
+}
+
+template <int BN, int STAGES>
+int dispatch_v2_cl(int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  if (need == 0) return launch_v2_cl<BN, STAGES, 0>(ta, tb, p, stream);
+  if (need == F_RES) return launch_v2_cl<BN, STAGES, F_RES>(ta, tb, p, stream);
+  if (need == F_GLU) return launch_v2_cl<BN, STAGES, F_GLU>(ta, tb, p, stream);
+  if (need == F_ACT) return launch_v2_cl<BN, STAGES, F_ACT>(ta, tb, p, stream);
+  if (need == F_RB) return launch_v2_cl<BN, STAGES, F_RB>(ta, tb, p, stream);
+  if (need == (F_RB | F_RES)) return launch_v2_cl<BN, STAGES, F_RB | F_RES>(ta, tb, p, stream);
+  return VB_ERR_UNSUPPORTED;
 }
 
 template <int BN, int STAGES, int F>
@@ -569,6 +666,7 @@ int dispatch_v2(int need, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   return launch_v2<BN, STAGES, F_ALL>(ta, tb, p, stream);
 }
 
+int launch_gemm_v2_cl(int bn, int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream);
 int launch_gemm_v2_resb(int bn, int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream);
 int launch_gemm_v2_256(int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream);
 int launch_gemm_v2_160(int need, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream);

@@ -210,22 +210,41 @@ def generate(task, language_instruction, grounding_texts, sketch_pad, alpha_samp
 def inference(image, task, *args, **kwargs):
     """modules/SEEM/demo_code/app.py:79-87 -> tasks/interactive.py:35: `image` is the widget dict {'image': HWC uint8, 'mask': ...}
     (already resized: the reference's PIL Resize(512, BICUBIC) is host-side), `task` the list of task names. Implemented: the
-    prompt-free branch (`[]` / `['Panoptic']`: backbone -> pixel decoder -> mask decoder with task 'seg'). The interactive
-    prompts ('Stroke', 'Text', 'Example', 'Audio', video) need the spatial / grounding / visual / audio `extra` queries of
-    seem.py:398-500 and raise NotImplementedError. Returns the predictor's output dict (pred_logits, pred_masks, ...); the
-    reference's visualiser (detectron2) is out of scope."""
+    prompt-free branch (`[]` / `['Panoptic']`) and the 'Stroke' (spatial), 'Text' (grounding) and 'Audio' prompts of
+    seem.py:398-500 through `extra` (the text / audio encoders are injected: their towers are outside §8). Returns the
+    predictor's output dict (pred_logits, pred_masks, pred_captions, pred_pspatials ...); the reference's visualiser
+    (detectron2) is out of scope."""
     tasks = list(task) if task is not None else []
-    if any(t for t in tasks if t != "Panoptic") or "Video" in " ".join(tasks):
-        raise NotImplementedError(f"SEEM interactive task(s) {tasks}: only the prompt-free panoptic branch is built (SURVEY.md §8f)")
+    unsupported = [t for t in tasks if t not in ("Panoptic", "Stroke", "Text", "Audio")]
+    if unsupported:
+        raise NotImplementedError(f"SEEM task(s) {unsupported}: 'Example' (reference image) goes through predictor(task='refimg') "
+                                  "directly; video tracking is host-side glue over the same head")
     head = _need("seem_model", "XDecoderHead (pixel decoder + mask decoder)")
     backbone = _need("seem_backbone", "D2FocalNet backbone")
     img = image["image"] if isinstance(image, dict) else image
     img = img if torch.is_tensor(img) else torch.from_numpy(np.asarray(img))
-    pix = img.permute(2, 0, 1)[None].float().to(head.predictor.device if hasattr(head, "predictor") else "cuda")
+    dev = head.predictor.device if hasattr(head, "predictor") else torch.device("cuda")
+    pix = img.permute(2, 0, 1)[None].float().to(dev)
     mean = torch.tensor([123.675, 116.280, 103.530], device=pix.device).view(1, 3, 1, 1)   # seem_focall_lang.yaml INPUT.PIXEL_MEAN/STD
     std = torch.tensor([58.395, 57.120, 57.375], device=pix.device).view(1, 3, 1, 1)
     feats = backbone((pix - mean) / std)
-    return head(feats)
+    extra = {}
+    if "Stroke" in tasks:                                       # interactive.py:96-104: the sketch mask is the positive prompt
+        m = image["mask"]
+        m = m if torch.is_tensor(m) else torch.from_numpy(np.asarray(m))
+        m = (m[..., 0] if m.ndim == 3 else m)[None, None].float()
+        m = torch.nn.functional.interpolate(m, (pix.shape[2], pix.shape[3]), mode="bilinear") > 0
+        extra["spatial_query_pos_mask"] = [m[0].to(dev)]
+        extra["spatial_query_neg_mask"] = [torch.zeros_like(m[0]).to(dev)]
+    if "Text" in tasks:                                         # interactive.py:106-114: grounding tokens from the language encoder
+        enc = _need("seem_text_encoder", "callable(list[str]) -> (tokens [T, 1, C], nonzero_mask [1, T]) of the SEEM language encoder")
+        tok, nz = enc([kwargs.get("reftxt") if "reftxt" in kwargs else (args[1] if len(args) > 1 else "")])
+        extra["grounding_tokens"], extra["grounding_nonzero_mask"] = tok, nz
+    if "Audio" in tasks:
+        enc = _need("seem_audio_encoder", "callable(audio path) -> (tokens [T, 1, C], nonzero_mask [1, T]) (whisper + language encoder)")
+        tok, nz = enc(kwargs.get("audio_pth") if "audio_pth" in kwargs else (args[2] if len(args) > 2 else None))
+        extra["audio_tokens"], extra["audio_nonzero_mask"] = tok, nz
+    return head(feats, extra=extra)
 
 
 # =========================================================================================== i2vgen-xl

@@ -159,7 +159,7 @@ class TransformerEncoderPixelDecoder:
 
 class MultiScaleMaskedTransformerDecoder:
     def __init__(self, hidden_dim=512, dim_proj=512, num_queries=101, nheads=8, dim_feedforward=2048, dec_layers=9,
-                 mask_dim=512, device="cuda"):
+                 mask_dim=512, device="cuda", task_switch=None, max_spatial_len=(512, 512, 512, 512)):
         self.hidden_dim, self.dim_proj, self.num_queries = hidden_dim, dim_proj, num_queries
         self.num_heads, self.num_layers, self.mask_dim = nheads, dec_layers, mask_dim
         self.num_feature_levels = 3
@@ -167,6 +167,12 @@ class MultiScaleMaskedTransformerDecoder:
         self.text_embeddings = None
         self.logit_scale = 0.0
         self._pos = {}
+        # seem_focall_lang.yaml:60-86 enables MASK / SPATIAL / GROUNDING / VISUAL / AUDIO for the demo model
+        self.task_switch = dict(mask=True, spatial=True, grounding=True, visual=True, audio=True)
+        self.task_switch.update(task_switch or {})
+        self.max_spatial_len = list(max_spatial_len)
+        self.mask_sptial_embed = None   # (sic) seem.py:342
+        self.pn_indicator = None
 
     def set_text_embeddings(self, t_emb, logit_scale):
         """Stand-in for lang_encoder.default_text_embeddings / logit_scale (vlpencoder.py:293-299)."""
@@ -190,6 +196,9 @@ class MultiScaleMaskedTransformerDecoder:
         self.query_feat, self.query_embed, self.level_embed = g("query_feat.weight"), g("query_embed.weight"), g("level_embed.weight")
         self.mask_embed = [(g(f"mask_embed.layers.{i}.weight"), g(f"mask_embed.layers.{i}.bias")) for i in range(3)]
         self.class_embed_t = g("class_embed").t().contiguous()  # [dim_proj, hidden] as a GEMM weight
+        if prefix + "mask_sptial_embed.0" in sd:                  # spatial prompts (seem.py:342-347, 312)
+            self.mask_sptial_embed = [g(f"mask_sptial_embed.{i}").t().contiguous() for i in range(3)]   # x @ E == gemm(x, E^T)
+            self.pn_indicator = sd[prefix + "pn_indicator.weight"].detach().to(device=dev, dtype=torch.float32)
         # grouped K / V projection weights per feature level (level l feeds layers l, l+3, l+6)
         self.kgrp, self.vgrp = [], []
         for lvl in range(self.num_feature_levels):
@@ -229,22 +238,112 @@ class MultiScaleMaskedTransformerDecoder:
         return dict(attn_mask=attn_mask, predictions_class=outputs_class, predictions_mask=outputs_mask,
                     predictions_caption=class_embed.view(bs, Q, -1), predictions_maskemb=me.view(bs, Q, -1))
 
+    # ------------------------------------------------------------------ interactive prompts (seem.py:398-500)
+    @staticmethod
+    def _rand_sample(x, max_len):
+        """utils.py:11-16 (same RNG call, so a seeded torch generator reproduces the reference's subset)."""
+        if x.shape[1] <= max_len:
+            return x
+        return x[:, torch.randperm(x.shape[1])[:max_len]]
+
+    @staticmethod
+    def _point_sample(inp, coords):
+        """detectron2 point_rend.point_sample(input [N,C,H,W], coords [N,P,2] in [0,1], align_corners=True) -> [N,C,P]."""
+        return F.grid_sample(inp, 2.0 * coords.unsqueeze(2) - 1.0, align_corners=True).squeeze(3)
+
+    def _spatial_prompts(self, extra, mask_features_nchw, src_rows, size_list, bs, task):
+        """Spatial-query pre-processing (seem.py:414-469): sampled positive / negative points -> mean-pooled mask-feature
+        queries (reported as pred_pspatials / pred_nspatials) and, per feature level, point-sampled tokens of
+        src @ mask_sptial_embed[level] + pn_indicator with their padding masks. Index / gather work in torch on the device."""
+        if self.mask_sptial_embed is None:
+            raise ValueError("spatial prompts need mask_sptial_embed / pn_indicator in the state dict")
+        dev = self.device
+        pos_masks, neg_masks = extra["spatial_query_pos_mask"], extra["spatial_query_neg_mask"]
+        _, h, w = pos_masks[0].shape
+        divisor = torch.tensor([h, w], device=dev)[None, ]
+        pad = torch.nn.utils.rnn.pad_sequence
+        mf = mask_features_nchw.float()
+
+        def mean_query(masks):
+            pts = [self._rand_sample((m.to(dev).nonzero()[:, 1:] / divisor).t(), self.max_spatial_len[-1]).t() for m in masks]
+            pts = pad(pts, padding_value=-1).permute(1, 0, 2)
+            dead = pts.sum(dim=-1) < 0
+            q = self._point_sample(mf, pts.flip(dims=(2,)).type(mf.dtype))
+            return torch.stack([xx[m].mean(dim=0, keepdim=True) for xx, m in zip(q.transpose(1, 2), ~dead)]).transpose(0, 1).nan_to_num()
+        spatial_query_pos, spatial_query_neg = mean_query(pos_masks), mean_query(neg_masks)
+        tokens, maskings = [], []
+        for i in range(self.num_feature_levels):
+            hi, wi = size_list[i]
+            feat = ops.gemm(src_rows[i], self.mask_sptial_embed[i]).view(bs, hi, wi, -1).permute(0, 3, 1, 2).float()   # [bs,C,h,w]
+            ppos = [self._rand_sample((m.to(dev).nonzero()[:, 1:] / divisor).t(), self.max_spatial_len[i]).t() for m in pos_masks]
+            pneg = [self._rand_sample((m.to(dev).nonzero()[:, 1:] / divisor).t(), self.max_spatial_len[i]).t() for m in neg_masks]
+            pts = [torch.cat([a, b_], dim=0) for a, b_ in zip(ppos, pneg)]
+            ind = pad([torch.cat([torch.ones(a.shape[0], device=dev), -torch.ones(b_.shape[0], device=dev)]) for a, b_ in zip(ppos, pneg)],
+                      padding_value=0)                                                   # [P, bs]
+            pts = pad(pts, padding_value=-1).permute(1, 0, 2)
+            dead = pts.sum(dim=-1) < 0
+            pts[dead] = 0
+            tok = self._point_sample(feat, pts.flip(dims=(2,)).type(feat.dtype)).permute(2, 0, 1)   # [P, bs, C]
+            tok[ind == 1] += self.pn_indicator[0:1]
+            tok[ind == -1] += self.pn_indicator[1:2]
+            tokens.append(tok)
+            maskings.append(dead)
+        return spatial_query_pos, spatial_query_neg, tokens, maskings
+
+    def _self_attn_mask(self, Q, groups, bs):
+        """AttentionDataStruct.self_attn (attention_data_struct.py:173-225) for the shipped ATTENTION_ARCH
+        (seem_focall_lang.yaml:114-139): queries_object sees itself and every token group; tokens_grounding / tokens_audio see
+        queries_object and themselves; tokens_spatial / tokens_visual only themselves; padded tokens are masked both ways.
+        groups: [(name, T, masking [bs, T] bool or None)]. Returns uint8 [bs, 1, L, L], 1 = masked."""
+        L = Q + sum(t for _, t, _ in groups)
+        m = torch.ones((bs, L, L), dtype=torch.bool, device=self.device)
+        m[:, :Q, :Q] = False
+        off = Q
+        spans = {}
+        for name, T, _ in groups:
+            spans[name] = (off, off + T)
+            off += T
+        for name, T, masking in groups:
+            a, b_ = spans[name]
+            m[:, :Q, a:b_] = False                          # queries_object -> tokens_*
+            m[:, a:b_, a:b_] = False                        # tokens_* -> itself
+            if name in ("tokens_grounding", "tokens_audio"):
+                m[:, a:b_, :Q] = False                      # -> queries_object
+        for name, T, masking in groups:                      # MASKING: padded tokens (bi-directional inside the group,
+            if masking is None:                              # uni-directional against the object queries)
+                continue
+            a, b_ = spans[name]
+            mk = masking.to(self.device).bool()
+            blk = m[:, a:b_, a:b_]
+            blk[mk] = True
+            blk.transpose(1, 2)[mk] = True
+            m[:, :Q, a:b_].transpose(1, 2)[mk] = True        # pair [queries_object, tokens_*]: key2 in masking -> its columns
+            if name in ("tokens_grounding", "tokens_audio"):
+                m[:, a:b_, :Q][mk] = True                    # pair [tokens_*, queries_object]: key1 in masking -> its rows
+        return m.unsqueeze(1).to(torch.uint8).contiguous()
+
     @torch.no_grad()
     def forward(self, x, mask_features, mask=None, target_queries=None, target_vlp=None, task="seg", extra={}):
-        if extra:
-            raise NotImplementedError("interactive prompts (spatial / grounding / visual / audio) are not on the BASELINE path")
+        extra = extra or {}
+        spatial_flag = ("spatial_query_pos_mask" in extra or task == "refimg") and self.task_switch.get("spatial", False)
+        grounding_flag = "grounding_tokens" in extra and self.task_switch.get("grounding", False)
+        visual_flag = "visual_query_pos" in extra and self.task_switch.get("visual", False)
+        audio_flag = "audio_tokens" in extra and self.task_switch.get("audio", False)
+        if "prev_mask" in extra:
+            raise NotImplementedError("spatial memories (prev_mask) are not part of the shipped ATTENTION_ARCH's cross attention")
         assert len(x) == self.num_feature_levels
         Q, C, H = self.num_queries, self.hidden_dim, self.num_heads
         hd = C // H
         bs = x[0].shape[0]
         dev = self.device
         # prepare_features: src = feat + level_embed (V input), src + pos (K input); rows are (b, hw)
-        size_list, kproj, vproj = [], {}, {}
+        size_list, kproj, vproj, src_rows = [], {}, {}, []
         for lvl in range(self.num_feature_levels):
             f = _nhwc(x[lvl].to(dev))
             n, h, w, c = f.shape
             size_list.append((h, w))
             src = ops.add(f.view(n * h * w, c), self.level_embed[lvl].contiguous())
+            src_rows.append(src)
             kin = ops.add(src, self._pe(h, w))
             ids, wk, bk = self.kgrp[lvl]
             kall = ops.gemm(kin, wk, bias=bk).view(n, h * w, len(ids), H, hd)
@@ -258,6 +357,28 @@ class MultiScaleMaskedTransformerDecoder:
 
         output = self.query_feat.unsqueeze(0).repeat(bs, 1, 1).view(bs * Q, C).contiguous()
         qpos = self.query_embed.unsqueeze(0).repeat(bs, 1, 1).view(bs * Q, C).contiguous()
+
+        # ---- prompts: token groups that join the self-attention (carried groups keep their updated value across layers)
+        bt = lambda t: t.to(dev).permute(1, 0, 2).to(BF16).contiguous()          # [T, bs, C] -> [bs, T, C]
+        carried = []                                                              # [name, value [bs,T,C], pos [bs,T,C], masking]
+        if grounding_flag:
+            carried.append(["tokens_grounding", bt(extra["grounding_tokens"]), bt(extra["grounding_tokens"]),
+                            extra.get("grounding_nonzero_mask")])
+        if audio_flag:
+            carried.append(["tokens_audio", bt(extra["audio_tokens"]), bt(extra["audio_tokens"]), extra.get("audio_nonzero_mask")])
+        spatial_query_pos = spatial_query_neg = None
+        src_spatial_queries = src_spatial_maskings = None
+        if spatial_flag:
+            spatial_query_pos, spatial_query_neg, src_spatial_queries, src_spatial_maskings = self._spatial_prompts(
+                extra, mask_features.to(dev), src_rows, size_list, bs, task)
+            if "refimg" in task:                                                  # seem.py:459-465
+                return dict(visual_query_pos=spatial_query_pos, visual_query_neg=spatial_query_neg,
+                            src_visual_queries=src_spatial_queries, src_visual_maskings=src_spatial_maskings)
+        visual_query_pos = visual_query_neg = None
+        if visual_flag:
+            visual_query_pos, visual_query_neg = extra["visual_query_pos"], extra["visual_query_neg"]
+        has_prompts = bool(carried) or spatial_flag or visual_flag
+
         results = [self._heads(output, mask_rows, mask_hw, size_list[0], bs)]
         for i in range(self.num_layers):
             lvl = i % self.num_feature_levels
@@ -267,22 +388,67 @@ class MultiScaleMaskedTransformerDecoder:
             att = ops.attention(q, kproj[i], vproj[i], scale=hd ** -0.5, mask=results[-1]["attn_mask"])
             ops.gemm(att.view(bs * Q, C), a.wo, bias=a.bo, residual=output, out=output)
             ops.layernorm(output, *self.cross[i]["n"], 1e-5, out=output)
-            # self attention among the object queries (mask all-False for task 'seg')
             a = self.selfa[i]["att"]
-            qk = ops.gemm(ops.add(output, qpos), a.wqk, bias=a.bqk).view(bs, Q, 2, H, hd)
-            v = ops.gemm(output, a.wv, bias=a.bv).view(bs, Q, H, hd)
-            att = ops.attention(qk[:, :, 0], qk[:, :, 1], v, scale=hd ** -0.5)
-            ops.gemm(att.view(bs * Q, C), a.wo, bias=a.bo, residual=output, out=output)
-            ops.layernorm(output, *self.selfa[i]["n"], 1e-5, out=output)
-            # FFN
-            f1 = ops.gemm(output, self.ffn[i]["l1"][0], bias=self.ffn[i]["l1"][1], act=ops.ACT_RELU)
-            ops.gemm(f1, self.ffn[i]["l2"][0], bias=self.ffn[i]["l2"][1], residual=output, out=output)
-            ops.layernorm(output, *self.ffn[i]["n"], 1e-5, out=output)
+            if not has_prompts:
+                # self attention among the object queries (mask all-False for task 'seg')
+                qk = ops.gemm(ops.add(output, qpos), a.wqk, bias=a.bqk).view(bs, Q, 2, H, hd)
+                v = ops.gemm(output, a.wv, bias=a.bv).view(bs, Q, H, hd)
+                att = ops.attention(qk[:, :, 0], qk[:, :, 1], v, scale=hd ** -0.5)
+                ops.gemm(att.view(bs * Q, C), a.wo, bias=a.bo, residual=output, out=output)
+                ops.layernorm(output, *self.selfa[i]["n"], 1e-5, out=output)
+                # FFN
+                f1 = ops.gemm(output, self.ffn[i]["l1"][0], bias=self.ffn[i]["l1"][1], act=ops.ACT_RELU)
+                ops.gemm(f1, self.ffn[i]["l2"][0], bias=self.ffn[i]["l2"][1], residual=output, out=output)
+                ops.layernorm(output, *self.ffn[i]["n"], 1e-5, out=output)
+            else:
+                # the token groups of this layer: carried ones + the level's spatial / visual tokens (re-set every layer,
+                # seem.py:512-527), sequence = [queries_object | groups...] per sample
+                groups = [(g_[0], g_[1], g_[2], g_[3]) for g_ in carried]
+                if spatial_flag:
+                    tk = bt(src_spatial_queries[lvl])
+                    groups.append(("tokens_spatial", tk, tk, src_spatial_maskings[lvl]))
+                if visual_flag:
+                    tk = bt(extra["src_visual_queries"][lvl])
+                    groups.append(("tokens_visual", tk, tk, extra["src_visual_maskings"][lvl]))
+                order = {"tokens_grounding": 0, "tokens_spatial": 1, "tokens_visual": 2, "tokens_audio": 3}   # SELF_ATTENTION dict order
+                groups.sort(key=lambda g_: order[g_[0]])
+                X = torch.cat([output.view(bs, Q, C)] + [g_[1] for g_ in groups], 1)
+                P = torch.cat([qpos.view(bs, Q, C)] + [g_[2] for g_ in groups], 1)
+                Ltot = X.shape[1]
+                X = X.reshape(bs * Ltot, C).contiguous()
+                sm = self._self_attn_mask(Q, [(g_[0], g_[1].shape[1], g_[3]) for g_ in groups], bs)
+                qk = ops.gemm(ops.add(X, P.reshape(bs * Ltot, C).contiguous()), a.wqk, bias=a.bqk).view(bs, Ltot, 2, H, hd)
+                v = ops.gemm(X, a.wv, bias=a.bv).view(bs, Ltot, H, hd)
+                att = ops.attention(qk[:, :, 0], qk[:, :, 1], v, scale=hd ** -0.5, mask=sm)
+                ops.gemm(att.view(bs * Ltot, C), a.wo, bias=a.bo, residual=X, out=X)
+                ops.layernorm(X, *self.selfa[i]["n"], 1e-5, out=X)
+                f1 = ops.gemm(X, self.ffn[i]["l1"][0], bias=self.ffn[i]["l1"][1], act=ops.ACT_RELU)
+                ops.gemm(f1, self.ffn[i]["l2"][0], bias=self.ffn[i]["l2"][1], residual=X, out=X)
+                ops.layernorm(X, *self.ffn[i]["n"], 1e-5, out=X)
+                X3 = X.view(bs, Ltot, C)
+                output = X3[:, :Q].reshape(bs * Q, C).contiguous()
+                off = Q
+                for g_ in groups:                                  # update_variables(output, 'self_attn')
+                    T = g_[1].shape[1]
+                    for cg in carried:
+                        if cg[0] == g_[0]:
+                            cg[1] = X3[:, off:off + T].contiguous()
+                    off += T
             results.append(self._heads(output, mask_rows, mask_hw, size_list[(i + 1) % self.num_feature_levels], bs))
         # organize_output (attention_data_struct.py:250-264) for the object queries
         names = {"predictions_class": "pred_logits", "predictions_mask": "pred_masks", "predictions_maskemb": "pred_maskembs"}
+        if grounding_flag or audio_flag:
+            names["predictions_caption"] = "pred_captions"        # attention_data_struct.py:12-28 (queries_object slice)
         out = {v: results[-1][k] for k, v in names.items()}
         out["aux_outputs"] = [{v: r[k] for k, v in names.items()} for r in results[:-1]]
+        extras_out = {}
+        if spatial_flag:
+            extras_out.update(pred_pspatials=spatial_query_pos.transpose(0, 1), pred_nspatials=spatial_query_neg.transpose(0, 1))
+        if visual_flag:
+            extras_out.update(pred_pvisuals=visual_query_pos.transpose(0, 1), pred_nvisuals=visual_query_neg.transpose(0, 1))
+        out.update(extras_out)
+        for a_ in out["aux_outputs"]:
+            a_.update(extras_out)
         out["attn_masks"] = [r["attn_mask"] for r in results]  # extra (not in the reference dict): for parity tests
         return out
 
