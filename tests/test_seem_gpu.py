@@ -105,8 +105,7 @@ def test_seem_end_to_end_head(cuda):
     assert out["pred_logits"] is None
     assert_close(out["aux_outputs"][0]["pred_masks"], ref["aux_outputs"][0]["pred_masks"], "e2e layer-0 masks", 0.06, 0.05)
     assert_close(out["pred_masks"], ref["pred_masks"], "e2e pred_masks", 0.12, 0.1)
-    with pytest.raises(NotImplementedError):
-        head({k: v.to(cuda) for k, v in feats.items()}, extra={"grounding_tokens": None})
+    # interactive prompts (`extra` keys) are covered by test_seem_prompts_vs_reference_golden
 
 
 def test_seem_vs_reference_golden(cuda):

@@ -24,7 +24,7 @@ with torch.no_grad():
             Rs = [torch.randn((M, No), device=dev).to(BF) for _ in range(nrot)] if res else [None] * nrot
             outs = [torch.empty((M, No), device=dev, dtype=BF) for _ in range(nrot)]
             fns = [(lambda j=j: ops.gemm(As[j], W, bias=b, glu=glu, residual=Rs[j], out=outs[j])) for j in range(nrot)]
-            for mode, (rb, dbg) in {"plain": (0, 0), "resb": (3, 0), "cl": (4, 0), "plain_noepi": (0, 1), "cl_noepi": (4, 1)}.items():
+            for mode, (rb, dbg) in {"plain": (0, 0), "plain_noepi": (0, 1), "plain_nostore": (0, 2)}.items():
                 ops.set_gemm_debug(rb, dbg)
                 row[f"{temp}_{mode}_us"] = round(graph_time(fns) * 1e3, 1)
             ops.set_gemm_debug(1, 0)

@@ -495,6 +495,12 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   }
                 } else {
                   bf16* dst = reinterpret_cast<bf16*>(orow_ptr) + ci * OUTS;
+                  if (p.dbg & 2) {   // measurement aid: everything but the global stores (result kept alive through one lane)
+                    float acc_ = 0.f;
+#pragma unroll
+                    for (int j = 0; j < OUTS; ++j) acc_ += f[j];
+                    if (acc_ == 123.456f) dst[0] = __float2bfloat16(acc_);
+                  } else
 #pragma unroll
                   for (int q = 0; q < OUTS / 16; ++q) {
                     const uint32_t o[8] = {pack_bf16(f[q * 16], f[q * 16 + 1]),       pack_bf16(f[q * 16 + 2], f[q * 16 + 3]),
