@@ -166,10 +166,11 @@ def test_gemm_resident_b(cuda, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(40960, 320, 320), (8192, 1280, 320), (5000, 640, 192), (4096, 2560, 320), (10240, 640, 640),
-                                   (4224, 336, 128), (4100, 512, 2048)])
+                                   (4224, 336, 128), (4100, 512, 2048), (300, 1280, 1280), (2560, 1280, 5120)])
 def test_gemm_cluster_pair(cuda, M, N, K):
-    """The cluster-pair variant of the v2 kernel (two CTAs on adjacent n-blocks, each half of the A tile fetched once and
-    multicast into both): plain, activation, residual in place, GEGLU, per-group rowbias; ragged M and N tails."""
+    """The CTA-pair variant of the v2 kernel (tcgen05 cta_group::2: a 256-row tile over two SMs, each CTA loads its own 128
+    rows of A and half of the B tile) forced on: plain, activation, residual in place, GEGLU, per-group rowbias; ragged M
+    and N tails, odd number of m-blocks (the last pair's second CTA has no rows)."""
     from vitron_b200 import ops
     a, w, bias = rnd((M, K), cuda, 1), rnd((N, K), cuda, 2, 0.05), rnd((N,), cuda, 3)
     res = rnd((M, N), cuda, 4)
@@ -202,8 +203,8 @@ def test_gemm_cluster_pair(cuda, M, N, K):
                                                           (16, 40, 64, 320, 320, 3, 3, 2), (4, 40, 64, 320, 640, 1, 1, 1),
                                                           (8, 37, 50, 128, 512, 3, 3, 1), (64, 8, 8, 256, 512, 3, 3, 1)])
 def test_conv_cluster_pair(cuda, nb, h, w, cin, cout, kh, kw, stride):
-    """Implicit-GEMM convolution on the cluster-pair kernel: the pixel tile's two halves (split along rows or samples) are
-    fetched by different CTAs; ragged tiles at the image border, stride 2, ResBlock epilogue."""
+    """Implicit-GEMM convolution on the CTA-pair kernel (two pixel tiles per 256-row MMA): ragged tiles at the image
+    border, odd tile counts, stride 2, ResBlock epilogue."""
     from vitron_b200 import ops
     x = rnd((nb, h, w, cin), cuda, 1)
     wt = rnd((cout, cin, kh, kw), cuda, 2, 0.03)

@@ -9,7 +9,7 @@ from tools.kbench_unet import graph_time  # noqa: E402
 
 dev = torch.device("cuda:0")
 BF = torch.bfloat16
-CASES = [(40960, 320, 320, 0, False), (40960, 320, 320, 0, True), (40960, 960, 320, 0, False), (40960, 2560, 320, 2, False),
+CASES = [(6144, 12288, 4096, 0, False), (6144, 4096, 11008, 0, True), (40960, 320, 320, 0, False), (40960, 320, 320, 0, True), (40960, 960, 320, 0, False), (40960, 2560, 320, 2, False),
          (40960, 1280, 320, 0, False), (10240, 640, 640, 0, True), (10240, 1920, 640, 0, False), (10240, 5120, 640, 2, False),
          (40960, 320, 1280, 0, True), (2560, 1280, 1280, 0, True)]
 with torch.no_grad():
@@ -24,7 +24,7 @@ with torch.no_grad():
             Rs = [torch.randn((M, No), device=dev).to(BF) for _ in range(nrot)] if res else [None] * nrot
             outs = [torch.empty((M, No), device=dev, dtype=BF) for _ in range(nrot)]
             fns = [(lambda j=j: ops.gemm(As[j], W, bias=b, glu=glu, residual=Rs[j], out=outs[j])) for j in range(nrot)]
-            for mode, (rb, dbg) in {"plain": (0, 0), "plain_noepi": (0, 1), "plain_nostore": (0, 2)}.items():
+            for mode, (rb, dbg) in {"plain": (8, 0), "pair": (4, 0), "auto": (0, 0), "plain_noepi": (8, 1), "pair_noepi": (4, 1)}.items():
                 ops.set_gemm_debug(rb, dbg)
                 row[f"{temp}_{mode}_us"] = round(graph_time(fns) * 1e3, 1)
             ops.set_gemm_debug(1, 0)

@@ -140,22 +140,32 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_
       : "memory");
 }
 
-// Multicast variants: the box lands at the same CTA-relative smem offset in every CTA of `cta_mask` (bit i = cluster rank i)
-// and each destination CTA's mbarrier (same offset) receives the complete_tx for the bytes that landed in it.
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+// 2-CTA (cta_group::2) loads: issued by BOTH CTAs of a pair, each into its OWN shared memory; the complete_tx goes to the
+// mbarrier at `bar_leader` = the shared::cluster address of the LEADER CTA's barrier (mapa_rank0), which collects the bytes
+// of both CTAs before the leader issues the pair's tcgen05.mma.cta_group::2.
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const void* tmap, uint32_t bar_leader, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_leader), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d_mc(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
-                                               uint16_t cta_mask) {
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const void* tmap, uint32_t bar_leader, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// shared::cluster address of the same shared-memory location in the cluster's rank-0 CTA
+__device__ __forceinline__ uint32_t mapa_rank0(const void* smem_ptr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(smem_ptr)));
+  return r;
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa_rank0)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -216,12 +226,32 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
           smem_u32(bar))
       : "memory");
 }
-// ... and on the mbarrier at the same offset in every CTA of `cta_mask` (slot release towards every CTA that writes into it)
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+// 2-CTA pair: arrive — once every MMA the pair has issued so far has retired — on the mbarrier at this offset in every CTA
+// of `cta_mask` (ring-slot release towards both producers, accumulator hand-over to both CTAs' epilogue warps)
+__device__ __forceinline__ void tc_commit2_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
       "h"(cta_mask)
+      : "memory");
+}
+// TMEM allocation of a CTA pair: the same warp of BOTH CTAs executes these; the columns are reserved in both SMs.
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs: 256 x N] (+)= A[each CTA's 128 rows] * B[each CTA's N / 2 columns]: issued by the pair's leader only.
+__device__ __forceinline__ void tc_mma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.
@@ -303,8 +333,9 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float erf_abs = fmaf(-poly, e, 1.0f);           // erf(|x| / sqrt 2)
   return 0.5f * x + 0.5f * fabsf(x) * erf_abs;          // 0.5 x (1 + sign(x) erf_abs)
 }
-__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// __fdividef: MUFU.RCP + FMUL (2 ulp); the IEEE `/` compiles to FCHK + a called slow path per element
+__device__ __forceinline__ float quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   bf162 v = __floats2bfloat162_rn(lo, hi);

@@ -59,7 +59,6 @@ struct GemmParams {
   int* counters;      // one arrival counter per output tile (zero on entry, zero again on exit)
   int rows_c, cols_c; // extent of the output in C orientation (rows = tokens, cols = features)
   int vec_ok;         // v2: workspace rows are 32-byte aligned (N % 8 == 0) -> 256-bit partial stores
-  int half_dh, half_dn; // v2 cluster pair (conv): coordinate offset of rank 1's half of the A pixel tile along h resp. n
   int dbg;            // v2 measurement aid (vb200_set_gemm_debug): bit 0 = epilogue skips its loads / math / stores
 };
 

@@ -667,7 +667,7 @@ static int validate_epi(const vb_epilogue* e, long long N) {
 // ------------------------------------------------------------------ v2 planning
 static int g_gemm_impl = 0;  // 0: v2 whenever eligible, 1: generic kernel only (A/B measurements, parity tests of both)
 static int g_gemm_resb = 1;  // resident-B variant: bit 0 = K <= 320 (5 k-blocks), bit 1 = also K <= 640 at BN = 128; 0 = off
-                             // bit 2: cluster-pair variant (A tile multicast to two CTAs working on adjacent n-blocks)
+                             // bit 2: force the CTA-pair (cta_group::2) variant wherever it applies; bit 3: never use it
 static int g_gemm_dbg = 0;   // GemmParams.dbg of the v2 launches (measurement aid)
 int resb_smem_bytes(int bn, int nkb);  // gemm_v2_resb.cu
 
@@ -696,29 +696,30 @@ static int resb_tile(long long M, long long N, int nkb, int need) {
   return best;
 }
 
-// Tile width of the cluster-pair variant (even number of n-blocks required), or 0 when it does not apply.
-static int cl_tile(long long mb, long long N, int nkb, int need) {
-  if (!(g_gemm_resb & 4)) return 0;
+// Tile width of the CTA-pair (cta_group::2, 256-row tile) variant for `mb` m-blocks, or 0 when it does not apply. Time per
+// k-step of a pair in units of the 1-CTA 128x256x64 step: operand bytes per SM drop from 16 + BN/8 KB to 16 + BN/16 KB.
+static int cl_tile(long long mb, long long N, int nkb, int need, float* t_out) {
   if (need != 0 && need != F_RES && need != F_GLU && need != F_ACT && need != F_RB && need != (F_RB | F_RES)) return 0;
-  if (mb < 32) return 0;
+  if (mb < 2) return 0;
   const int cands[3] = {256, 160, 128};
-  const float tk[3] = {1.0f, 0.66f, 0.56f};    // A crosses the fabric once per pair: narrow tiles approach their MMA time
+  const float tk[3] = {0.70f, 0.56f, 0.52f};
   int best = 0;
   float best_t = 1e30f;
   const int clusters = vb_num_sms() / 2;
   for (int i = 0; i < 3; ++i) {
     const long long nb = (N + cands[i] - 1) / cands[i];
-    if (nb & 1) continue;
-    const long long units = mb * (nb / 2);
+    const long long units = ((mb + 1) / 2) * nb;
     const long long waves = (units + clusters - 1) / clusters;
-    const float t = static_cast<float>(waves) * (nkb * tk[i] + 2.0f * cands[i] / 256.f);
+    const float t = static_cast<float>(waves) * (nkb * tk[i]) + 2.0f * cands[i] / 256.f;
     if (t < best_t - 1e-4f) { best_t = t; best = cands[i]; }
   }
+  if (t_out) *t_out = best_t;
   return best;
 }
 
 struct TilePlan {
   int bn, splits;
+  float t;   // modelled time (units of one 1-CTA 128x256x64 k-step)
 };
 
 // Tile width and split-K factor for `mb` 128-row m-blocks x N columns x `kblocks` k-steps. Time model in units of one
@@ -728,11 +729,11 @@ static TilePlan plan_tiles(long long mb, long long N, int kblocks, bool allow_sp
   const int sms = vb_num_sms();
   const int cands[5] = {256, 160, 128, 64, 32};
   const float tk[5] = {1.0f, 0.78f, 0.76f, 0.625f, 0.57f};
-  TilePlan best = {256, 1};
+  TilePlan best = {256, 1, 1e30f};
   float best_t = 1e30f;
   if (const char* force = getenv("VB200_FORCE_BN")) {
     const int v = atoi(force);
-    if (v == 256 || v == 160 || v == 128 || v == 64 || v == 32) return {v, 1};
+    if (v == 256 || v == 160 || v == 128 || v == 64 || v == 32) return {v, 1, 0.f};
   }
   for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
@@ -753,7 +754,7 @@ static TilePlan plan_tiles(long long mb, long long N, int kblocks, bool allow_sp
       // a split writes and re-reads sp fp32 copies of the output (~5 TB/s through L2; one unit = 0.27 us) and pays one
       // more launch (~2.5 us)
       if (sp > 1) t += static_cast<float>(sp) * out_rows * N * 8.0f / 5.0e6f / 0.27f + 9.0f;
-      if (t < best_t - 1e-4f) { best_t = t; best = {bn, sp}; }
+      if (t < best_t - 1e-4f) { best_t = t; best = {bn, sp, t}; }
     }
   }
   return best;
@@ -924,20 +925,6 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   p.m_blocks = static_cast<int>((M + BLOCK_M - 1) / BLOCK_M);
   if (v2_eligible(epi, out, ldo, N)) {
     p.dbg = g_gemm_dbg;
-    if (const int cbn = cl_tile(p.m_blocks, N, p.num_k_blocks, v2_need(epi, 1))) {
-      p.n_blocks = static_cast<int>((N + cbn - 1) / cbn);
-      p.splits = 1;
-      uint64_t dA[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
-      uint64_t sA[1] = {static_cast<uint64_t>(lda) * 2};
-      uint32_t bA[2] = {BLOCK_K, BLOCK_M / 2};   // each CTA of the pair loads (and multicasts) half of the A tile
-      if (int r = make_tmap(&ta, A, 2, dA, sA, bA, estr2)) return r;
-      uint64_t dB[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
-      uint64_t sB[1] = {static_cast<uint64_t>(ldw) * 2};
-      uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(cbn)};
-      if (int r = make_tmap(&tb, W, 2, dB, sB, bB, estr2)) return r;
-      const int r = launch_gemm_v2_cl(cbn, v2_need(epi, 1), ta, tb, p, stream);
-      if (r != VB_ERR_UNSUPPORTED) return r;
-    }
     if (const int rbn = resb_tile(M, N, p.num_k_blocks, v2_need(epi, 1))) {
       p.n_blocks = static_cast<int>((N + rbn - 1) / rbn);
       p.splits = 1;
@@ -956,6 +943,23 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
     if (pl.splits > 1) {
       const size_t need_ws = GEMM_COUNTER_BYTES + static_cast<size_t>(pl.splits) * M * N * sizeof(float);
       if (workspace == nullptr || workspace_bytes < need_ws || !aligned32(workspace)) pl = plan_tiles(p.m_blocks, N, p.num_k_blocks, false, M);
+    }
+    // CTA pair (cta_group::2) when its modelled time beats the best 1-CTA plan
+    float t_cl = 0.f;
+    const int cbn = (g_gemm_resb & 8) ? 0 : cl_tile(p.m_blocks, N, p.num_k_blocks, v2_need(epi, 1), &t_cl);
+    if (cbn && ((g_gemm_resb & 4) || t_cl < pl.t)) {
+      p.n_blocks = static_cast<int>((N + cbn - 1) / cbn);
+      p.splits = 1;
+      uint64_t dA[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+      uint64_t sA[1] = {static_cast<uint64_t>(lda) * 2};
+      uint32_t bA[2] = {BLOCK_K, BLOCK_M};
+      if (int r = make_tmap(&ta, A, 2, dA, sA, bA, estr2)) return r;
+      uint64_t dB[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+      uint64_t sB[1] = {static_cast<uint64_t>(ldw) * 2};
+      uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(cbn / 2)};   // each CTA of the pair loads half of the B tile
+      if (int r = make_tmap(&tb, W, 2, dB, sB, bB, estr2)) return r;
+      const int r = launch_gemm_v2_cl(cbn, v2_need(epi, 1), ta, tb, p, stream);
+      if (r != VB_ERR_UNSUPPORTED) return r;
     }
     p.n_blocks = static_cast<int>((N + pl.bn - 1) / pl.bn);
     p.splits = pl.splits;
@@ -1077,6 +1081,7 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
 
   const bool v2 = v2_eligible(epi, out, p.ldo, cout);
   int bn;
+  float t_one = 1e30f;   // modelled time of the chosen 1-CTA plan
   if (v2) {
     TilePlan pl = plan_tiles(p.m_blocks, cout, p.num_k_blocks, true, p.M);
     if (pl.splits > 1) {
@@ -1084,6 +1089,7 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
       if (workspace == nullptr || workspace_bytes < need_ws || !aligned32(workspace)) pl = plan_tiles(p.m_blocks, cout, p.num_k_blocks, false, p.M);
     }
     bn = pl.bn;
+    t_one = pl.t;
     p.splits = pl.splits;
     if (pl.splits > 1) {
       p.counters = reinterpret_cast<int*>(workspace);
@@ -1095,14 +1101,16 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
   } else {
     bn = pick_block_n(static_cast<long long>(p.m_blocks) * BLOCK_M, cout, epi->glu);
   }
-  // cluster pair: the A pixel tile splits into two contiguous halves along its outermost extent (samples, else rows)
-  int cl_bn = 0, box_h = th, box_n = tn;
-  if (v2 && p.splits == 1 && ((tw * th * tn) % 16) == 0 && ((tn % 2) == 0 || (tn == 1 && (th % 2) == 0))) {
-    cl_bn = cl_tile(p.m_blocks, cout, p.num_k_blocks, v2_need(epi, 1));
-    if (cl_bn) {
-      bn = cl_bn;
-      if ((tn % 2) == 0) { box_n = tn / 2; p.half_dn = tn / 2; }
-      else { box_h = th / 2; p.half_dh = (th / 2) * stride; }
+  // CTA pair (cta_group::2): two pixel tiles per 256-row MMA, each CTA loads its own tile + half of the weight tile
+  int cl_bn = 0;
+  if (v2 && !(g_gemm_resb & 8)) {
+    float t_cl = 0.f;
+    const int cbn = cl_tile(p.m_blocks, cout, p.num_k_blocks, v2_need(epi, 1), &t_cl);
+    if (cbn && ((g_gemm_resb & 4) || t_cl < t_one)) {
+      cl_bn = bn = cbn;
+      p.splits = 1;
+      p.counters = nullptr;
+      p.ws = nullptr;
     }
   }
   p.n_blocks = static_cast<int>((cout + bn - 1) / bn);
@@ -1114,12 +1122,12 @@ extern "C" int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, in
                     static_cast<uint64_t>(cin) * w * h * 2};
   // box extents are in traversed global elements: (tw-1)*stride+1 columns yield tw samples
   uint32_t bA[4] = {BLOCK_K, static_cast<uint32_t>((tw - 1) * stride + 1),
-                    static_cast<uint32_t>((box_h - 1) * stride + 1), static_cast<uint32_t>(box_n)};
+                    static_cast<uint32_t>((th - 1) * stride + 1), static_cast<uint32_t>(tn)};
   uint32_t eA[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
   if (int r = make_tmap(&ta, X, 4, dA, sA, bA, eA)) return r;
   uint64_t dB[2] = {static_cast<uint64_t>(kh) * kw * cin_pad, static_cast<uint64_t>(cout)};
   uint64_t sB[1] = {static_cast<uint64_t>(kh) * kw * cin_pad * 2};
-  uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
+  uint32_t bB[2] = {BLOCK_K, static_cast<uint32_t>(cl_bn ? bn / 2 : bn)};
   const uint32_t estr2[2] = {1, 1};
   if (int r = make_tmap(&tb, Wt, 2, dB, sB, bB, estr2)) return r;
   if (cl_bn) {

@@ -87,18 +87,23 @@ static __device__ __noinline__ void epi_ragged(const uint32_t* acc, int n_valid,
 // memory for its whole life and works on m-tiles of that n-block only; the ring then carries A alone. Without it every
 // 128 x BN tile re-fetches its B tile from L2: at K = 320 the level-0 UNet GEMMs moved 184 KB per tile for 0.85 us of MMA —
 // 8.6 TB/s of L2 -> SM traffic, L2-bandwidth bound (in-situ 16.7 us for M 40960, N = K = 320 against ~4 us of MMA).
-// CL ("cluster pair"): two CTAs of a thread-block cluster work on the SAME m-block and ADJACENT n-blocks (2j, 2j + 1). Each
-// loads one half of the A tile of every k-step and the TMA unit MULTICASTS it into both CTAs' shared memory, so the large
-// streamed operand crosses the L2 -> SM fabric once per pair instead of once per CTA (measured: the main loop of the
-// small-K UNet GEMMs runs at a constant ~5.5 TB/s of A traffic, A being re-read once per n-block). A ring slot may be
-// refilled when BOTH CTAs' MMAs have retired it: tcgen05.commit arrives on the slot's empty barrier of both CTAs
-// (UTCBAR.MULTICAST); the barriers expect two arrivals.
+// CL ("CTA pair", tcgen05 cta_group::2): the two CTAs of a cluster (two SMs of one TPC) compute ONE 256 x BLOCK_N tile.
+// Each CTA loads its own 128 rows of A and only HALF of the B tile (BLOCK_N / 2 weight rows); the leader CTA's single MMA
+// thread issues tcgen05.mma.cta_group::2 (M = 256), which reads A and B from both CTAs' shared memory and accumulates
+// rows 0..127 into the leader's TMEM and rows 128..255 into the peer's. Per SM and k-step the same 128 x BLOCK_N x 64 MMA
+// work now needs 16 KB + BLOCK_N x 64 B of operand traffic instead of 16 KB + BLOCK_N x 128 B (BLOCK_N = 256: 32 KB instead
+// of 48 KB) — the 1-CTA kernel is bound by the L2 -> SM operand stream, not by the tensor pipe (measured in round 2:
+// main loop alone at K = 320, N >= 960 = 0.45 us per k-step against 0.27 us of MMA).
+// Protocol: both producers wait on their OWN ring-slot barrier and issue cta_group::2 TMA loads whose bytes are counted
+// by the LEADER's full barrier (which expects both CTAs' bytes); the leader's tcgen05.commit multicasts the slot release
+// and the accumulator hand-over to both CTAs; each CTA's epilogue warps drain their own TMEM and arrive on the leader's
+// accumulator-empty barrier (2 x NUM_EPI_WARPS arrivals). TMEM is allocated / freed by warp 1 of both CTAs (cta_group::2).
 template <int BLOCK_N, int STAGES, int F, bool RESB = false, bool CL = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int B_BYTES = (CL ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;   // CTA pair: this CTA's half of the B tile
   constexpr int STAGE_BYTES = RESB ? A_BYTES : A_BYTES + B_BYTES;
   constexpr int ACC_STAGES = 2;
   constexpr uint32_t TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32)    ? 32
@@ -142,33 +147,38 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_b);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL ? 2 : 1);
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[i], CL ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
     }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
+  uint32_t crank = 0;
+  if constexpr (CL) {
+    cluster_sync_all();   // both CTAs' barriers exist before anything arrives on them from the other CTA
+    crank = cluster_ctarank();
+  }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CL) {
+      tmem_alloc2(tmem_slot, TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  uint32_t crank = 0;
-  if constexpr (CL) {
-    cluster_sync_all();   // the peer's barriers exist before anything is multicast into / arrives on them
-    crank = cluster_ctarank();
-  }
   pdl_wait();
 
   // work units of this CTA: (m-block, n-block, split) in grouped raster order, or — RESB — the m-blocks
   // m = blockIdx.x / n_blocks, += gridDim.x / n_blocks of the ONE n-block blockIdx.x % n_blocks (grid is a multiple of n_blocks)
-  const int total_units = RESB ? p.m_blocks : CL ? p.m_blocks * (p.n_blocks >> 1) : p.m_blocks * p.n_blocks * p.splits;
+  const int total_units = RESB ? p.m_blocks : CL ? ((p.m_blocks + 1) >> 1) * p.n_blocks : p.m_blocks * p.n_blocks * p.splits;
   const int unit_first = RESB ? static_cast<int>(blockIdx.x) / p.n_blocks : CL ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int unit_step = RESB ? static_cast<int>(gridDim.x) / p.n_blocks : CL ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int my_n_blk = RESB ? static_cast<int>(blockIdx.x) % p.n_blocks : 0;
@@ -178,16 +188,17 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       t.m_blk = unit; t.n_blk = my_n_blk; t.split = 0;
       return t;
     } else if constexpr (CL) {
-      // grouped raster over (m-block, n-PAIR); this CTA takes n-block 2 * pair + rank
+      // grouped raster over (m-block PAIR, n-block); this CTA owns m-block 2 * pair + rank (may be one past the last
+      // m-block when their number is odd: its loads are all out of bounds = zeros, its rows are never stored)
       TileCoord t;
-      const int npairs = p.n_blocks >> 1;
-      const int per_group = 16 * npairs;
+      const int mpairs = (p.m_blocks + 1) >> 1;
+      const int per_group = 8 * p.n_blocks;
       const int group = unit / per_group;
-      const int first_m = group * 16;
-      const int gsize = min(p.m_blocks - first_m, 16);
+      const int first_m = group * 8;
+      const int gsize = min(mpairs - first_m, 8);
       const int in_group = unit - group * per_group;
-      t.m_blk = first_m + in_group % gsize;
-      t.n_blk = 2 * (in_group / gsize) + static_cast<int>(crank);
+      t.m_blk = 2 * (first_m + in_group % gsize) + static_cast<int>(crank);
+      t.n_blk = in_group / gsize;
       t.split = 0;
       return t;
     } else {
@@ -200,6 +211,8 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      [[maybe_unused]] uint32_t full_bar_leader = 0;
+      if constexpr (CL) full_bar_leader = mapa_rank0(full_bar);
       if constexpr (RESB) {
         mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(p.num_k_blocks) * B_BYTES);
         for (int kb = 0; kb < p.num_k_blocks; ++kb)
@@ -224,20 +237,24 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           else mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes + (RESB ? 0 : B_BYTES));
           if constexpr (CL) {
-            // this CTA's half of the A tile, multicast to both CTAs of the pair (tmap_a's box is the half tile)
-            uint8_t* dst = sa + crank * (p.a_box_bytes >> 1);
+            // the leader's barrier counts the bytes of BOTH CTAs (own A rows + own half of the B tile each)
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (p.a_box_bytes + B_BYTES));
+            const uint32_t fb = full_bar_leader + stage * 8;
             if (p.a_mode == 0) {
-              tma_load_2d_mc(dst, &tmap_a, &full_bar[stage], kb * BLOCK_K, t.m_blk * BLOCK_M + static_cast<int>(crank) * (BLOCK_M / 2), 3);
+              tma_load_2d_2sm(sa, &tmap_a, fb, kb * BLOCK_K, t.m_blk * BLOCK_M);
             } else {
               int tap = kb / p.cin_chunks;
               int cc = kb - tap * p.cin_chunks;
               int dy = tap / p.kw, dx = tap - dy * p.kw;
-              tma_load_4d_mc(dst, &tmap_a, &full_bar[stage], cc * BLOCK_K, cw + dx, ch + dy + static_cast<int>(crank) * p.half_dh,
-                             cn + static_cast<int>(crank) * p.half_dn, 3);
+              tma_load_4d_2sm(sa, &tmap_a, fb, cc * BLOCK_K, cw + dx, ch + dy, cn);
             }
-          } else if (p.a_mode == 0) {
+            tma_load_2d_2sm(sb, &tmap_b, fb, kb * BLOCK_K, t.n_blk * BLOCK_N + static_cast<int>(crank) * (BLOCK_N / 2));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes + (RESB ? 0 : B_BYTES));
+          if (p.a_mode == 0) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, t.m_blk * BLOCK_M);
           } else {
             int tap = kb / p.cin_chunks;
@@ -252,7 +269,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = umma_idesc_bf16(CL ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -260,11 +277,13 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if constexpr (RESB) {
       if (unit_first < total_units) mbar_wait(b_full, 0);
     }
-    for (int unit = unit_first; unit < total_units; unit += unit_step) {
+    // CTA pair: only the leader issues MMAs (they drive the tensor cores of both SMs)
+    for (int unit = (CL && crank != 0) ? total_units : unit_first; unit < total_units; unit += unit_step) {
       TileCoord t = work_of(unit);
       int k0, k1;
       split_range(p, t.split, k0, k1);
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      if constexpr (CL) mbar_wait_bounded(&tmem_empty[acc], acc_phase ^ 1);
+      else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
       for (int kb = k0; kb < k1; ++kb) {
@@ -276,12 +295,19 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sb = RESB ? smem_u32(sB_res + kb * B_BYTES) : sa + A_BYTES;
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sb);
+          if constexpr (CL) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
-          if constexpr (CL) tc_commit_mc(&empty_bar[stage], 3);   // both CTAs of the pair wrote into this slot
-          else tc_commit(&empty_bar[stage]);
-          if (kb == k1 - 1) tc_commit(&tmem_full[acc]);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              tc_mma2_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+            tc_commit2_mc(&empty_bar[stage], 3);                      // slot free again in both CTAs
+            if (kb == k1 - 1) tc_commit2_mc(&tmem_full[acc], 3);      // accumulator halves ready in both CTAs
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+            tc_commit(&empty_bar[stage]);
+            if (kb == k1 - 1) tc_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -531,7 +557,10 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CL) mbar_arrive_cluster(mapa_rank0(&tmem_empty[acc]));   // the leader waits for both CTAs' drains
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
 
     }
@@ -539,10 +568,11 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (CL) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers
+  if constexpr (CL) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal / write into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CL) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -573,12 +603,12 @@ int launch_v2_resb(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   return VB_OK;
 }
 
-// cluster-pair launch: grid = 2 x clusters (<= SM count), cluster dimension 2, PDL attribute when enabled
+// CTA-pair launch: grid = 2 x clusters (<= SM count), cluster dimension 2, PDL attribute when enabled
 template <int BN, int STAGES, int F>
 int launch_v2_cl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 1024 + 256 + NUM_EPI_WARPS * BN * 4;
+  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + (BN / 2) * BLOCK_K * 2) + 1024 + 256 + NUM_EPI_WARPS * BN * 4;
   static_assert(smem <= SMEM_LIMIT, "smem budget");
-  if ((p.n_blocks & 1) || p.splits != 1) return VB_ERR_UNSUPPORTED;
+  if (p.splits != 1) return VB_ERR_UNSUPPORTED;
   static bool attr_set = false;
   static int max_clusters = 0;
   auto kern = gemm_v2_kernel<BN, STAGES, F, false, true>;
@@ -602,7 +632,7 @@ int launch_v2_cl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams&
     max_clusters = n < vb_num_sms() / 2 ? n : vb_num_sms() / 2;
     attr_set = true;
   }
-  const int units = p.m_blocks * (p.n_blocks >> 1);
+  const int units = ((p.m_blocks + 1) >> 1) * p.n_blocks;
   int clusters = max_clusters;
   if (clusters > units) clusters = units;
   cfg.gridDim = dim3(2 * clusters);
