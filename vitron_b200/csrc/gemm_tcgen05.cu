@@ -674,7 +674,7 @@ int resb_smem_bytes(int bn, int nkb);  // gemm_v2_resb.cu
 // Tile width of the resident-B variant for M x N x (nkb k-blocks), or 0 when it does not apply: the widest slab that
 // fits next to an A ring deep enough to cover the L2 latency (BN = 160 with 6 A stages at K <= 320; BN = 128 at K <= 640).
 static int resb_tile(long long M, long long N, int nkb, int need) {
-  if (!g_gemm_resb || (need != 0 && need != F_RES && need != F_GLU && need != F_ACT)) return 0;
+  if (!(g_gemm_resb & 3) || (need != 0 && need != F_RES && need != F_GLU && need != F_ACT)) return 0;
   if (nkb > 5 && !(g_gemm_resb & 2)) return 0;
   if (M < 4096) return 0;                       // few m-tiles: nothing to amortise the slab load over
   const int cands[3] = {160, 256, 128};
@@ -701,8 +701,11 @@ static int resb_tile(long long M, long long N, int nkb, int need) {
 static int cl_tile(long long mb, long long N, int nkb, int need, float* t_out) {
   if (need != 0 && need != F_RES && need != F_GLU && need != F_ACT && need != F_RB && need != (F_RB | F_RES)) return 0;
   if (mb < 2) return 0;
+  // measured (profiles/r02_gemm_pair_vs_1cta.jsonl): 3-8 % faster than the 1-CTA kernel from K = 4096 up (LLM prefill), equal
+  // or slower on the short-K UNet shapes, whose time is tile hand-over + epilogue + output stores, not operand traffic
+  if (nkb < 32 && !(g_gemm_resb & 4)) return 0;
   const int cands[3] = {256, 160, 128};
-  const float tk[3] = {0.70f, 0.56f, 0.52f};
+  const float tk[3] = {0.93f, 0.74f, 0.70f};
   int best = 0;
   float best_t = 1e30f;
   const int clusters = vb_num_sms() / 2;
