@@ -102,6 +102,9 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    mode = os.environ.get("VB200_GEMM_MODE")   # measurement aid: the `mode` argument of vb200_set_gemm_debug (A/B runs of bench.py)
+    if mode:
+        lib.vb200_set_gemm_debug(int(mode), -1)
     return lib
 
 

@@ -6,6 +6,7 @@
 // here a paged cache [num_pages, n_heads, page_size, head_dim]; splice =
 // LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal (vitron/model/llava_arch.py:478-521).
 #include "common.cuh"
+#include <cstdlib>
 #include "vitron_b200.h"
 #include <limits.h>
 
@@ -135,6 +136,18 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
     pg[i] = (pi < max_pages && i * 64 < per) ? bt[pi] : 0;
   }
   pdl_trigger();
+  // L2 prefetch of this CTA's first page (K and V, 16 KB each for this head) while the predecessor (the qkv projection,
+  // which does not touch the cache) drains: pages of earlier tokens are constant during the step. One 128-byte line per
+  // 4 lanes; the remaining trips are prefetched two trips ahead inside the loop.
+  const long long pf_head = static_cast<long long>(h) * page_size * HD;
+  const long long pf_stride = static_cast<long long>(H) * page_size * HD;
+  auto prefetch_page = [&](int page) {
+    const long long base = static_cast<long long>(page) * pf_stride + pf_head + static_cast<long long>(threadIdx.x) * 64;  // 128 thr x 128 B
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(k_pages + base));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(v_pages + base));
+  };
+  if (per > 0) prefetch_page(pg[0]);
+  if (MAX_TRIPS > 1 && per > 64) prefetch_page(pg[1]);
   pdl_wait();
   const int len = kv_len[b];
   const int c1 = min(len, c0 + per);
@@ -206,6 +219,7 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
       vq[u][0] = *reinterpret_cast<const uint4*>(v_pages + off);
       vq[u][1] = *reinterpret_cast<const uint4*>(v_pages + off + 8);
     }
+    if (i + 2 < MAX_TRIPS && tb + 128 < c1) prefetch_page(pg[i + 2]);   // two trips ahead -> L2, behind this trip's loads
     float sc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -438,10 +452,28 @@ extern "C" int vb200_rope_kv_append(void* qkv, int64_t ld_qkv, const int32_t* po
   return VB_OK;
 }
 
-static int decode_splits(int64_t max_kv_len) {
-  // 256-key splits: the per-CTA chain of dependent 64-key trips (the kernel's critical path at decode-time
-  // context lengths) stays at 4; contexts beyond 32 x 256 keys fall back to 512-key splits
-  int s = static_cast<int>((max_kv_len + DEC_CHUNK / 2 - 1) / (DEC_CHUNK / 2));
+static int decode_splits(int64_t max_kv_len, int64_t bh) {
+  // As few splits as still give every SM its 4 resident CTAs (113 registers x 128 threads): the whole grid runs as ONE
+  // wave and the per-CTA fixed cost (q load + RoPE, partial write, arrival atomics, merge) is paid once per 512 keys, with
+  // the next page already on its way to L2 while a 64-key trip is processed. Measured at B = 8, 896-token cache inside
+  // the real decode step (profiles/r02_decode_attention_split_keys.txt): 128 / 256 / 512 keys per split -> 3.77 / 3.68 /
+  // 3.58 ms per token. Small batches get more, shorter splits (down to 128 keys) to fill the machine.
+  static int keys_env = -1;   // VB200_DEC_SPLIT_KEYS = 128 / 256 / 512 pins the split length (tuning aid)
+  if (keys_env < 0) {
+    const char* e = getenv("VB200_DEC_SPLIT_KEYS");
+    const int v = e ? atoi(e) : 0;
+    keys_env = (v == 128 || v == 256 || v == 512) ? v : 0;
+  }
+  int s;
+  if (keys_env) {
+    s = static_cast<int>((max_kv_len + keys_env - 1) / keys_env);
+  } else {
+    const int s_min = static_cast<int>((max_kv_len + DEC_CHUNK - 1) / DEC_CHUNK);          // a split is at most 512 keys
+    const int s_max = static_cast<int>((max_kv_len + 127) / 128);                           // ... and at least 128
+    int s_fill = static_cast<int>(4LL * vb_num_sms() / (bh > 0 ? bh : 1));                  // one wave of 4 CTAs per SM
+    if (s_fill > s_max) s_fill = s_max;
+    s = s_fill > s_min ? s_fill : s_min;
+  }
   if (s < 1) s = 1;
   if (s > 32) s = 32;
   return s;
@@ -465,7 +497,7 @@ static int launch_attn_decode(const void* q, int64_t ld_q, void* k_pages, void* 
   if (head_dim != 128) return VB_ERR_UNSUPPORTED;
   VB_CHECK_ARG(ld_q % 8 == 0);
   if (page_size != 64) return VB_ERR_UNSUPPORTED;  // one 64-key trip == one page
-  const int splits = decode_splits(max_kv_len);
+  const int splits = decode_splits(max_kv_len, B * n_heads);
   int per = static_cast<int>((max_kv_len + splits - 1) / splits);
   per = (per + 63) / 64 * 64;
   if (per > DEC_CHUNK) return VB_ERR_ARG;
