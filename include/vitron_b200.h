@@ -238,6 +238,11 @@ int vb200_region_mask_pool(const void* feats, const float* boxes, void* out, int
  * cleared (seem.py:569-574, attention_data_struct.py:187). */
 int vb200_seem_attn_mask(const float* mask_logits, uint8_t* out_mask, int64_t Q, int64_t H,
                          int64_t W, int64_t h2, int64_t w2, cudaStream_t stream);
+/* F.interpolate(mode="bilinear", align_corners=False) of NHWC bf16 images [nb, H, W, C] -> [nb, h2, w2, C] (C % 8 == 0).
+ * SEEM inference path without aux outputs: mask_features resized once per feature level so that the attention-mask logits
+ * of seem.py:569-574 (bilinear of einsum('bqc,bchw->bqhw')) become one small GEMM per layer (bilinear is linear). */
+int vb200_resize_bilinear_nhwc(const void* x, void* out, int64_t nb, int64_t H, int64_t W, int64_t C,
+                               int64_t h2, int64_t w2, cudaStream_t stream);
 
 /* out = softmax over the last dim of fp32 x [rows, n] (row stride ldx) -> bf16 [rows, n] (row stride ldo): the
  * single-head c-channel attention of the first-stage VAE's AttnBlock (i2vgen-xl tools/modules/autoencoder.py:418-442),

@@ -294,6 +294,12 @@ def seem_attn_mask(mask_logits, h2, w2):
     return m.to(torch.uint8)
 
 
+def resize_bilinear_nhwc(x, h2, w2):
+    """bf16 NHWC [nb, H, W, C] -> [nb, h2, w2, C], bilinear, align_corners=False."""
+    r = F.interpolate(x.float().permute(0, 3, 1, 2), size=(h2, w2), mode="bilinear", align_corners=False)
+    return r.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+
+
 def attention_short(q, k, v, scale=None, out=None):
     """q/k/v [nseq, S, H, D] or [outer, inner, S, H, D] strided views; attention over S per (sequence, head)."""
     D = q.shape[-1]
@@ -439,7 +445,7 @@ def install(monkeypatch):
     for name in ("gemm", "layernorm", "layernorm_add", "pack_dwconv_weight", "dwconv_nhwc", "colmean", "focal_modulate",
                  "mul_rows", "im2col_nchw", "pack_conv_weight", "conv_nhwc", "groupnorm_nhwc", "conv_nhwc_direct",
                  "upsample2x_nhwc", "softmax_rows", "preprocess_frames", "pack_glu_weight", "attention",
-                 "splice_multimodal", "add", "patchify", "vit_embed_ln", "seem_attn_mask", "attention_short",
+                 "splice_multimodal", "add", "patchify", "vit_embed_ln", "seem_attn_mask", "resize_bilinear_nhwc", "attention_short",
                  "cfg_combine", "rope_kv_append", "region_mask_pool", "add_rowgroup", "row_rstd", "rope_table", "attn_decode_rope",
                  "argmax_rows", "argmax_advance"):
         monkeypatch.setattr(ops, name, globals()[name])

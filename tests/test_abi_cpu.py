@@ -280,6 +280,18 @@ def test_seem_host_logic_against_reference_golden(monkeypatch):
         assert e_inf < 0.03 and e_l2 < 0.03, (k, e_inf, e_l2)
     e_inf, e_l2 = _rel(out["pred_masks"], fx["out"]["pred_masks"])
     assert e_l2 < 0.08, (e_inf, e_l2)
+    # inference mode (aux_outputs off): intermediate layers derive the attention masks from mask_features resized once per
+    # level (bilinear is linear); the final outputs must still match the reference, the intermediate masks the aux-on run
+    full_masks = out["attn_masks"]
+    head.predictor.aux_outputs = False
+    out2 = head.predictor(fx["multi_scale"], fx["mask_features"])
+    assert out2["aux_outputs"] == []
+    e_inf, e_l2 = _rel(out2["pred_masks"], fx["out"]["pred_masks"])
+    assert e_l2 < 0.08, (e_inf, e_l2)
+    e_inf, e_l2 = _rel(out2["pred_logits"], fx["out"]["pred_logits"])
+    assert e_l2 < 0.08, (e_inf, e_l2)
+    agree = [float((a == b).float().mean()) for a, b in zip(out2["attn_masks"], full_masks)]
+    assert min(agree) > 0.97, agree
 
 
 def test_unet_i2vgen_host_logic_against_reference_golden(monkeypatch):

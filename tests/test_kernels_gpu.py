@@ -586,6 +586,26 @@ def test_region_pool_and_seem_mask(cuda):
     refm = (r.sigmoid() < 0.5).flatten(1)
     refm[refm.sum(-1) == refm.shape[-1]] = False
     assert torch.equal(mk.bool(), refm)
+    mk_same = ops.seem_attn_mask(lg, 64, 64)   # same size: threshold + fully-masked-row reset only
+    refs = (lg < 0).flatten(1)
+    refs[refs.all(-1)] = False
+    assert torch.equal(mk_same.bool(), refs)
+
+
+@pytest.mark.parametrize("nb,H,W,C,h2,w2", [(1, 256, 256, 512, 32, 32), (1, 256, 256, 512, 128, 128), (2, 36, 52, 64, 9, 13),
+                                            (1, 37, 50, 128, 18, 26), (1, 16, 16, 8, 16, 16), (1, 10, 14, 64, 20, 28)])
+def test_resize_bilinear_nhwc(cuda, nb, H, W, C, h2, w2):
+    """F.interpolate(bilinear, align_corners=False) on NHWC bf16 (SEEM: mask_features resized once per level); also the
+    linearity the decoder relies on: resize(E . F) == E . resize(F)."""
+    from vitron_b200 import ops
+    x = rnd((nb, H, W, C), cuda, 1)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(h2, w2), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    close(ops.resize_bilinear_nhwc(x, h2, w2), ref, 1e-2, 8e-3, "bilinear resize")
+    e = rnd((5, C), cuda, 2).float()
+    full = torch.einsum("qc,nhwc->nqhw", e, x.float())
+    lhs = F.interpolate(full, size=(h2, w2), mode="bilinear", align_corners=False)
+    rhs = torch.einsum("qc,nhwc->nqhw", e, ref)
+    assert (lhs - rhs).abs().max() < 1e-3 * max(1.0, float(full.abs().max()))
 
 
 @pytest.mark.parametrize("M", [1, 8, 13, 16, 40, 300])

@@ -156,6 +156,30 @@ def test_seem_head_graph_replay_equals_eager(cuda):
     assert not torch.equal(outs[0], outs[1])
 
 
+def test_seem_inference_mode_without_aux_outputs(cuda):
+    """predictor.aux_outputs = False (what the reference's evaluate() needs): intermediate layers derive only the next
+    layer's attention mask, from mask_features resized once per level; final masks / logits / embeddings stay within
+    rounding of the aux-on run, the intermediate attention masks agree except for logits next to the threshold."""
+    in_ch, C, ffn, Q, heads, dim_proj = (32, 64, 64, 96), 128, 256, 16, 2, 64
+    sd, head = build(cuda, in_ch, C, ffn, Q, 1, 3, heads, dim_proj, 9)
+    g = torch.Generator().manual_seed(6)
+    sizes = [(64, 96), (32, 48), (16, 24), (8, 12)]
+    feats = {f"res{i + 2}": torch.randn((2, c, *sizes[i]), generator=g).to(cuda) for i, c in enumerate(in_ch)}
+    full = head(feats)
+    f_masks, f_emb, f_att = full["pred_masks"].clone(), full["pred_maskembs"].clone(), [m.clone() for m in full["attn_masks"]]
+    assert len(full["aux_outputs"]) == 3   # dec_layers of this test head
+    head.predictor.aux_outputs = False
+    fast = head(feats)
+    assert fast["aux_outputs"] == []
+    assert_close(fast["pred_masks"], f_masks, "pred_masks aux off vs on", 0.08, 0.06)
+    assert_close(fast["pred_maskembs"], f_emb, "pred_maskembs aux off vs on", 0.08, 0.06)
+    agree = [float((a == b).float().mean()) for a, b in zip(fast["attn_masks"], f_att)]
+    assert min(agree) > 0.97, agree
+    head.enable_graph(True)       # and under graph replay (folded position terms are cached tensors)
+    g1 = head(feats)
+    assert_close(g1["pred_masks"], f_masks, "graph, aux off", 0.08, 0.06)
+
+
 def test_seem_interactive_prompts_vs_reference_golden(cuda):
     """Grounding / audio token prompts, spatial point prompts and the refimg -> visual route on the B200 kernels against the
     golden outputs of the UNMODIFIED reference decoder (tests/golden/seem_prompts_tiny.pt): the self-attention over

@@ -72,6 +72,7 @@ SIGNATURES = {
     "vb200_cfg_combine": (_i32, [_p, _p, _p, _f, _i64, _p]),
     "vb200_region_mask_pool": (_i32, [_p, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "vb200_seem_attn_mask": (_i32, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p]),
+    "vb200_resize_bilinear_nhwc": (_i32, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p]),
     "vb200_softmax_rows": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "vb200_preprocess_frames": (_i32, [_p, _p] + [_i64] * 11 + [_p, _p, _i32, _i32, _i32, _p]),
     "vb200_im2col_nchw": (_i32, [_p, _i32, _p] + [_i64] * 10 + [_p]),

@@ -193,6 +193,43 @@ seem_mask_kernel(const float* __restrict__ logits, uint8_t* __restrict__ out, in
     for (int i = threadIdx.x; i < h2 * w2; i += blockDim.x) dst[i] = 0;
 }
 
+// Bilinear (align_corners=False, no antialias = F.interpolate) resize of NHWC bf16 images; one thread per (output pixel,
+// 8 channels). SEEM: the next layer's attention-mask logits are bilinear(mask_embed . mask_features) — bilinear resizing is
+// linear in the pixel axis, so resizing mask_features ONCE per level and multiplying the 101 mask embeddings with the small
+// map gives the same logits without materialising a [Q, 256, 256] fp32 map per layer.
+__global__ void __launch_bounds__(256)
+resize_bilinear_nhwc_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int nb, int H, int W, int C, int h2, int w2) {
+  const int vec = C >> 3;
+  const long long total = static_cast<long long>(nb) * h2 * w2 * vec;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = static_cast<int>(idx % vec);
+  long long r = idx / vec;
+  const int ox = static_cast<int>(r % w2); r /= w2;
+  const int oy = static_cast<int>(r % h2);
+  const long long n = r / h2;
+  const float sh = static_cast<float>(H) / h2, sw = static_cast<float>(W) / w2;
+  const float sy = fmaxf((oy + 0.5f) * sh - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * sw - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), H - 1), x0 = min(static_cast<int>(sx), W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const bf16* base = x + n * H * W * C + cv * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x0) * C);
+  const uint4 b = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x1) * C);
+  const uint4 c = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x0) * C);
+  const uint4 d = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x1) * C);
+  const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w}, cc[4] = {c.x, c.y, c.z, c.w}, dd[4] = {d.x, d.y, d.z, d.w};
+  uint32_t oo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fa = unpack_bf16(aa[j]), fb = unpack_bf16(bb[j]), fc = unpack_bf16(cc[j]), fd = unpack_bf16(dd[j]);
+    const float v0 = (1 - ly) * ((1 - lx) * fa.x + lx * fb.x) + ly * ((1 - lx) * fc.x + lx * fd.x);
+    const float v1 = (1 - ly) * ((1 - lx) * fa.y + lx * fb.y) + ly * ((1 - lx) * fc.y + lx * fd.y);
+    oo[j] = pack_bf16(v0, v1);
+  }
+  *reinterpret_cast<uint4*>(out + ((n * h2 + oy) * w2 + ox) * C + cv * 8) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+}
+
 // direct NHWC conv, one thread per (output pixel, output channel); only for tiny layers
 __global__ void conv_direct_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wt, const bf16* __restrict__ bias,
                                    bf16* __restrict__ out, int nb, int h, int w, int cin, int cout, int kh, int kw,
@@ -352,6 +389,16 @@ extern "C" int vb200_seem_attn_mask(const float* mask_logits, uint8_t* out_mask,
                                     int64_t h2, int64_t w2, cudaStream_t stream) {
   VB_CHECK_ARG(mask_logits && out_mask && Q > 0 && H > 0 && W > 0 && h2 > 0 && w2 > 0);
   seem_mask_kernel<<<static_cast<unsigned>(Q), 256, 0, stream>>>(mask_logits, out_mask, (int)H, (int)W, (int)h2, (int)w2);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+extern "C" int vb200_resize_bilinear_nhwc(const void* x, void* out, int64_t nb, int64_t H, int64_t W, int64_t C, int64_t h2,
+                                          int64_t w2, cudaStream_t stream) {
+  VB_CHECK_ARG(x && out && nb > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0 && h2 > 0 && w2 > 0);
+  const long long total = nb * h2 * w2 * (C / 8);
+  resize_bilinear_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), (int)nb, (int)H, (int)W, (int)C, (int)h2, (int)w2);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }

@@ -570,6 +570,18 @@ def seem_attn_mask(mask_logits, h2, w2):
     return out
 
 
+def resize_bilinear_nhwc(x, h2, w2):
+    """bf16 NHWC [nb, H, W, C] -> [nb, h2, w2, C], F.interpolate(bilinear, align_corners=False) semantics."""
+    lib = _lib.load()
+    _req(x.dim() == 4 and x.is_contiguous() and x.dtype == BF16 and x.shape[-1] % 8 == 0, "x: contiguous NHWC bf16, C % 8 == 0")
+    nb, H, W, C = x.shape
+    out = torch.empty((nb, h2, w2, C), dtype=BF16, device=x.device)
+    check(lib.vb200_resize_bilinear_nhwc(x.data_ptr(), out.data_ptr(), nb, H, W, C, int(h2), int(w2), _stream()),
+          "vb200_resize_bilinear_nhwc")
+    _launches[0] += 1
+    return out
+
+
 # ---- FocalNet backbone glue (focal.cu) ---------------------------------------------------------
 
 def im2col_nchw(pixels, k, stride, pad, ho, wo, kpad):

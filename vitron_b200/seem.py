@@ -83,8 +83,10 @@ class TransformerEncoderPixelDecoder:
         self.device = torch.device(device)
         self.maskformer_num_feature_levels = 3
         self._pos = {}
+        self._folded = {}   # per (layer, h, w): pos @ Wqk^T + b, the constant half of (src + pos) Wqk + b
 
     def load_state_dict(self, sd, prefix=""):
+        self._folded = {}
         dev = self.device
         g = lambda n: sd[prefix + n].detach().to(device=dev, dtype=BF16).contiguous()
         L = len(self.in_features)
@@ -131,10 +133,15 @@ class TransformerEncoderPixelDecoder:
             if idx == 0:
                 src = ops.gemm(x.view(n * h * w, cin), self.w["input_proj"][0], bias=self.w["input_proj"][1])
                 pos = self._pe(h, w)
-                for lw in self.w["enc"]:
+                for li, lw in enumerate(self.w["enc"]):
                     a = lw["att"]
-                    qk_in = ops.add(src, pos)
-                    qk = ops.gemm(qk_in, a.wqk, bias=a.bqk).view(n, h * w, 2, H, hd)
+                    if n == 1:   # (src + pos) Wqk + b = src Wqk + [pos Wqk + b]: constant per feature-map size
+                        key = ("enc", li, h, w)
+                        if key not in self._folded:
+                            self._folded[key] = ops.gemm(pos, a.wqk, bias=a.bqk).contiguous()
+                        qk = ops.gemm(src, a.wqk, rowbias=self._folded[key], rowbias_rows=1).view(n, h * w, 2, H, hd)
+                    else:
+                        qk = ops.gemm(ops.add(src, pos), a.wqk, bias=a.bqk).view(n, h * w, 2, H, hd)
                     v = ops.gemm(src, a.wv, bias=a.bv).view(n, h * w, H, hd)
                     att = ops.attention(qk[:, :, 0], qk[:, :, 1], v, scale=hd ** -0.5)
                     ops.gemm(att.view(n * h * w, C), a.wo, bias=a.bo, residual=src, out=src)
@@ -167,6 +174,12 @@ class MultiScaleMaskedTransformerDecoder:
         self.text_embeddings = None
         self.logit_scale = 0.0
         self._pos = {}
+        # aux_outputs=True (reference behaviour): every layer's full-resolution pred_masks / pred_logits are computed and
+        # returned under 'aux_outputs'. False (inference: the reference's evaluate() never reads them): intermediate layers
+        # only produce the NEXT layer's attention mask, from mask_features resized once per level (bilinear is linear, see
+        # vb200_resize_bilinear_nhwc) — no [Q, H, W] fp32 map, no class / caption logits for them; 'aux_outputs' is [].
+        self.aux_outputs = True
+        self._folded = {}
         # seem_focall_lang.yaml:60-86 enables MASK / SPATIAL / GROUNDING / VISUAL / AUDIO for the demo model
         self.task_switch = dict(mask=True, spatial=True, grounding=True, visual=True, audio=True)
         self.task_switch.update(task_switch or {})
@@ -180,6 +193,7 @@ class MultiScaleMaskedTransformerDecoder:
         self.logit_scale = float(logit_scale)
 
     def load_state_dict(self, sd, prefix=""):
+        self._folded = {}
         dev = self.device
         g = lambda n: sd[prefix + n].detach().to(device=dev, dtype=BF16).contiguous()
         L = self.num_layers
@@ -214,10 +228,21 @@ class MultiScaleMaskedTransformerDecoder:
             self._pos[(h, w)] = position_embedding_sine(h, w, self.hidden_dim // 2, self.device).to(BF16).contiguous()
         return self._pos[(h, w)]
 
-    def _heads(self, output, mask_rows, mask_hw, target_size, bs):
-        """forward_prediction_heads (seem.py:555-586). output [bs*Q, C] rows (batch-major)."""
+    def _heads(self, output, mask_rows, mask_hw, target_size, bs, small_rows=None):
+        """forward_prediction_heads (seem.py:555-586). output [bs*Q, C] rows (batch-major). small_rows (aux_outputs off,
+        intermediate layers): per-sample rows of mask_features already resized to target_size -> only the attention mask."""
         Q, C = self.num_queries, self.hidden_dim
         dec = ops.layernorm(output, *self.decoder_norm, 1e-5)
+        if small_rows is not None:
+            me = dec
+            for i, (w, b) in enumerate(self.mask_embed):
+                me = ops.gemm(me, w, bias=b, act=ops.ACT_RELU if i < 2 else ops.ACT_NONE)
+            h2, w2 = int(target_size[0]), int(target_size[1])
+            logits = torch.empty((bs, Q, h2 * w2), dtype=torch.float32, device=output.device)
+            for b in range(bs):
+                ops.gemm(me[b * Q:(b + 1) * Q], small_rows[b], out=logits[b], out_fp32=True)
+            attn_mask = ops.seem_attn_mask(logits.view(bs * Q, h2, w2), h2, w2)     # same size: threshold + row reset only
+            return dict(attn_mask=attn_mask.view(bs, 1, Q, -1))
         class_embed = ops.gemm(dec, self.class_embed_t)  # decoder_output @ class_embed
         outputs_class = None
         if self.text_embeddings is not None:
@@ -342,13 +367,30 @@ class MultiScaleMaskedTransformerDecoder:
             f = _nhwc(x[lvl].to(dev))
             n, h, w, c = f.shape
             size_list.append((h, w))
-            src = ops.add(f.view(n * h * w, c), self.level_embed[lvl].contiguous())
-            src_rows.append(src)
-            kin = ops.add(src, self._pe(h, w))
             ids, wk, bk = self.kgrp[lvl]
-            kall = ops.gemm(kin, wk, bias=bk).view(n, h * w, len(ids), H, hd)
             _, wv, bv = self.vgrp[lvl]
-            vall = ops.gemm(src, wv, bias=bv).view(n, h * w, len(ids), H, hd)
+            need_src = ("spatial_query_pos_mask" in extra or task == "refimg") and self.task_switch.get("spatial", False)
+            if n == 1 and not need_src:
+                # K = (f + level_embed + pos) Wk + bk = f Wk + [(level_embed + pos) Wk + bk]  (a per-row additive term that
+                # depends on the feature-map size only), V = (f + level_embed) Wv + bv = f Wv + [level_embed Wv + bv]:
+                # the two elementwise passes over the level's features disappear into the GEMM epilogues
+                key = ("kv", lvl, h, w)
+                if key not in self._folded:
+                    le = self.level_embed[lvl].contiguous()
+                    kb = ops.gemm(ops.add(self._pe(h, w), le), wk, bias=bk)                       # [h*w, len(ids)*C]
+                    vb = ops.gemm(le.view(1, -1).contiguous(), wv, bias=bv)[0].contiguous()                  # [len(ids)*C]
+                    self._folded[key] = (kb, vb)
+                kb, vb = self._folded[key]
+                frows = f.view(h * w, c)
+                src_rows.append(None)
+                kall = ops.gemm(frows, wk, rowbias=kb, rowbias_rows=1).view(n, h * w, len(ids), H, hd)
+                vall = ops.gemm(frows, wv, bias=vb).view(n, h * w, len(ids), H, hd)
+            else:
+                src = ops.add(f.view(n * h * w, c), self.level_embed[lvl].contiguous())
+                src_rows.append(src)
+                kin = ops.add(src, self._pe(h, w))
+                kall = ops.gemm(kin, wk, bias=bk).view(n, h * w, len(ids), H, hd)
+                vall = ops.gemm(src, wv, bias=bv).view(n, h * w, len(ids), H, hd)
             for j, i in enumerate(ids):
                 kproj[i], vproj[i] = kall[:, :, j], vall[:, :, j]
         mf = _nhwc(mask_features.to(dev))
@@ -379,19 +421,34 @@ class MultiScaleMaskedTransformerDecoder:
             visual_query_pos, visual_query_neg = extra["visual_query_pos"], extra["visual_query_neg"]
         has_prompts = bool(carried) or spatial_flag or visual_flag
 
-        results = [self._heads(output, mask_rows, mask_hw, size_list[0], bs)]
+        # aux_outputs off: mask_features resized once per level -> the intermediate heads need no full-resolution map
+        small = None
+        if not self.aux_outputs:
+            small = {}
+            for hw in set(size_list):
+                r = ops.resize_bilinear_nhwc(mf, hw[0], hw[1])
+                small[hw] = [r[b].view(-1, r.shape[-1]) for b in range(bs)]
+        head = lambda out_rows, j, last=False: self._heads(out_rows, mask_rows, mask_hw, size_list[j % self.num_feature_levels], bs,
+                                                           None if (small is None or last) else small[size_list[j % self.num_feature_levels]])
+        # (output + query_pos) W + b = output W + [query_pos W + b]: the constant term becomes a per-row bias of the GEMM
+        def qfold(name, i, w, b):
+            key = (name, i, bs)
+            if key not in self._folded:
+                self._folded[key] = ops.gemm(qpos, w, bias=b).contiguous()
+            return self._folded[key]
+        results = [head(output, 0)]
         for i in range(self.num_layers):
             lvl = i % self.num_feature_levels
             # masked cross attention (post-norm)
             a = self.cross[i]["att"]
-            q = ops.gemm(ops.add(output, qpos), a.wq, bias=a.bq).view(bs, Q, H, hd)
+            q = ops.gemm(output, a.wq, rowbias=qfold("cq", i, a.wq, a.bq), rowbias_rows=1).view(bs, Q, H, hd)
             att = ops.attention(q, kproj[i], vproj[i], scale=hd ** -0.5, mask=results[-1]["attn_mask"])
             ops.gemm(att.view(bs * Q, C), a.wo, bias=a.bo, residual=output, out=output)
             ops.layernorm(output, *self.cross[i]["n"], 1e-5, out=output)
             a = self.selfa[i]["att"]
             if not has_prompts:
                 # self attention among the object queries (mask all-False for task 'seg')
-                qk = ops.gemm(ops.add(output, qpos), a.wqk, bias=a.bqk).view(bs, Q, 2, H, hd)
+                qk = ops.gemm(output, a.wqk, rowbias=qfold("sqk", i, a.wqk, a.bqk), rowbias_rows=1).view(bs, Q, 2, H, hd)
                 v = ops.gemm(output, a.wv, bias=a.bv).view(bs, Q, H, hd)
                 att = ops.attention(qk[:, :, 0], qk[:, :, 1], v, scale=hd ** -0.5)
                 ops.gemm(att.view(bs * Q, C), a.wo, bias=a.bo, residual=output, out=output)
@@ -434,13 +491,13 @@ class MultiScaleMaskedTransformerDecoder:
                         if cg[0] == g_[0]:
                             cg[1] = X3[:, off:off + T].contiguous()
                     off += T
-            results.append(self._heads(output, mask_rows, mask_hw, size_list[(i + 1) % self.num_feature_levels], bs))
+            results.append(head(output, i + 1, last=(i == self.num_layers - 1)))
         # organize_output (attention_data_struct.py:250-264) for the object queries
         names = {"predictions_class": "pred_logits", "predictions_mask": "pred_masks", "predictions_maskemb": "pred_maskembs"}
         if grounding_flag or audio_flag:
             names["predictions_caption"] = "pred_captions"        # attention_data_struct.py:12-28 (queries_object slice)
         out = {v: results[-1][k] for k, v in names.items()}
-        out["aux_outputs"] = [{v: r[k] for k, v in names.items()} for r in results[:-1]]
+        out["aux_outputs"] = [{v: r[k] for k, v in names.items()} for r in results[:-1]] if self.aux_outputs else []
         extras_out = {}
         if spatial_flag:
             extras_out.update(pred_pspatials=spatial_query_pos.transpose(0, 1), pred_nspatials=spatial_query_neg.transpose(0, 1))
