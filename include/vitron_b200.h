@@ -86,6 +86,8 @@ int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
                     int64_t M, int64_t N, int64_t K, const vb_epilogue* epi, void* workspace,
                     size_t workspace_bytes, cudaStream_t stream);
 
+
+
 /* ---- implicit-GEMM convolution on NHWC activations, im2col-free (gemm_tcgen05.cu) ----------
  * X [nb,h,w,cin]; Wt [cout, kh*kw, ceil64(cin)] (zero padded); out [nb,ho,wo,cout].
  * Replaces nn.Conv2d 3x3/1x1 (i2vgen util.py:651,677; Upsample/Downsample util.py:579-607,

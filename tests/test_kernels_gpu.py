@@ -46,6 +46,8 @@ GEMM_SHAPES = [
     (4096, 32000, 128), (130, 8, 64), (300, 48, 128), (1000, 80, 320), (129, 2560, 64), (40960, 320, 320),
     # few tiles, long K: split-K on the v2 kernel
     (640, 1280, 3840), (200, 1280, 5120), (2560, 1280, 11520), (128, 256, 4096), (640, 336, 2048),
+    # 17..64 rows with a small weight matrix: persistent kernel with a mostly empty 128-row tile (not the swap-AB path)
+    (64, 512, 512), (33, 1024, 1024), (17, 512, 256), (60, 768, 768), (40, 2048, 512),
 ]
 
 

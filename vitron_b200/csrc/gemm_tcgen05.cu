@@ -847,11 +847,17 @@ extern "C" int vb200_set_gemm_impl(int impl) {
 int vb_launch_gemv(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int64_t M,
                    int64_t N, int64_t K, const vb_epilogue* e, cudaStream_t stream);  // gemv.cu
 
+// 17..64 rows: swap-AB + split-K (weights in the 128-row MMA slot, every SM streams a K slice) pays off only when the
+// weight matrix is large enough to be an HBM stream (LLM decode at batch 17..64: 33-180 MB per GEMM). For the small
+// matrices of the SEEM / GLIGEN token paths it measured 25.8 us per dependent GEMM (M = 64, N = K = 512) against 4.8 us on
+// the persistent kernel with a mostly empty 128-row tile (profiles/r02_smallm_chain_latency.jsonl).
+static bool use_swap(int64_t M, int64_t N, int64_t K) { return M <= 64 && N * K > (4ll << 20); }
+
 extern "C" size_t vb200_gemm_bf16_workspace_size(int64_t M, int64_t N, int64_t K) {
-  // M <= 16: weight-streaming kernel (gemv.cu), no workspace; 16 < M <= 64: swap-AB + split-K
+  // M <= 16: weight-streaming kernel (gemv.cu), no workspace; 16 < M <= 64 and a long weight stream: swap-AB + split-K
   if (M <= 16 || N <= 0 || K <= 0) return 0;
   // [tile counters | fp32 partials]; the caller zero-fills it ONCE, the kernels leave the counters zeroed
-  if (M <= 64)
+  if (use_swap(M, N, K))
     return GEMM_COUNTER_BYTES + static_cast<size_t>(swap_splits(M, N, K)) * static_cast<size_t>(M) *
                                     static_cast<size_t>(N) * sizeof(float);
   // M > 64: split-K only when the tile set cannot fill the SMs (plan_tiles)
@@ -870,7 +876,6 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   VB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   if (int r = validate_epi(epi, N)) return r;
   if (M <= 16) return vb_launch_gemv(A, lda, W, ldw, out, ldo, M, N, K, epi, stream);
-
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.num_k_blocks = static_cast<int>((K + BLOCK_K - 1) / BLOCK_K);
@@ -892,7 +897,7 @@ extern "C" int vb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
 
   CUtensorMap ta, tb;
   const uint32_t estr2[2] = {1, 1};
-  const bool swap = (M <= 64);  // small M: weights take the 128-row MMA slot
+  const bool swap = use_swap(M, N, K);  // small M, long weight stream: weights take the 128-row MMA slot
   if (swap) {
     // kernel-M = N (weight rows), kernel-N = M (tokens); partials -> workspace -> reduce kernel
     const int bn = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
