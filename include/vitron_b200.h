@@ -60,7 +60,10 @@ const char* vb200_last_error(void); /* text of the last CUDA error seen by this 
 int vb200_device_ok(void);          /* 1 iff the current device is sm_100 (B200) */
 /* Programmatic Dependent Launch for the decode-step kernels (gemv, decode attention, splice, rope table,
  * arg-max): when on, each of them is launched with programmaticStreamSerialization and overlaps its
- * prologue / weight prefetch with the tail of its predecessor. Returns the previous setting. */
+ * prologue / weight prefetch with the tail of its predecessor. Returns the previous setting.
+ * Contract while it is on: the weight operand W of an M <= 16 vb200_gemm_bf16 call (the weight-streaming kernel requests its
+ * first weight groups BEFORE the dependency wait) must be a constant, i.e. not written by kernels still in flight on the
+ * stream; activations used as W (attention-style products) belong on the M > 16 paths or in a PDL-off region. */
 int vb200_set_pdl(int enable);
 /* Attention kernel selection for vb200_attention: 0 = automatic (tcgen05/TMEM kernel for unmasked head_dim
  * 64/128 with >= 96 query rows, mma.sync otherwise), 1 = mma.sync only, 2 = tcgen05 whenever supported.
