@@ -178,6 +178,9 @@ int vb200_rope_kv_append(void* qkv, int64_t ld_qkv, const int32_t* positions,
                          void* v_pages, const int32_t* block_table, int64_t max_pages,
                          int64_t tokens, int64_t n_heads, int64_t head_dim, int64_t page_size,
                          float rope_theta, cudaStream_t stream);
+/* split-KV decode attention workspace: [16 KB of arrival counters (B * n_heads <= 4096) | per-split partials]; zero-filled
+ * ONCE by the caller. The counter prefix has a fixed size so that ONE buffer sized for the largest batch can serve calls
+ * (and captured graphs) of every smaller batch size in any order. */
 size_t vb200_attn_decode_workspace_size(int64_t B, int64_t n_heads, int64_t head_dim,
                                         int64_t max_splits);
 int vb200_attn_decode_paged(const void* q, int64_t ld_q, const void* k_pages, const void* v_pages,

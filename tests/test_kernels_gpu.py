@@ -525,6 +525,22 @@ def test_rope_kv_append_and_decode(cuda):
     o1 = ops.attn_decode_paged(qd, kp, vp, perm, torch.tensor([100, 64, 1], dtype=torch.int32, device=cuda), H, D, PS, 100)
     kk = out[:100, 1].unsqueeze(0).to(BF); vv = out[:100, 2].unsqueeze(0).to(BF)
     close(o1[0].view(H, D), sdpa_ref(qd[0, :H * D].view(1, 1, H, D), kk, vv, 1 / math.sqrt(D))[0, 0], 2e-2, 2e-2, "decode 1 split")
+    # ONE workspace, calls of different batch sizes / head counts in turn (what one engine's per-batch-size graphs do): the
+    # partial results a small call leaves behind must never be read as arrival counters by a larger one
+    for rep in range(2):
+        for bsub, hsub in ((1, 4), (3, 32), (2, 8), (3, 32)):
+            kvs = kvl[:bsub].contiguous()
+            qs = qd[:bsub].contiguous()
+            os_ = ops.attn_decode_paged(qs[:, :3 * hsub * D].contiguous(), kp[:, :hsub].contiguous(), vp[:, :hsub].contiguous(),
+                                        perm[:bsub].contiguous(), kvs, hsub, D, PS, max(lens))
+            off = 0
+            for b in range(bsub):
+                l = lens[b]
+                kk = out[off:off + l, 1, :hsub].unsqueeze(0).to(BF)
+                vv = out[off:off + l, 2, :hsub].unsqueeze(0).to(BF)
+                ref = sdpa_ref(qs[b, :hsub * D].view(1, 1, hsub, D), kk, vv, 1 / math.sqrt(D))
+                close(os_[b].view(hsub, D), ref[0, 0], 2e-2, 2e-2, f"decode attn shared workspace B={bsub} H={hsub} b={b} rep={rep}")
+                off += l
 
 
 def test_splice_argmax(cuda):

@@ -479,12 +479,17 @@ static int decode_splits(int64_t max_kv_len, int64_t bh) {
   return s;
 }
 
+// The arrival counters live in a FIXED-size prefix: the partial regions behind it move with (B, n_heads, splits), and a
+// workspace that serves calls of different batch sizes (one CUDA graph per batch size replays against the same buffer) must
+// never see a later call's counters where an earlier call left partial results (stale non-zero "counters" = a merge that
+// fires early or never).
+constexpr size_t DEC_COUNTER_BYTES = 16384;   // B * n_heads <= 4096
+
 extern "C" size_t vb200_attn_decode_workspace_size(int64_t B, int64_t n_heads, int64_t head_dim,
                                                    int64_t max_splits) {
-  // [B*H arrival counters | (m, l) per split | unnormalised o per split]; zero-fill ONCE before first use
+  // [arrival counters: 16 KB | (m, l) per split | unnormalised o per split]; zero-fill ONCE before first use
   if (max_splits < 1) max_splits = 32;
-  return static_cast<size_t>(B) * n_heads * sizeof(int) +
-         static_cast<size_t>(B) * n_heads * max_splits * (head_dim + 2) * sizeof(float);
+  return DEC_COUNTER_BYTES + static_cast<size_t>(B) * n_heads * max_splits * (head_dim + 2) * sizeof(float);
 }
 
 static int launch_attn_decode(const void* q, int64_t ld_q, void* k_pages, void* v_pages,
@@ -507,8 +512,9 @@ static int launch_attn_decode(const void* q, int64_t ld_q, void* k_pages, void* 
   if (splits > 1) {
     size_t need = vb200_attn_decode_workspace_size(B, n_heads, head_dim, splits);
     if (!workspace || workspace_bytes < need) return VB_ERR_WORKSPACE;
+    if (static_cast<size_t>(B) * n_heads * sizeof(int) > DEC_COUNTER_BYTES) return VB_ERR_UNSUPPORTED;
     counters = reinterpret_cast<int*>(workspace);
-    ws_ml = reinterpret_cast<float*>(counters + B * n_heads);
+    ws_ml = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + DEC_COUNTER_BYTES);
     ws_o = ws_ml + static_cast<size_t>(B) * n_heads * splits * 2;
   }
   dim3 grid(splits, static_cast<unsigned>(n_heads), static_cast<unsigned>(B));
