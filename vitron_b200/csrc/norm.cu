@@ -5,6 +5,7 @@
 //   groupnorm : nn.GroupNorm(32, C) (+SiLU) of ResBlock / TemporalConvBlock_v2 / transformers
 //               (i2vgen util.py:640-655, 1358-1375, 1014) on NHWC [n, spatial, c] tensors
 #include "common.cuh"
+#include <cstdio>
 #include "vitron_b200.h"
 
 namespace vb {
@@ -571,15 +572,23 @@ template <int ACT, bool CACHED>
 static int gn_launch(const bf16* x, const bf16* w, const bf16* b, bf16* out, GnWs ws, int spatial, int c, int groups, int rpc,
                      int rpp, float eps, dim3 grid, int threads, size_t smem, cudaStream_t stream) {
   auto kern = gn_onepass_kernel<ACT, CACHED>;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    // 227 KB per CTA minus the kernel's static shared memory (gsum + flags: 5 KB)
+  static bool attr_set = false;
+  if (!attr_set) {
+    // opt in once per instantiation, whatever the first launch needs: the default limit of 48 KB counts the kernel's 4 KB of
+    // STATIC shared memory too (a first launch with exactly 48 KB of dynamic smem failed with "invalid argument").
+    // 227 KB per CTA minus the static part (gsum + flags: 5 KB)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_DYN_SMEM_MAX);
     if (e != cudaSuccess) { vb_set_last_error(e); return VB_ERR_CUDA; }
-    smem_set = GN_DYN_SMEM_MAX;
+    attr_set = true;
   }
   cudaError_t le = vb_launch(kern, grid, dim3(threads), smem, stream, x, w, b, out, ws, spatial, c, groups, rpc, rpp, eps);
-  if (le != cudaSuccess) { vb_set_last_error(le); return VB_ERR_CUDA; }
+  if (le != cudaSuccess) {
+    fprintf(stderr, "vb200_groupnorm_nhwc launch failed (%s): grid (%u, %u) threads %d smem %zu cached %d spatial %d c %d groups %d rpc %d rpp %d\n",
+            cudaGetErrorString(le), grid.x, grid.y, threads, smem, CACHED ? 1 : 0, spatial, c, groups, rpc, rpp);
+    (void)cudaGetLastError();   // the failed launch must not be reported again by the next kernel's check
+    vb_set_last_error(le);
+    return VB_ERR_CUDA;
+  }
   return VB_OK;
 }
 

@@ -378,6 +378,7 @@ extern "C" int vb200_cfg_combine(const void* y, const void* u, void* out, float 
 extern "C" int vb200_region_mask_pool(const void* feats, const float* boxes, void* out, int64_t B, int64_t grid,
                                       int64_t c, int64_t image_size, cudaStream_t stream) {
   VB_CHECK_ARG(feats && boxes && out && B > 0 && grid > 0 && c > 0 && image_size > 0);
+  VB_CHECK_ARG(grid * grid * sizeof(float) <= 40 * 1024);   // cell weights live in (default-limit) dynamic shared memory
   dim3 g(static_cast<unsigned>((c + 255) / 256), static_cast<unsigned>(B));
   region_pool_kernel<<<g, 256, grid * grid * sizeof(float), stream>>>(
       reinterpret_cast<const bf16*>(feats), boxes, reinterpret_cast<bf16*>(out), (int)grid, (int)c, (int)image_size);
