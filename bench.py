@@ -323,7 +323,7 @@ def run_profile():
 UNET_CFG = dict(in_dim=4, concat_dim=4, dim=320, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
                 head_dim=64, num_res_blocks=2, attn_scales=[1.0, 0.5, 0.25], num_tokens=4)
 UNET_TFLOP_PER_FORWARD = 12.67  # algorithmic FLOPs of the reference class at f=16, 40x64 latent
-UNET_METRIC = "i2vgen-xl UNet3D DDIM steps/s (2 UNet forwards + CFG per step), latent [1,4,16,40,64] = 16 frames of 320x512 px"
+UNET_METRIC = "i2vgen-xl UNet3D DDIM steps/s (conditional + unconditional UNet evaluation + CFG per step), latent [1,4,16,40,64] = 16 frames of 320x512 px"
 UNET_LATENT = (1, 4, 16, 40, 64)
 
 
@@ -337,11 +337,12 @@ def _unet_inputs(device, seed=4):
     return noise, cond, unc
 
 
-def unet_gemm_roofline(unet, noise, cond, tf_peak, peak_kind):
+def unet_gemm_roofline(unet, noise, cond, tf_peak, peak_kind, t_steps=None):
     """Dominant kernel family of a UNet forward = the tcgen05 GEMM / implicit-GEMM conv kernel (gemm_v2_kernel<BN,...>,
     ~70 % of the forward). Every ops.gemm / ops.conv_nhwc call of ONE forward is recorded with its live operands, then
     exactly those calls are replayed back to back from a CUDA graph and timed with CUDA events: achieved = their
-    algorithmic FLOPs (2*M*N*K, conv 2*pixels*cout*cin*taps) / that time."""
+    algorithmic FLOPs (2*M*N*K, conv 2*pixels*cout*cin*taps) / that time. `noise` / `cond` are what the timed step feeds the
+    UNet: the batch-2 [cond | uncond] tensors of the graphed CFG denoiser."""
     from vitron_b200 import ops
     calls = []
     real_gemm, real_conv = ops.gemm, ops.conv_nhwc
@@ -365,7 +366,7 @@ def unet_gemm_roofline(unet, noise, cond, tf_peak, peak_kind):
     ops.gemm, ops.conv_nhwc = rec_gemm, rec_conv
     import vitron_b200.unet_i2vgen as U
     try:
-        unet(noise, torch.tensor([981], device=noise.device), **cond)
+        unet(noise, torch.full((noise.shape[0],), 981, dtype=torch.long, device=noise.device), **cond)
     finally:
         ops.gemm, ops.conv_nhwc = real_gemm, real_conv
     torch.cuda.synchronize()
@@ -425,7 +426,8 @@ def unet_cpu_baseline():
 
 def bench_unet(device, tf_peak, peak_kind, steps=10, rank=0, world=1, with_cpu=True):
     """Second half of BASELINE.json's metric: i2vgen-xl UNet3D denoise steps/s (configs[4] at the primary latent reading
-    16 x (40x64) = 320x512 px; DDIM step = 2 UNet forwards with classifier-free guidance 9.0 + the v-prediction update),
+    16 x (40x64) = 320x512 px; DDIM step = the conditional and the unconditional UNet evaluation of classifier-free guidance 9.0
+    — run as ONE batch-2 forward [cond | uncond], GraphedCFGDenoiser — + the v-prediction update),
     bf16, random-init 1.42 B-parameter UNetSD_I2VGen, CUDA-graphed.
     N = 1: one request. N > 1: `value` = N independent requests (replicas, no collective); `cfg_split` =
     the cond / uncond branches of ONE request on a GPU pair, one NCCL all_gather of the two [1,4,16,40,64] fp32 branch
@@ -477,6 +479,7 @@ def bench_unet(device, tf_peak, peak_kind, steps=10, rank=0, world=1, with_cpu=T
            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
            "config": {"workload": "BASELINE.json configs[4], primary latent reading [1,4,16,40,64]; DDIM-50 schedule, guide 9.0",
                       "parallelism": f"{world} request replica(s)", "requests_in_flight": world,
+                      "cfg_evaluation": "one batch-2 forward [cond | uncond]" if den.batched else "two batch-1 forwards",
                       "l2": "2.8 GB of weights + ~0.6 GB of activations streamed per forward (> 126 MB L2)"},
            "latent": list(UNET_LATENT), "guide_scale": 9.0, "gpu_launches": launches,
            "achieved_tflops_per_gpu": tfs, "frac_of_bf16_peak": tfs / tf_peak, "finite": finite,
@@ -498,7 +501,11 @@ def bench_unet(device, tf_peak, peak_kind, steps=10, rank=0, world=1, with_cpu=T
         nb = x_pin.numel() * 4
         out["e2e"] = {"value": 1000.0 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": nb,
                       "d2h_bytes_per_step": nb, "input": "x_t fp32 [1,4,16,40,64] from pinned host memory, x_{t-1} read back"}
-        out["roofline"] = unet_gemm_roofline(unet, noise, cond, tf_peak, peak_kind)
+        if den.batched:   # the forward the timed step runs: ONE batch-2 evaluation [cond | uncond]
+            out["roofline"] = unet_gemm_roofline(unet, den.xt2, den.both, tf_peak, peak_kind)
+            out["roofline"]["forward"] = "batch-2 [cond | uncond] (one CFG evaluation)"
+        else:
+            out["roofline"] = unet_gemm_roofline(unet, noise, cond, tf_peak, peak_kind)
         if with_cpu:
             out["cpu_baseline"] = unet_cpu_baseline()
     elif world % 2 == 0:
