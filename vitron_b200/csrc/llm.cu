@@ -114,7 +114,7 @@ __global__ void rope_table_kernel(const int32_t* __restrict__ positions, float* 
 }
 
 template <bool ROPE, int MAX_TRIPS>
-__global__ void __launch_bounds__(DEC_THREADS)
+__global__ void __launch_bounds__(DEC_THREADS, 4)   // 4 CTAs per SM: the one-wave split policy counts on 4 x 148 slots
 attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict__ k_pages,
                    bf16* __restrict__ v_pages, const int32_t* __restrict__ block_table, int max_pages,
                    const int32_t* __restrict__ kv_len, int H, int page_size, float scale, int splits, int per,
@@ -199,31 +199,32 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
   const long long head_off = static_cast<long long>(h) * page_size * HD + sub * 16;
   const long long page_stride = static_cast<long long>(H) * page_size * HD;
 
-  // 16 lane groups per CTA; trip i covers page pg[i] = keys c0 + 64 i .. + 63: lane group gid takes the keys
-  // gid + 16 u (u < 4) of the page and issues all 16 K/V loads (256 B per lane) before the first dot product.
+  // 16 lane groups per CTA. The split is walked in HALF pages of 32 keys: lane group gid takes the keys gid and gid + 16 of
+  // the half (2 K rows + 2 V rows = 128 B per lane) and the loop is software pipelined over two register buffers — the
+  // loads of half h + 1 are issued BEFORE the dot products / softmax / PV of half h, so every warp has loads in flight all
+  // the time (ncu of the one-buffer version: 4.7 long-scoreboard stall cycles per issued instruction, issue slots 33 % busy,
+  // DRAM traffic = algorithmic: the kernel waited, it did not waste). Same register footprint as 4 keys per 64-key trip.
   const int gid = warp * 4 + grp;
+  struct Half { uint4 k[2][2], v[2][2]; };
+  const int nh = c1 > c0 ? (c1 - c0 + 31) / 32 : 0;   // halves this split holds (warp-uniform)
+  auto load_half = [&](int hs, Half& h) {
+    const long long pbase = static_cast<long long>(pg[hs >> 1]) * page_stride + head_off;
 #pragma unroll
-  for (int i = 0; i < MAX_TRIPS; ++i) {
-    const int tb = c0 + 64 * i;
-    if (tb >= c1) break;  // warp-uniform (shuffles below use the full mask)
-    const long long pbase = static_cast<long long>(pg[i]) * page_stride + head_off;
-    uint4 kq[4][2], vq[4][2];
-    bool has[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int kk = gid + 16 * u;  // key inside the page
-      has[u] = tb + kk < c1;
-      const long long off = pbase + static_cast<long long>(has[u] ? kk : 0) * HD;
-      kq[u][0] = *reinterpret_cast<const uint4*>(k_pages + off);
-      kq[u][1] = *reinterpret_cast<const uint4*>(k_pages + off + 8);
-      vq[u][0] = *reinterpret_cast<const uint4*>(v_pages + off);
-      vq[u][1] = *reinterpret_cast<const uint4*>(v_pages + off + 8);
+    for (int u = 0; u < 2; ++u) {
+      const int kk = gid + 16 * u + 32 * (hs & 1);  // key inside the page
+      const bool has = c0 + 64 * (hs >> 1) + kk < c1;
+      const long long off = pbase + static_cast<long long>(has ? kk : 0) * HD;
+      h.k[u][0] = *reinterpret_cast<const uint4*>(k_pages + off);
+      h.k[u][1] = *reinterpret_cast<const uint4*>(k_pages + off + 8);
+      h.v[u][0] = *reinterpret_cast<const uint4*>(v_pages + off);
+      h.v[u][1] = *reinterpret_cast<const uint4*>(v_pages + off + 8);
     }
-    if (i + 2 < MAX_TRIPS && tb + 128 < c1) prefetch_page(pg[i + 2]);   // two trips ahead -> L2, behind this trip's loads
-    float sc[4];
+  };
+  auto compute_half = [&](int hs, const Half& h) {
+    float sc[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t kw[8] = {kq[u][0].x, kq[u][0].y, kq[u][0].z, kq[u][0].w, kq[u][1].x, kq[u][1].y, kq[u][1].z, kq[u][1].w};
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t kw[8] = {h.k[u][0].x, h.k[u][0].y, h.k[u][0].z, h.k[u][0].w, h.k[u][1].x, h.k[u][1].y, h.k[u][1].z, h.k[u][1].w};
       float a = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -235,27 +236,28 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
 #pragma unroll
     for (int sh = 1; sh < 8; sh <<= 1) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], sh);
+      for (int u = 0; u < 2; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], sh);
     }
     float mn = m;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (!has[u]) sc[u] = -INFINITY;
+    for (int u = 0; u < 2; ++u) {
+      const bool has = c0 + 64 * (hs >> 1) + gid + 16 * u + 32 * (hs & 1) < c1;
+      if (!has) sc[u] = -INFINITY;
       mn = fmaxf(mn, sc[u]);
     }
     const float msafe = (mn == -INFINITY) ? 0.f : mn;
     const float corr = __expf(m - msafe);  // m = -inf on first use -> 0
-    float pr[4];
+    float pr[2];
     float psum = 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { pr[u] = __expf(sc[u] - msafe); psum += pr[u]; }
+    for (int u = 0; u < 2; ++u) { pr[u] = __expf(sc[u] - msafe); psum += pr[u]; }
     l = l * corr + psum;
     m = mn;
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] *= corr;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t vw[8] = {vq[u][0].x, vq[u][0].y, vq[u][0].z, vq[u][0].w, vq[u][1].x, vq[u][1].y, vq[u][1].z, vq[u][1].w};
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t vw[8] = {h.v[u][0].x, h.v[u][0].y, h.v[u][0].z, h.v[u][0].w, h.v[u][1].x, h.v[u][1].y, h.v[u][1].z, h.v[u][1].w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float2 f = unpack_bf16(vw[j]);
@@ -263,6 +265,18 @@ attn_decode_kernel(const bf16* __restrict__ q, long long ld_q, bf16* __restrict_
         o[2 * j + 1] += pr[u] * f.y;
       }
     }
+  };
+  Half buf0, buf1;
+  if (nh > 0) load_half(0, buf0);
+#pragma unroll
+  for (int hs = 0; hs < 2 * MAX_TRIPS; hs += 2) {   // one iteration = one 64-key page
+    if (hs >= nh) break;                            // warp-uniform (the shuffles use the full mask)
+    if (hs + 1 < nh) load_half(hs + 1, buf1);
+    if ((hs >> 1) + 2 < MAX_TRIPS && c0 + 64 * ((hs >> 1) + 2) < c1) prefetch_page(pg[(hs >> 1) + 2]);   // two pages ahead -> L2
+    compute_half(hs, buf0);
+    if (hs + 1 >= nh) break;
+    if (hs + 2 < nh && hs + 2 < 2 * MAX_TRIPS) load_half(hs + 2, buf0);
+    compute_half(hs + 1, buf1);
   }
 
   // ---- merge the 16 lane groups
