@@ -20,9 +20,10 @@ with torch.no_grad():
     unet.load_state_dict(PS.random_state_dict(PS.unet_shapes(bench.UNET_CFG), dev, seed=4))
     g = torch.Generator(device=dev).manual_seed(4)
     rn = lambda *s: torch.randn(s, generator=g, device=dev)
-    x, local = rn(1, 4, 16, 40, 64), rn(1, 4, 16, 40, 64)
-    kw = dict(y=rn(1, 77, 1024), image=rn(1, 1, 1024), local_image=local, fps=torch.tensor([16], device=dev))
-    t = torch.tensor([981], device=dev)
+    nb = 2 if "b2" in sys.argv else 1   # b2: the batch-2 [cond | uncond] forward of the graphed CFG denoiser
+    x, local = rn(nb, 4, 16, 40, 64), rn(nb, 4, 16, 40, 64)
+    kw = dict(y=rn(nb, 77, 1024), image=rn(nb, 1, 1024), local_image=local, fps=torch.tensor([16] * nb, device=dev))
+    t = torch.tensor([981] * nb, device=dev)
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
