@@ -291,7 +291,7 @@ def test_norms(cuda, rows, d):
     close(ops.layernorm(x, w, b, 1e-5), F.layer_norm(xf, (d,), w.float(), b.float(), 1e-5), 2e-2, 1e-2, "layernorm")
 
 
-@pytest.mark.parametrize("n,sp,c,act", [(8, 128, 64, 4), (8, 128, 64, 0), (8, 128, 64, 3), (16, 40 * 64, 320, 4), (2, 16 * 100, 640, 0), (3, 77, 1280, 4), (1, 64 * 64, 512, 3),
+@pytest.mark.parametrize("n,sp,c,act", [(2, 40960, 320, 4), (32, 2560, 320, 0), (3, 40960, 320, 4), (32, 2560, 640, 4), (8, 128, 64, 4), (8, 128, 64, 0), (8, 128, 64, 3), (16, 40 * 64, 320, 4), (2, 16 * 100, 640, 0), (3, 77, 1280, 4), (1, 64 * 64, 512, 3),
                                         (2, 50, 2560, 4), (2, 33, 960, 4),
                                         (1, 16 * 2560, 320, 4), (1, 16 * 640, 640, 4), (2, 5000, 1920, 0),
                                         # UNet temporal layouts
