@@ -312,6 +312,51 @@ def test_unet_i2vgen_host_logic_against_reference_golden(monkeypatch):
     assert out.shape == fx["out"].shape and e_inf < 0.05 and e_l2 < 0.04, (e_inf, e_l2)
 
 
+def test_cfg_denoiser_batched_equals_two_calls_and_rebind(monkeypatch):
+    """Host logic of GraphedCFGDenoiser without a GPU (its _eval, i.e. what the CUDA graph captures, on the CPU emulator): the
+    ONE batch-2 forward [cond | uncond] gives the same guidance result as the reference's two UNet calls
+    (diffusion_ddim.py:153-158), mismatching conditioning dicts fall back to the two-call form, and rebind() refreshes the
+    batched static tensors of both branches."""
+    import os
+    import torch
+    from oracle.weights import seeded_state_dict
+    from tests import cpu_ops_emulator
+    from vitron_b200.unet_i2vgen import GraphedCFGDenoiser, UNetSD_I2VGen
+    cpu_ops_emulator.install(monkeypatch)
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "unet_tiny.pt"), weights_only=False)
+    m = UNetSD_I2VGen(**fx["cfg"], device="cpu")
+    m.load_state_dict(seeded_state_dict(fx["shapes"], fx["seed"], fx["gain"]))
+    i = fx["inputs"]
+    pick = lambda j: dict(y=i["y"][j:j + 1].clone(), image=i["image"][j:j + 1].clone(), local_image=i["local_image"][:1].clone(),
+                          fps=i["fps"][:1].clone())
+    cond, unc = pick(0), pick(1)
+    xt, t = i["x"][:1].float(), i["t"][:1]
+    two = GraphedCFGDenoiser(m, cond, unc, 7.5, xt, t, batched=False)
+    one = GraphedCFGDenoiser(m, cond, unc, 7.5, xt, t)
+    assert one.batched and not two.batched
+    ref, got = two._eval().float(), one._eval().float()
+    assert got.shape == ref.shape == xt.shape
+    # guidance amplifies the bf16-level differences between a batch-1 and a batch-2 evaluation of the same sample by (1 + 2 s)
+    y_sep, u_sep = m(xt, t, **cond).float(), m(xt, t, **unc).float()
+    yu = m(one.xt2, one.t2, **one.both).float()
+    branch_scale = float(torch.maximum(y_sep.abs().max(), u_sep.abs().max()))
+    assert (yu[:1] - y_sep).abs().max() <= 1e-2 * branch_scale and (yu[1:] - u_sep).abs().max() <= 1e-2 * branch_scale
+    tol = 1e-2 * branch_scale * (1 + 2 * 7.5)
+    assert (got - ref).abs().max() <= tol, (float((got - ref).abs().max()), tol)
+    assert (got - (yu[1:] + 7.5 * (yu[:1] - yu[1:]))).abs().max() <= 2e-2 * got.abs().max() + 1e-3
+    # a branch without the image embedding cannot be batched with one that has it
+    unc_none = dict(unc, image=None)
+    assert not GraphedCFGDenoiser(m, cond, unc_none, 7.5, xt, t).batched
+    # rebind: new conditioning values reach the batched static tensors (cond rows first, uncond rows second)
+    new_c = {k: (v + 0.25 if v.is_floating_point() else v) for k, v in cond.items()}
+    new_u = {k: (v - 0.25 if v.is_floating_point() else v) for k, v in unc.items()}
+    one.rebind(new_c, new_u)
+    assert torch.equal(one.both["y"][:1], new_c["y"]) and torch.equal(one.both["y"][1:], new_u["y"])
+    fresh = GraphedCFGDenoiser(m, new_c, new_u, 7.5, xt, t, batched=False)._eval().float()
+    again = one._eval().float()
+    assert (again - fresh).abs().max() <= tol, float((again - fresh).abs().max())
+
+
 def test_gligen_block_host_logic_against_reference_golden(monkeypatch):
     """Host side of vitron_b200.gligen (concat-free gated self-attention over [visual ; grounding] rows, packed GEGLU
     weights, tanh-gated residual epilogues) with the kernels replaced by torch statements, against the golden outputs of
