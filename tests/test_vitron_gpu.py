@@ -66,12 +66,17 @@ def test_multimodal_logits_vs_reference_golden(cuda, golden):
 
 
 def _check_tokens(got, ref, gaps, tol):
-    """identical until the first step whose oracle margin is inside the tolerance."""
+    """identical until the first step whose oracle margin is inside the tolerance; returns how many tokens were compared (the
+    callers assert a minimum: on these tiny random models the margins are small, so the count is what the oracle allows — the
+    teacher-forced 7B test in test_fullsize_gpu.py compares every decode position)."""
+    compared = 0
     for b in range(ref.shape[0]):
         for t in range(ref.shape[1]):
             if gaps[b, t] <= tol:
                 break
             assert int(got[b, t]) == int(ref[b, t]), f"token mismatch b={b} t={t}: {got[b].tolist()} vs {ref[b].tolist()} (margin {gaps[b, t]:.3f})"
+            compared += 1
+    return compared
 
 
 def test_greedy_generate_vs_reference_golden(cuda, golden):
@@ -90,7 +95,7 @@ def test_greedy_generate_vs_reference_golden(cuda, golden):
         got = out[:, g["input_ids"].shape[1]:].cpu()
         assert got.shape == g["tokens"].shape
         scale = 0.04 * fx[("img" if key == "gen_img" else "vid")]["logits"].abs().max().item()
-        _check_tokens(got, g["tokens"], gaps, 2 * scale)
+        assert _check_tokens(got, g["tokens"], gaps, 2 * scale) >= (2 if key == "gen_img" else 1)   # oracle-decisive prefix of this fixture
 
 
 def test_midsize_vs_oracle(cuda):
@@ -154,7 +159,7 @@ def test_midsize_vs_oracle(cuda):
     for use_graph_chunk in (16, 3):
         got = m.generate(ids.to(cuda), attention_mask=am.to(cuda), images=[i.to(cuda) for i in imgs], regions=regions,
                          do_sample=False, max_new_tokens=n_new, eos_token_id=-1, sync_every=use_graph_chunk)
-        _check_tokens(got[:, L:].cpu(), otoks, gaps, tol)
+        assert _check_tokens(got[:, L:].cpu(), otoks, gaps, tol) >= 2   # sample 2's first two steps are oracle-decisive
     # eos handling: force eos = first generated token of sample 0 -> that row is padded afterwards
     eos = int(otoks[0, 0])
     got = m.generate(ids.to(cuda), attention_mask=am.to(cuda), images=[i.to(cuda) for i in imgs], regions=regions,
