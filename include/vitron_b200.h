@@ -108,9 +108,11 @@ int vb200_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int64_t nb, i
 /* 0 = the compile-time-specialised kernel (gemm_v2) whenever the operands allow its 256-bit epilogue accesses
  * (default), 1 = the generic kernel only. Returns the previous setting. For A/B measurements and parity tests. */
 int vb200_set_gemm_impl(int impl);
-/* Measurement aids of the v2 kernel: resident_b 0 / 1 switches the small-K "weight slab stays in shared memory" variant
- * (default 1), dbg bit 0 makes the epilogue skip its work (wrong results: timing of the main loop alone). -1 keeps a
- * setting. Returns the previous (resident_b | dbg << 8). */
+/* Variant switches / measurement aids of the v2 kernel. `resident_b` is a bit set (default 1): bit 0 = the "weight slab stays
+ * in shared memory" variant for K <= 320, bit 1 = also for K <= 640, bit 2 = force the CTA-pair (tcgen05 cta_group::2) variant
+ * wherever it applies (default: K >= 2048 only), bit 3 = never use it. `dbg`: bit 0 makes the epilogue skip its work, bit 1
+ * only its global stores (wrong results: timing of the main loop / of the epilogue math alone). -1 keeps a setting.
+ * Returns the previous (resident_b | dbg << 8). */
 int vb200_set_gemm_debug(int resident_b, int dbg);
 
 /* direct (SIMT) convolution for the two odd-shaped layers (cin < 8-aligned or tiny cout) */
